@@ -1,0 +1,230 @@
+/*
+ * pcdb200.h — C-ABI boundary of the B200-native classification hot path of
+ * point-cloud-donkey (SHOT/CSHOT at voxel-grid keypoints -> kNN codebook
+ * activation -> Hough vote casting -> mean-shift maxima).
+ *
+ * The reference (vseib/point-cloud-donkey) has no FFI: its plug-in surface is
+ * C++ virtual hooks behind string-keyed factories.  Every entry point below
+ * names the reference hook it replaces (file:line under
+ * src/implicit_shape_model/ unless stated otherwise).  The host-side C++ shim
+ * (point-cloud-donkey_b200/host) wraps these behind the reference's own class
+ * names; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature
+ *   - all pointers are HOST memory unless the name ends in `_d` (device)
+ *   - clouds are concatenated; `*_off` arrays have B+1 int64 entries
+ *   - every function returns PCDB_OK (0) or a negative pcdb_status; the text
+ *     of the last failure is kept per context (pcdb_last_error)
+ *   - there is NO CPU fallback: without a usable sm_100 device pcdb_create
+ *     fails with PCDB_E_NO_DEVICE
+ */
+#ifndef PCDB200_H_
+#define PCDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCDB_ABI_VERSION 1
+
+typedef enum pcdb_status {
+  PCDB_OK = 0,
+  PCDB_E_INVALID = -1,     /* bad argument / bad parameter (ism3d::BadParamException) */
+  PCDB_E_NO_DEVICE = -2,   /* no CUDA device / not sm_100 */
+  PCDB_E_CUDA = -3,        /* CUDA runtime failure (text in pcdb_last_error) */
+  PCDB_E_CAPACITY = -4,    /* caller-provided output buffer too small */
+  PCDB_E_STATE = -5,       /* call order (e.g. classify before set_codebook) */
+  PCDB_E_UNSUPPORTED = -6, /* a reference option outside the built hot path */
+  PCDB_E_COMM = -7         /* multi-GPU exchange failed */
+} pcdb_status;
+
+enum { PCDB_FEATURE_SHOT = 0, PCDB_FEATURE_CSHOT = 1 };           /* features_factory.h:54,62 */
+enum { PCDB_DIST_EUCLIDEAN = 0, PCDB_DIST_CHISQUARED = 1 };       /* utils/distance.h:42-75 (squared L2 / chi^2) */
+enum { PCDB_KERNEL_GAUSSIAN = 0, PCDB_KERNEL_UNIFORM = 1 };       /* voting_mean_shift.cpp:378-417 */
+enum { PCDB_SUPPRESS_AVERAGE = 0, PCDB_SUPPRESS_SUPPRESS = 1 };   /* voting_mean_shift.cpp:98-122 */
+enum { PCDB_KNN_AUTO = 0, PCDB_KNN_SCAN = 1, PCDB_KNN_GEMM = 2 }; /* which exact-kNN kernel family */
+
+#define PCDB_SHOT_DIM 352
+#define PCDB_CSHOT_DIM 1344
+#define PCDB_MAX_K 16
+
+/* Hot-path parameters; names and defaults follow the reference's JSON keys
+ * (SURVEY.md App. C).  Filled by the host shim from the .ism file. */
+typedef struct pcdb_params {
+  /* Features (features_shot.cpp:21, features.cpp:32-33) */
+  int32_t feature_type;   /* PCDB_FEATURE_*; Features.Type */
+  double feature_radius;  /* Features.Radius (double member, features_shot.h:43) */
+  double lrf_radius;      /* Features.ReferenceFrameRadius: the float member promoted to double */
+  /* Keypoints (keypoints_voxel_grid.cpp:23) */
+  float leaf_size;        /* Keypoints.LeafSize */
+  /* Activation (activation_strategy_knn.cpp:19, activation_strategy.cpp:19-20) */
+  int32_t distance_type;  /* Parameters.DistanceType */
+  int32_t knn_k;          /* Codebook.ActivationStrategy.K, 1..PCDB_MAX_K */
+  int32_t use_distance_ratio;
+  float distance_ratio_threshold;
+  /* Vote weights (codebook.cpp:32-35) */
+  int32_t use_class_weight, use_vote_weight, use_matching_weight, use_codeword_weight;
+  int32_t filter_abs_is_int; /* 1 = treat the unqualified abs() at codeword_distribution.cpp:131 as abs(int) */
+  /* Mean-shift voting (voting_mean_shift.cpp:22-26, voting.cpp:28-36) */
+  float bandwidth;        /* Voting.Bandwidth */
+  float ms_threshold;     /* Voting.Threshold */
+  int32_t ms_max_iter;    /* Voting.MaxIter */
+  int32_t ms_kernel;      /* PCDB_KERNEL_* */
+  int32_t maxima_suppression; /* PCDB_SUPPRESS_* */
+  float min_threshold;    /* Voting.MinThreshold */
+  int32_t min_votes_threshold; /* Voting.MinVotesThreshold */
+  int32_t best_k;         /* Voting.BestK (<=0: keep all) */
+  int32_t average_rotation;    /* Voting.AverageRotation */
+  int32_t single_object_mode;  /* Voting.SingleObjectMode (only gates cross-class filtering on this path) */
+} pcdb_params;
+
+/* One Hough vote — ism3d::Vote, voting/voting_maximum.h:25-42 (80 bytes). */
+typedef struct pcdb_vote {
+  float position[3];
+  float weight;
+  float keypoint[3];
+  uint32_t class_id;
+  float keypoint_training[3];
+  uint32_t instance_id;
+  float bbox_quat[4]; /* w,x,y,z  (Utils::BoundingBox::rotQuat) */
+  float bbox_size[3];
+  int32_t codeword_id;
+} pcdb_vote;
+
+/* One voting maximum — ism3d::VotingMaximum, voting/voting_maximum.h:51-88. */
+typedef struct pcdb_maximum {
+  float position[3];
+  float weight;            /* normalised over the cloud's maxima (voting.cpp:441-462) */
+  uint32_t class_id;
+  uint32_t instance_id;
+  float instance_weight;
+  float raw_weight;        /* sum of member vote weights before normalisation */
+  float bbox_quat[4];      /* w,x,y,z */
+  float bbox_size[3];
+  int32_t n_votes;
+  int64_t vote_begin;      /* first entry of this maximum in the member list (pcdb_get_maximum_votes) */
+} pcdb_maximum;
+
+typedef struct pcdb_ctx pcdb_ctx;
+
+/* ---- lifecycle ------------------------------------------------------- */
+int pcdb_abi_version(void);
+/* Replaces: ImplicitShapeModel ctor + first-call FLANN hook (implicit_shape_model.cpp:131-143,651-660). */
+int pcdb_create(pcdb_ctx** out, int device);
+void pcdb_destroy(pcdb_ctx* ctx);
+const char* pcdb_last_error(const pcdb_ctx* ctx); /* ctx may be NULL: error of a failed pcdb_create */
+void pcdb_default_params(pcdb_params* p);         /* code defaults of SURVEY App. C */
+int pcdb_set_params(pcdb_ctx* ctx, const pcdb_params* p); /* JSONObject::readObject (utils/json_object.cpp:97-178) */
+/* Launch on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+int pcdb_set_stream(pcdb_ctx* ctx, void* cuda_stream);
+
+/* ---- model upload ---------------------------------------------------- */
+/* Replaces: FlannHelper::createDataset/buildIndex (utils/flann_helper.cpp:21-70) and the in-memory
+ * Codebook / CodewordDistribution tables (codebook/codebook.cpp:763-950, codeword_distribution.cpp:395-465).
+ * words: N x D row-major in codeword-id order (codebook.cpp:857-859).  Votes are CSR by codeword row:
+ * vote_off[N+1]; per vote: LRF-relative offset xyz, learned weight, class, instance, bbox (quat wxyz + size),
+ * statistical class weight.  kp_train: N x 3 (Codeword::getFeaturePosition).  codeword_ids: the stored ids
+ * (NULL = row index + row_base).  codeword_weight: N (NULL = 1).  class_sigma2[c] for c < n_classes
+ * (missing class => pass 1.0f as the reference does, codeword_distribution.cpp:117-121). */
+int pcdb_set_codebook(pcdb_ctx* ctx, const float* words, int64_t N, int32_t D,
+                      const int64_t* vote_off, const float* vote_xyz, const float* vote_weight,
+                      const uint32_t* vote_class, const uint32_t* vote_instance,
+                      const float* vote_bbox /* V x 7 */, const float* vote_class_weight /* V or NULL */,
+                      const float* kp_train, const int32_t* codeword_ids, const float* codeword_weight,
+                      const float* class_sigma2, int32_t n_classes, int64_t row_base);
+
+/* ---- stage-level entry points (one per reference hook) ---------------- */
+/* KeypointsVoxelGrid::iComputeKeypoints (keypoints/keypoints_voxel_grid.cpp:30-46 -> pcl::VoxelGrid).
+ * rgb: packed 0x00RRGGBB per point or NULL.  kp_capacity in keypoints. */
+int pcdb_voxel_keypoints(pcdb_ctx* ctx, const float* xyz, const uint32_t* rgb, const int64_t* cloud_off,
+                         int32_t B, float leaf, float* kp_xyz_out, uint32_t* kp_rgb_out,
+                         int64_t* kp_off_out, int64_t kp_capacity);
+
+/* Radius neighbourhoods (pcl::search::KdTree::radiusSearch as used at features.cpp:243-249 and
+ * features_shot.cpp:37-60): for every keypoint the surface indices (cloud-local) with d^2 < float(r*r),
+ * sorted by (d^2, index).  nbr_off has Q+1 entries.  Parity/debug entry; the descriptor kernels fuse this. */
+int pcdb_radius_neighbours(pcdb_ctx* ctx, const float* surf_xyz, const int64_t* surf_off,
+                           const float* kp_xyz, const int64_t* kp_off, int32_t B, double radius,
+                           int64_t* nbr_off_out, int32_t* nbr_idx_out, float* nbr_d2_out, int64_t capacity);
+
+/* Features::computeSHOTReferenceFrames (features/features.cpp:238-252 -> pcl::SHOTLocalReferenceFrameEstimationOMP).
+ * lrf9_out: Q x 9 (x_axis, y_axis, z_axis); NaN rows for invalid frames. */
+int pcdb_shot_lrf(pcdb_ctx* ctx, const float* surf_xyz, const int64_t* surf_off, const float* kp_xyz,
+                  const int64_t* kp_off, int32_t B, double radius, float* lrf9_out);
+
+/* FeaturesSHOT / FeaturesCSHOT::iComputeDescriptors (features/features_shot.cpp:28-81,
+ * features/features_cshot.cpp:28-103 -> pcl::SHOT(Color)EstimationOMP) with given reference frames.
+ * desc_out: Q x 352 (SHOT) or Q x 1344 (CSHOT); all-NaN rows where the reference yields NaN. */
+int pcdb_shot_describe(pcdb_ctx* ctx, int32_t feature_type, const float* surf_xyz, const float* surf_normals,
+                       const uint32_t* surf_rgb, const int64_t* surf_off, const float* kp_xyz,
+                       const uint32_t* kp_rgb, const float* kp_lrf9, const int64_t* kp_off, int32_t B,
+                       double radius, float* desc_out);
+
+/* Features::operator() + removeNaNFeatures (features/features.cpp:40-116, implicit_shape_model.cpp:1276-1308):
+ * keypoints -> LRF -> drop invalid -> descriptor -> drop NaN; uses the context's params.  Outputs are the
+ * surviving features (position, LRF, descriptor) per cloud. */
+int pcdb_compute_features(pcdb_ctx* ctx, const float* xyz, const float* normals, const uint32_t* rgb,
+                          const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
+                          float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity);
+
+/* ActivationStrategyKNN::activateKNN (activation_strategy/activation_strategy_knn.h:41-126) against the uploaded
+ * codebook, exact search (FLANNExactMatch semantics), FLANN functor values.  idx_out/dist_out: Q x k, ascending
+ * distance, ties -> lower row; count_out[q] = number of activated rows (0 after a failed ratio test, N if N<=k). */
+int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t dist_type, int32_t mode,
+             int32_t* idx_out, float* dist_out, int32_t* count_out);
+
+/* Codebook::castVotes + CodewordDistribution::castVotes/castVote (codebook/codebook.cpp:403-555,
+ * codebook/codeword_distribution.cpp:73-167).  Votes are emitted per cloud in (feature, activation rank,
+ * stored vote) order.  vote_off_out has B+1 entries. */
+int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9, const int64_t* feat_off,
+                    int32_t B, const int32_t* knn_idx, const float* knn_dist, const int32_t* knn_count,
+                    int32_t k, pcdb_vote* votes_out, int64_t* vote_off_out, int64_t vote_capacity);
+
+/* Voting::findMaxima + VotingMeanShift::iFindMaxima (voting/voting.cpp:79-328,
+ * voting/voting_mean_shift.cpp:39-177).  maxima sorted per cloud by weight (descending). */
+int pcdb_find_maxima(pcdb_ctx* ctx, const pcdb_vote* votes, const int64_t* vote_off, int32_t B,
+                     pcdb_maximum* maxima_out, int64_t* maxima_off_out, int64_t maxima_capacity);
+/* Member votes of the maxima of the last pcdb_find_maxima / pcdb_classify_batch call
+ * (VotingMaximum::votes): indices into that call's vote array and the kernel-re-weighted weights. */
+int pcdb_get_maximum_votes(pcdb_ctx* ctx, int64_t* vote_index_out, float* vote_weight_out, int64_t capacity,
+                           int64_t* n_out);
+/* Votes of the last pcdb_classify_batch call (Voting::getVotes, read by training_gui.cpp:1012). */
+int pcdb_get_votes(pcdb_ctx* ctx, pcdb_vote* votes_out, int64_t* vote_off_out, int64_t capacity);
+
+/* ---- fused batch path (the throughput entry) -------------------------- */
+/* ImplicitShapeModel::detect (implicit_shape_model.cpp:583-712) for B clouds at once, label pick of
+ * eval_tool (src/eval_tool/eval_classification.cpp:412-417) included.  Host buffers in, host buffers out.
+ * label_out[b] = class of the best maximum or -1.  maxima_out/maxima_off_out may be NULL.
+ * times_ms_out[7]: complete, features, keypoints, normals, flann, voting, maxima (implicit_shape_model.cpp:160). */
+int pcdb_classify_batch(pcdb_ctx* ctx, const float* xyz, const float* normals, const uint32_t* rgb,
+                        const int64_t* cloud_off, int32_t B, int32_t* label_out, pcdb_maximum* maxima_out,
+                        int64_t* maxima_off_out, int64_t maxima_capacity, double* times_ms_out);
+/* Same, inputs already resident in device memory (xyz P x 3, normals P x 3, rgb P or NULL, cloud_off on HOST),
+ * labels written to device memory. */
+int pcdb_classify_batch_d(pcdb_ctx* ctx, const float* xyz_d, const float* normals_d, const uint32_t* rgb_d,
+                          const int64_t* cloud_off, int32_t B, int32_t* label_out_d);
+
+/* ---- multi-GPU: row-sharded codebook --------------------------------- */
+/* Per-query merge of per-shard top-k lists.  cand_* : S x Q x k (shard-major), global row ids;
+ * result: Q x k ascending (distance, row).  Runs on the device of ctx; used after an all-gather. */
+int pcdb_merge_topk(pcdb_ctx* ctx, const int32_t* cand_idx, const float* cand_dist, int32_t S, int64_t Q,
+                    int32_t k, int32_t* idx_out, float* dist_out);
+
+/* ---- introspection for bench / profiling ------------------------------ */
+typedef struct pcdb_stats {
+  int64_t n_points, n_keypoints, n_features, n_neighbours_lrf, n_neighbours_shot, n_votes, n_maxima;
+  int64_t knn_queries, knn_candidates, knn_fallback_queries;
+  int64_t kernel_launches;  /* launches of this library's own kernels since the last reset */
+  /* device time of the last classify batch (CUDA events on the context's stream) */
+  double features_ms, knn_ms, knn_gemm_ms /* tcgen05 activation kernel alone */, votes_ms, maxima_ms;
+} pcdb_stats;
+int pcdb_get_stats(pcdb_ctx* ctx, pcdb_stats* out);
+int pcdb_reset_stats(pcdb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDB200_H_ */

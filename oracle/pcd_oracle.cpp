@@ -1,0 +1,1872 @@
+/*
+ * pcd_oracle.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (C++17 + OpenMP, no dependencies) of the classification hot path of
+ * vseib/point-cloud-donkey.  It is the parity checker for the CUDA library in
+ * point-cloud-donkey_b200/csrc and the `cpu_baseline` / `--impl reference` arm of bench.py.
+ * Nothing under point-cloud-donkey_b200/ may include, link or call it.
+ *
+ * PARITY STATUS: the reference cannot be built here (needs PCL/FLANN/Eigen/Boost) and ships no
+ * tests or golden vectors, so most of this file is "parity unpinned": it follows the in-repo
+ * orchestration line by line and restates the PCL 1.10 / FLANN 1.9 arithmetic.
+ * Two pieces ARE pinned:
+ *   - RGB->CIELab + colour distance: against the reference's own
+ *     third_party/pcl_color_conversion/color_conversion.cpp compiled into oracle/_ref
+ *     (tests/test_oracle_pins.py, tests/golden/lab_golden.npz);
+ *   - the L2 / chi^2 functor values and exact-kNN order: against a real FLANN build
+ *     (cv2.flann linear index; tests/golden/flann_golden.npz).
+ *
+ * Reference paths are relative to /root/reference/src/implicit_shape_model/.
+ * Build: see oracle/Makefile (-ffp-contract=off: the reference is an x86-64 SSE build without FMA).
+ */
+#include "../include/pcdb200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+const float kNaNf = std::numeric_limits<float>::quiet_NaN();
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.2  radius search: pcl::search::KdTree -> FLANN KDTreeSingleIndex<L2_Simple<float>>, exact  */
+/* ------------------------------------------------------------------------------------------- */
+struct Nbr {
+  float d2;
+  int idx;
+};
+inline bool nbr_less(const Nbr& a, const Nbr& b) { return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx); }
+
+/* flann L2_Simple: result += diff*diff, x then y then z, float, no FMA (compiled -ffp-contract=off). */
+inline float sqdist3(const float* a, const float* b) {
+  float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+  float r = d0 * d0;
+  r += d1 * d1;
+  r += d2 * d2;
+  return r;
+}
+
+/* pcl::KdTreeFLANN::radiusSearch squares the double radius and narrows: float(radius*radius). */
+inline float radius_sq(double radius) { return static_cast<float>(radius * radius); }
+
+/* Uniform grid used only to make the brute-force membership test cheap on big clouds; the set it
+ * returns is the same as testing every point (cells are wider than the radius). */
+struct CloudGrid {
+  const float* xyz = nullptr;
+  int n = 0;
+  bool brute = true;
+  float mn[3] = {0, 0, 0};
+  float inv = 0;
+  int dim[3] = {1, 1, 1};
+  std::vector<int> start, order;
+
+  void build(const float* pts, int count, double radius) {
+    xyz = pts;
+    n = count;
+    brute = true;
+    if (n < 512 || !(radius > 0)) return;
+    float mx[3];
+    for (int a = 0; a < 3; ++a) mn[a] = mx[a] = pts[a];
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = std::min(mn[a], pts[3 * i + a]);
+        mx[a] = std::max(mx[a], pts[3 * i + a]);
+      }
+    float cell = static_cast<float>(radius * 1.001);
+    inv = 1.0f / cell;
+    double total = 1;
+    for (int a = 0; a < 3; ++a) {
+      double d = std::floor((double(mx[a]) - double(mn[a])) * inv) + 1;
+      if (!(d >= 1) || d > 4096) return;
+      dim[a] = int(d);
+      total *= d;
+    }
+    if (total > 8e6) return;
+    int ncell = dim[0] * dim[1] * dim[2];
+    start.assign(ncell + 1, 0);
+    std::vector<int> cid(n);
+    for (int i = 0; i < n; ++i) {
+      cid[i] = cell_of(pts + 3 * i);
+      start[cid[i] + 1]++;
+    }
+    for (int c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    order.resize(n);
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) order[fill[cid[i]]++] = i;
+    brute = false;
+  }
+  int coord(float v, int a) const {
+    int c = int(std::floor((v - mn[a]) * inv));
+    return std::max(0, std::min(dim[a] - 1, c));
+  }
+  int cell_of(const float* p) const { return (coord(p[2], 2) * dim[1] + coord(p[1], 1)) * dim[0] + coord(p[0], 0); }
+
+  void query(const float* q, float r2, std::vector<Nbr>& out) const {
+    out.clear();
+    if (brute) {
+      for (int i = 0; i < n; ++i) {
+        float d2 = sqdist3(q, xyz + 3 * i);
+        if (d2 < r2) out.push_back({d2, i});
+      }
+    } else {
+      int c[3];
+      for (int a = 0; a < 3; ++a) c[a] = int(std::floor((q[a] - mn[a]) * inv));
+      for (int z = std::max(0, c[2] - 1); z <= std::min(dim[2] - 1, c[2] + 1); ++z)
+        for (int y = std::max(0, c[1] - 1); y <= std::min(dim[1] - 1, c[1] + 1); ++y)
+          for (int x = std::max(0, c[0] - 1); x <= std::min(dim[0] - 1, c[0] + 1); ++x) {
+            int cell = (z * dim[1] + y) * dim[0] + x;
+            for (int s = start[cell]; s < start[cell + 1]; ++s) {
+              int i = order[s];
+              float d2 = sqdist3(q, xyz + 3 * i);
+              if (d2 < r2) out.push_back({d2, i});
+            }
+          }
+    }
+    std::sort(out.begin(), out.end(), nbr_less); /* sorted_results_ = true; DistanceIndex::operator< */
+  }
+};
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.1  pcl::VoxelGrid<PointXYZRGB> (keypoints/keypoints_voxel_grid.cpp:30-46)                  */
+/* ------------------------------------------------------------------------------------------- */
+struct Keypoints {
+  std::vector<float> xyz;
+  std::vector<uint32_t> rgb;
+};
+
+bool finite3(const float* p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); }
+
+/* returns false when PCL would warn "leaf size too small" (output = input copy) */
+bool voxel_keypoints(const float* xyz, const uint32_t* rgb, int n, float leaf, Keypoints& out) {
+  out.xyz.clear();
+  out.rgb.clear();
+  if (n <= 0) return true;
+  float inv = 1.0f / leaf;
+  float mn[3], mx[3];
+  bool any = false;
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!finite3(p)) continue;
+    if (!any) {
+      for (int a = 0; a < 3; ++a) mn[a] = mx[a] = p[a];
+      any = true;
+    } else
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = std::min(mn[a], p[a]);
+        mx[a] = std::max(mx[a], p[a]);
+      }
+  }
+  if (!any) return true;
+  int64_t dx = static_cast<int64_t>((mx[0] - mn[0]) * inv) + 1;
+  int64_t dy = static_cast<int64_t>((mx[1] - mn[1]) * inv) + 1;
+  int64_t dz = static_cast<int64_t>((mx[2] - mn[2]) * inv) + 1;
+  if ((dx * dy * dz) > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+    for (int i = 0; i < n; ++i) {
+      out.xyz.insert(out.xyz.end(), xyz + 3 * i, xyz + 3 * i + 3);
+      out.rgb.push_back(rgb ? rgb[i] : 0u);
+    }
+    return false;
+  }
+  int min_b[3], max_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = static_cast<int>(std::floor(mn[a] * inv));
+    max_b[a] = static_cast<int>(std::floor(mx[a] * inv));
+    div_b[a] = max_b[a] - min_b[a] + 1;
+  }
+  int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<int, int>> iv; /* (voxel idx, point idx) */
+  iv.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!finite3(p)) continue;
+    int ijk0 = static_cast<int>(std::floor(p[0] * inv) - static_cast<float>(min_b[0]));
+    int ijk1 = static_cast<int>(std::floor(p[1] * inv) - static_cast<float>(min_b[1]));
+    int ijk2 = static_cast<int>(std::floor(p[2] * inv) - static_cast<float>(min_b[2]));
+    iv.push_back({ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2], i});
+  }
+  /* PCL: std::sort on idx (unstable); the oracle DEFINES the order as stable by point index. */
+  std::stable_sort(iv.begin(), iv.end(),
+                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+  size_t s = 0;
+  while (s < iv.size()) {
+    size_t e = s;
+    float sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0;
+    while (e < iv.size() && iv[e].first == iv[s].first) {
+      int i = iv[e].second;
+      sx += xyz[3 * i];
+      sy += xyz[3 * i + 1];
+      sz += xyz[3 * i + 2];
+      uint32_t c = rgb ? rgb[i] : 0u;
+      sr += static_cast<float>((c >> 16) & 0xFF);
+      sg += static_cast<float>((c >> 8) & 0xFF);
+      sb += static_cast<float>(c & 0xFF);
+      ++e;
+    }
+    float cnt = static_cast<float>(e - s);
+    out.xyz.push_back(sx / cnt);
+    out.xyz.push_back(sy / cnt);
+    out.xyz.push_back(sz / cnt);
+    uint32_t r = static_cast<uint32_t>(sr / cnt), g = static_cast<uint32_t>(sg / cnt),
+             b = static_cast<uint32_t>(sb / cnt);
+    out.rgb.push_back((r << 16) | (g << 8) | b);
+    s = e;
+  }
+  return true;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* symmetric 3x3 eigen (double).  The reference uses Eigen::SelfAdjointEigenSolver<Matrix3d>     */
+/* (third_party/pcl_shot_na_lrf/shot_na_lrf.hpp:95); restated as cyclic Jacobi, ascending.       */
+/* ------------------------------------------------------------------------------------------- */
+void eig3_sym(const double Ain[3][3], double w[3], double V[3][3]) {
+  double A[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      A[i][j] = Ain[i][j];
+      V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+    if (off == 0.0) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = A[p][q];
+        if (apq == 0.0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (!std::isfinite(theta)) t = 0.0;
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { /* A <- A * J */
+          double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) { /* A <- J^T * A */
+          double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        A[p][q] = A[q][p] = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int ord[3] = {0, 1, 2};
+  double d[3] = {A[0][0], A[1][1], A[2][2]};
+  std::sort(ord, ord + 3, [&](int a, int b) { return d[a] < d[b] || (d[a] == d[b] && a < b); });
+  double Vs[3][3];
+  for (int j = 0; j < 3; ++j) {
+    w[j] = d[ord[j]];
+    for (int i = 0; i < 3; ++i) Vs[i][j] = V[i][ord[j]];
+  }
+  std::memcpy(V, Vs, sizeof(Vs));
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.3  SHOT local reference frame (features/features.cpp:238-252 ->                             */
+/*      pcl::SHOTLocalReferenceFrameEstimation::getLocalRF; anchor shot_na_lrf.hpp:48-178)      */
+/* ------------------------------------------------------------------------------------------- */
+void shot_lrf(const float* surf, const std::vector<Nbr>& nb, const float* kp, double radius, float rf[9]) {
+  std::vector<double> vij;
+  vij.reserve(nb.size() * 3);
+  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double sum = 0.0;
+  int valid = 0;
+  for (const Nbr& nbr : nb) {
+    const float* pt = surf + 3 * nbr.idx;
+    if (pt[0] == kp[0] && pt[1] == kp[1] && pt[2] == kp[2]) continue; /* shot_na_lrf.hpp:69 */
+    double v[3] = {double(pt[0] - kp[0]), double(pt[1] - kp[1]), double(pt[2] - kp[2])};
+    double distance = radius - std::sqrt(double(nbr.d2)); /* :76 */
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) cov[i][j] += distance * (v[i] * v[j]);
+    sum += distance;
+    vij.insert(vij.end(), v, v + 3);
+    valid++;
+  }
+  if (valid < 5) { /* :85-91 */
+    for (int i = 0; i < 9; ++i) rf[i] = kNaNf;
+    return;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) cov[i][j] /= sum;
+  double w[3], V[3][3];
+  eig3_sym(cov, w, V);
+  if (!std::isfinite(w[0]) || !std::isfinite(w[1]) || !std::isfinite(w[2])) {
+    for (int i = 0; i < 9; ++i) rf[i] = kNaNf;
+    return;
+  }
+  double v1[3] = {V[0][2], V[1][2], V[2][2]}; /* largest eigenvalue -> x */
+  double v3[3] = {V[0][0], V[1][0], V[2][0]}; /* smallest -> z */
+  int plusNormal = 0, plusTangent = 0;
+  for (int ne = 0; ne < valid; ++ne) {
+    const double* r = &vij[3 * ne];
+    double dp = r[0] * v1[0] + r[1] * v1[1] + r[2] * v1[2];
+    if (dp >= 0) plusTangent++;
+    dp = r[0] * v3[0] + r[1] * v3[1] + r[2] * v3[2];
+    if (dp >= 0) plusNormal++;
+  }
+  auto disambiguate = [&](int plus, double* v) {
+    plus = 2 * plus - valid;
+    if (plus == 0) {
+      const int points = 5;
+      int medianIndex = valid / 2;
+      for (int i = -points / 2; i <= points / 2; ++i) {
+        const double* r = &vij[3 * (medianIndex - i)];
+        if (r[0] * v[0] + r[1] * v[1] + r[2] * v[2] > 0) plus++;
+      }
+      if (plus < points / 2 + 1)
+        for (int a = 0; a < 3; ++a) v[a] *= -1;
+    } else if (plus < 0)
+      for (int a = 0; a < 3; ++a) v[a] *= -1;
+  };
+  disambiguate(plusTangent, v1);
+  disambiguate(plusNormal, v3);
+  float x[3] = {float(v1[0]), float(v1[1]), float(v1[2])};
+  float z[3] = {float(v3[0]), float(v3[1]), float(v3[2])};
+  float y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+  for (int a = 0; a < 3; ++a) {
+    rf[a] = x[a];
+    rf[3 + a] = y[a];
+    rf[6 + a] = z[a];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.5  RGB -> CIELab (features/features_cshot.cpp:52-71 LUTs,                                   */
+/*      third_party/pcl_color_conversion/color_conversion.cpp:19-94)                             */
+/* ------------------------------------------------------------------------------------------- */
+struct LabLut {
+  float srgb[256];
+  float sxyz[4000];
+  LabLut() {
+    for (int i = 0; i < 256; i++) {
+      float f = static_cast<float>(i) / 255.0f;
+      if (f > 0.04045)
+        srgb[i] = powf((f + 0.055f) / 1.055f, 2.4f);
+      else
+        srgb[i] = f / 12.92f;
+    }
+    for (int i = 0; i < 4000; i++) {
+      float f = static_cast<float>(i) / 4000.0f;
+      if (f > 0.008856)
+        sxyz[i] = static_cast<float>(powf(f, 0.3333f));
+      else
+        sxyz[i] = static_cast<float>((7.787 * f) + (16.0 / 116.0));
+    }
+  }
+};
+const LabLut& lab_lut() {
+  static LabLut l;
+  return l;
+}
+
+/* L in [0,100], A,B in [-120,120] (PCL RGB2CIELAB); normalisation by 100/120/120 done by the caller */
+void rgb2lab(uint32_t rgb, float& L, float& A, float& B2) {
+  const LabLut& lut = lab_lut();
+  float fr = lut.srgb[(rgb >> 16) & 0xFF];
+  float fg = lut.srgb[(rgb >> 8) & 0xFF];
+  float fb = lut.srgb[rgb & 0xFF];
+  const float x = fr * 0.412453f + fg * 0.357580f + fb * 0.180423f;
+  const float y = fr * 0.212671f + fg * 0.715160f + fb * 0.072169f;
+  const float z = fr * 0.019334f + fg * 0.119193f + fb * 0.950227f;
+  float vx = x / 0.95047f;
+  float vy = y;
+  float vz = z / 1.08883f;
+  vx = lut.sxyz[int(vx * 4000)];
+  vy = lut.sxyz[int(vy * 4000)];
+  vz = lut.sxyz[int(vz * 4000)];
+  L = 116.0f * vy - 16.0f;
+  if (L > 100) L = 100.0f;
+  A = 500.0f * (vx - vy);
+  if (A > 120)
+    A = 120.0f;
+  else if (A < -120)
+    A = -120.0f;
+  B2 = 200.0f * (vy - vz);
+  if (B2 > 120)
+    B2 = 120.0f;
+  else if (B2 < -120)
+    B2 = -120.0f;
+}
+
+/* colour distance of features_short_cshot.cpp:194-198 / color_conversion.cpp:85-93 (float fabs overloads) */
+double color_distance(float L, float a, float b, float LRef, float aRef, float bRef) {
+  double cd = (std::fabs(LRef - L) + ((std::fabs(aRef - a) + std::fabs(bRef - b)) / 2)) / 3;
+  if (cd > 1.0) cd = 1.0;
+  if (cd < 0.0) cd = 0.0;
+  return cd;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.4/A.5  SHOT-352 / CSHOT-1344 (features/features_shot.cpp:28-81, features_cshot.cpp:28-103  */
+/*          -> pcl::SHOTEstimation::computePointSHOT / interpolateSingle/DoubleChannel)         */
+/* ------------------------------------------------------------------------------------------- */
+const double PST_PI = 3.1415926535897932384626433832795;
+const double PST_RAD_45 = 0.78539816339744830961566084581988;
+const double PST_RAD_90 = 1.5707963267948966192313216916398;
+const double PST_RAD_135 = 2.3561944901923449288469825374596;
+const double PST_RAD_PI_7_8 = 2.7488935718910690836548129603691;
+
+inline float dot3f(const float* a, const float* b) {
+  float r = a[0] * b[0];
+  r += a[1] * b[1];
+  r += a[2] * b[2];
+  return r;
+}
+
+void shot_describe(bool color, const float* surf, const float* normals, const uint32_t* surf_rgb,
+                   const std::vector<Nbr>& nb, const float* kp, uint32_t kp_rgb, const float* rf, double radius,
+                   float* shot) {
+  const int nr_shape = 10, nr_color = 30, D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  const int stride_color = 32 * (nr_shape + 1);
+  const double radius3_4 = (radius * 3) / 4, radius1_4 = radius / 4, radius1_2 = radius / 2;
+  if (nb.size() < 5 || !std::isfinite(rf[0]) || !std::isfinite(rf[3]) || !std::isfinite(rf[6])) {
+    for (int i = 0; i < D; ++i) shot[i] = kNaNf;
+    return;
+  }
+  const float* fx = rf;
+  const float* fy = rf + 3;
+  const float* fz = rf + 6;
+  std::vector<double> bdS(nb.size()), bdC;
+  for (size_t i = 0; i < nb.size(); ++i) {
+    const float* nrm = normals + 3 * nb[i].idx;
+    if (!finite3(nrm))
+      bdS[i] = std::numeric_limits<double>::quiet_NaN();
+    else {
+      double cosineDesc = dot3f(nrm, fz);
+      if (cosineDesc > 1.0) cosineDesc = 1.0;
+      if (cosineDesc < -1.0) cosineDesc = -1.0;
+      bdS[i] = ((1.0 + cosineDesc) * nr_shape) / 2;
+    }
+  }
+  if (color) {
+    bdC.resize(nb.size());
+    float LRef, aRef, bRef;
+    rgb2lab(kp_rgb, LRef, aRef, bRef);
+    LRef /= 100.0f;
+    aRef /= 120.0f;
+    bRef /= 120.0f;
+    for (size_t i = 0; i < nb.size(); ++i) {
+      float L, a, b;
+      rgb2lab(surf_rgb ? surf_rgb[nb[i].idx] : 0u, L, a, b);
+      L /= 100.0f;
+      a /= 120.0f;
+      b /= 120.0f;
+      bdC[i] = color_distance(L, a, b, LRef, aRef, bRef) * nr_color;
+    }
+  }
+  for (int i = 0; i < D; ++i) shot[i] = 0.0f;
+  for (size_t i = 0; i < nb.size(); ++i) {
+    if (!std::isfinite(bdS[i])) continue;
+    const float* p = surf + 3 * nb[i].idx;
+    float delta[3] = {p[0] - kp[0], p[1] - kp[1], p[2] - kp[2]};
+    double distance = std::sqrt(double(nb[i].d2));
+    if (std::fabs(distance - 0.0) < 1E-15) continue;
+    double xIn = dot3f(delta, fx), yIn = dot3f(delta, fy), zIn = dot3f(delta, fz);
+    if (std::fabs(yIn) < 1E-30) yIn = 0;
+    if (std::fabs(xIn) < 1E-30) xIn = 0;
+    if (std::fabs(zIn) < 1E-30) zIn = 0;
+    unsigned char bit4 = ((yIn > 0) || ((yIn == 0.0) && (xIn < 0))) ? 1 : 0;
+    unsigned char bit3 = static_cast<unsigned char>(((xIn > 0) || ((xIn == 0.0) && (yIn > 0))) ? !bit4 : bit4);
+    int desc_index = (bit4 << 3) + (bit3 << 2);
+    desc_index = desc_index << 1;
+    if ((xIn * yIn > 0) || (xIn == 0.0))
+      desc_index += (std::fabs(xIn) >= std::fabs(yIn)) ? 0 : 4;
+    else
+      desc_index += (std::fabs(xIn) > std::fabs(yIn)) ? 4 : 0;
+    desc_index += zIn > 0 ? 1 : 0;
+    desc_index += (distance > radius1_2) ? 2 : 0;
+
+    int stepS = static_cast<int>(std::floor(bdS[i] + 0.5));
+    int volS = desc_index * (nr_shape + 1);
+    double bS = bdS[i] - stepS;
+    double wS = (1 - std::fabs(bS));
+    if (bS > 0)
+      shot[volS + ((stepS + 1) % nr_shape)] += static_cast<float>(bS);
+    else
+      shot[volS + ((stepS - 1 + nr_shape) % nr_shape)] -= static_cast<float>(bS);
+    int stepC = 0, volC = 0;
+    double wC = 0;
+    if (color) {
+      stepC = static_cast<int>(std::floor(bdC[i] + 0.5));
+      volC = stride_color + desc_index * (nr_color + 1);
+      double bC = bdC[i] - stepC;
+      wC = (1 - std::fabs(bC));
+      if (bC > 0)
+        shot[volC + ((stepC + 1) % nr_color)] += static_cast<float>(bC);
+      else
+        shot[volC + ((stepC - 1 + nr_color) % nr_color)] -= static_cast<float>(bC);
+    }
+    auto add_nb = [&](int di, double v) { /* neighbouring volume `di` receives v in both channels */
+      shot[di * (nr_shape + 1) + stepS] += static_cast<float>(v);
+      if (color) shot[stride_color + di * (nr_color + 1) + stepC] += static_cast<float>(v);
+    };
+    /* radial */
+    if (distance > radius1_2) {
+      double rd = (distance - radius3_4) / radius1_2;
+      if (distance > radius3_4) {
+        wS += 1 - rd;
+        wC += 1 - rd;
+      } else {
+        wS += 1 + rd;
+        wC += 1 + rd;
+        add_nb(desc_index - 2, -rd);
+      }
+    } else {
+      double rd = (distance - radius1_4) / radius1_2;
+      if (distance < radius1_4) {
+        wS += 1 + rd;
+        wC += 1 + rd;
+      } else {
+        wS += 1 - rd;
+        wC += 1 - rd;
+        add_nb(desc_index + 2, rd);
+      }
+    }
+    /* elevation */
+    double inclinationCos = zIn / distance;
+    if (inclinationCos < -1.0) inclinationCos = -1.0;
+    if (inclinationCos > 1.0) inclinationCos = 1.0;
+    double inclination = std::acos(inclinationCos);
+    if (inclination > PST_RAD_90 || (std::fabs(inclination - PST_RAD_90) < 1e-30 && zIn <= 0)) {
+      double id = (inclination - PST_RAD_135) / PST_RAD_90;
+      if (inclination > PST_RAD_135) {
+        wS += 1 - id;
+        wC += 1 - id;
+      } else {
+        wS += 1 + id;
+        wC += 1 + id;
+        add_nb(desc_index + 1, -id);
+      }
+    } else {
+      double id = (inclination - PST_RAD_45) / PST_RAD_90;
+      if (inclination < PST_RAD_45) {
+        wS += 1 + id;
+        wC += 1 + id;
+      } else {
+        wS += 1 - id;
+        wC += 1 - id;
+        add_nb(desc_index - 1, id);
+      }
+    }
+    /* azimuth */
+    if (yIn != 0.0 || xIn != 0.0) {
+      double azimuth = std::atan2(yIn, xIn);
+      int sel = desc_index >> 2;
+      double ad = (azimuth - (-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) / PST_RAD_45;
+      ad = (std::max)(-0.5, std::min(ad, 0.5));
+      if (ad > 0) {
+        wS += 1 - ad;
+        wC += 1 - ad;
+        add_nb((desc_index + 4) % 32, ad);
+      } else {
+        wS += 1 + ad;
+        wC += 1 + ad;
+        add_nb((desc_index - 4 + 32) % 32, -ad);
+      }
+    }
+    shot[volS + stepS] += static_cast<float>(wS);
+    if (color) shot[volC + stepC] += static_cast<float>(wC);
+  }
+  double acc = 0.0;
+  for (int j = 0; j < D; ++j) acc += shot[j] * shot[j];
+  acc = std::sqrt(acc);
+  for (int j = 0; j < D; ++j) shot[j] /= static_cast<float>(acc);
+  (void)PST_PI;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.6  FLANN distance functors (utils/distance.h:42-75 -> flann::L2 / flann::ChiSquareDistance)*/
+/* ------------------------------------------------------------------------------------------- */
+inline float dist_l2(const float* a, const float* b, int n) {
+  float result = 0;
+  int i = 0;
+  for (; i + 3 < n; i += 4) {
+    float d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+    result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (; i < n; ++i) {
+    float d0 = a[i] - b[i];
+    result += d0 * d0;
+  }
+  return result;
+}
+inline float dist_chi2(const float* a, const float* b, int n) {
+  float result = 0;
+  for (int i = 0; i < n; ++i) {
+    float sum = a[i] + b[i];
+    if (sum > 0) {
+      float diff = a[i] - b[i];
+      result += diff * diff / sum;
+    }
+  }
+  return result;
+}
+inline float dist_fn(int type, const float* a, const float* b, int n) {
+  return type == PCDB_DIST_CHISQUARED ? dist_chi2(a, b, n) : dist_l2(a, b, n);
+}
+
+/* four codewords at once (independent accumulator chains; each chain keeps FLANN's order) */
+inline void dist_l2_x4(const float* q, const float* c0, const float* c1, const float* c2, const float* c3, int n,
+                       float out[4]) {
+  float r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  int i = 0;
+  for (; i + 3 < n; i += 4) {
+    float a0 = q[i], a1 = q[i + 1], a2 = q[i + 2], a3 = q[i + 3];
+    {
+      float d0 = a0 - c0[i], d1 = a1 - c0[i + 1], d2 = a2 - c0[i + 2], d3 = a3 - c0[i + 3];
+      r0 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    {
+      float d0 = a0 - c1[i], d1 = a1 - c1[i + 1], d2 = a2 - c1[i + 2], d3 = a3 - c1[i + 3];
+      r1 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    {
+      float d0 = a0 - c2[i], d1 = a1 - c2[i + 1], d2 = a2 - c2[i + 2], d3 = a3 - c2[i + 3];
+      r2 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    {
+      float d0 = a0 - c3[i], d1 = a1 - c3[i + 1], d2 = a2 - c3[i + 2], d3 = a3 - c3[i + 3];
+      r3 += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+  for (; i < n; ++i) {
+    float d;
+    d = q[i] - c0[i];
+    r0 += d * d;
+    d = q[i] - c1[i];
+    r1 += d * d;
+    d = q[i] - c2[i];
+    r2 += d * d;
+    d = q[i] - c3[i];
+    r3 += d * d;
+  }
+  out[0] = r0;
+  out[1] = r1;
+  out[2] = r2;
+  out[3] = r3;
+}
+
+/* exact kNN, ascending (distance, row) — FLANN's tie order is tree dependent */
+struct Cand {
+  float d;
+  int idx;
+};
+inline bool cand_less(const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.idx < b.idx); }
+
+void knn_one(const float* q, const float* words, int64_t N, int D, int k, int type, Cand* best /* k */, int& found) {
+  found = 0;
+  auto push = [&](float d, int idx) {
+    Cand c{d, idx};
+    if (found < k) {
+      int p = found++;
+      while (p > 0 && cand_less(c, best[p - 1])) {
+        best[p] = best[p - 1];
+        --p;
+      }
+      best[p] = c;
+    } else if (cand_less(c, best[k - 1])) {
+      int p = k - 1;
+      while (p > 0 && cand_less(c, best[p - 1])) {
+        best[p] = best[p - 1];
+        --p;
+      }
+      best[p] = c;
+    }
+  };
+  int64_t j = 0;
+  if (type == PCDB_DIST_EUCLIDEAN) {
+    for (; j + 3 < N; j += 4) {
+      float o[4];
+      dist_l2_x4(q, words + j * D, words + (j + 1) * D, words + (j + 2) * D, words + (j + 3) * D, D, o);
+      for (int t = 0; t < 4; ++t)
+        if (found < k || o[t] <= best[k - 1].d) push(o[t], int(j + t));
+    }
+  }
+  for (; j < N; ++j) push(dist_fn(type, q, words + j * D, D), int(j));
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* quaternion helpers restating utils/utils.cpp:136-178,342-394,560-574 with                    */
+/* boost::math::quaternion<float> operator*= evaluation order                                   */
+/* ------------------------------------------------------------------------------------------- */
+struct Quat {
+  float a, b, c, d; /* w x y z */
+};
+inline Quat qmul(const Quat& l, const Quat& r) {
+  Quat o;
+  o.a = +l.a * r.a - l.b * r.b - l.c * r.c - l.d * r.d;
+  o.b = +l.a * r.b + l.b * r.a + l.c * r.d - l.d * r.c;
+  o.c = +l.a * r.c - l.b * r.d + l.c * r.a + l.d * r.b;
+  o.d = +l.a * r.d + l.b * r.c - l.c * r.b + l.d * r.a;
+  return o;
+}
+inline Quat qconj(const Quat& q) { return Quat{q.a, -q.b, -q.c, -q.d}; }
+
+/* Utils::getRotQuaternion: Eigen's column-major matrix with columns = axes is read row-major by
+ * matrix2Quat, i.e. rows = axes (utils.cpp:136-152,384-394). */
+Quat lrf_quat(const float* rf) {
+  float m[3][3] = {{rf[0], rf[1], rf[2]}, {rf[3], rf[4], rf[5]}, {rf[6], rf[7], rf[8]}};
+  float quat[4] = {0, 0, 0, 0}; /* x y z w */
+  float trace = m[0][0] + m[1][1] + m[2][2];
+  float root;
+  if (trace > 0.0f) {
+    root = sqrtf(trace + 1.0f);
+    quat[3] = 0.5f * root;
+    root = 0.5f / root;
+    quat[0] = (m[2][1] - m[1][2]) * root;
+    quat[1] = (m[0][2] - m[2][0]) * root;
+    quat[2] = (m[1][0] - m[0][1]) * root;
+  } else {
+    static const size_t next[3] = {1, 2, 0};
+    size_t i = 0;
+    if (m[1][1] > m[0][0]) i = 1;
+    if (m[2][2] > m[i][i]) i = 2;
+    size_t j = next[i];
+    size_t k = next[j];
+    root = sqrtf(m[i][i] - m[j][j] - m[k][k] + 1.0);
+    quat[i] = 0.5f * root;
+    root = 0.5f / root;
+    quat[3] = (m[k][j] - m[j][k]) * root;
+    quat[j] = (m[j][i] + m[i][j]) * root;
+    quat[k] = (m[k][i] + m[i][k]) * root;
+  }
+  return Quat{quat[3], quat[0], quat[1], quat[2]};
+}
+inline void quat_rotate(const Quat& q, const float* p, float* out) { /* q p q*  (rotateInto) */
+  Quat t = qmul(qmul(q, Quat{0, p[0], p[1], p[2]}), qconj(q));
+  out[0] = t.b;
+  out[1] = t.c;
+  out[2] = t.d;
+}
+inline void quat_rotate_inv(const Quat& q, const float* p, float* out) { /* q* p q  (rotateBack) */
+  Quat t = qmul(qmul(qconj(q), Quat{0, p[0], p[1], p[2]}), q);
+  out[0] = t.b;
+  out[1] = t.c;
+  out[2] = t.d;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* model held by the oracle                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+struct Model {
+  pcdb_params prm;
+  int64_t N = 0;
+  int D = 0;
+  std::vector<float> words;
+  std::vector<int64_t> vote_off;
+  std::vector<float> vote_xyz, vote_weight, vote_bbox, vote_class_weight;
+  std::vector<uint32_t> vote_class, vote_instance;
+  std::vector<float> kp_train, codeword_weight;
+  std::vector<int32_t> codeword_ids;
+  std::vector<float> sigma2;
+};
+
+/* A.7  CodewordDistribution::castVotes / castVote (codebook/codeword_distribution.cpp:73-167) */
+void cast_votes_one(const Model& m, const float* kp, const float* rf, const float* /*desc*/, int row, float dist,
+                    std::vector<pcdb_vote>& out) {
+  const pcdb_params& P = m.prm;
+  Quat rq = lrf_quat(rf);
+  for (int64_t v = m.vote_off[row]; v < m.vote_off[row + 1]; ++v) {
+    uint32_t classId = m.vote_class[v];
+    float classWeight = m.vote_class_weight.empty() ? 1.0f : m.vote_class_weight[v];
+    float classSigma = classId < m.sigma2.size() ? m.sigma2[classId] : 1.0f;
+    float matching = float((1 / std::sqrt(2 * M_PI * classSigma)) * std::exp(-std::pow(dist, 2) / (2 * classSigma)));
+    float voteWeight = m.vote_weight[v];
+    float weight = 1.0f;
+    weight = P.use_class_weight ? weight * classWeight : weight;
+    weight = P.use_vote_weight ? weight * voteWeight : weight;
+    weight = P.use_matching_weight ? weight * matching : weight;
+    weight = P.use_codeword_weight ? weight * m.codeword_weight[row] : weight;
+    if (P.filter_abs_is_int) {
+      if (float(std::abs(int(dist))) > 2 * classSigma) continue;
+    } else {
+      if (std::fabs(dist) > 2 * classSigma) continue; /* :131-135 */
+    }
+    if (weight < std::numeric_limits<float>::epsilon()) continue;
+    pcdb_vote o;
+    float rot[3];
+    quat_rotate_inv(rq, &m.vote_xyz[3 * v], rot);
+    for (int a = 0; a < 3; ++a) {
+      o.position[a] = kp[a] + rot[a];
+      o.keypoint[a] = kp[a];
+      o.keypoint_training[a] = m.kp_train[3 * row + a];
+      o.bbox_size[a] = m.vote_bbox[7 * v + 4 + a];
+    }
+    Quat bq{m.vote_bbox[7 * v], m.vote_bbox[7 * v + 1], m.vote_bbox[7 * v + 2], m.vote_bbox[7 * v + 3]};
+    Quat nb = qmul(bq, rq);
+    o.bbox_quat[0] = nb.a;
+    o.bbox_quat[1] = nb.b;
+    o.bbox_quat[2] = nb.c;
+    o.bbox_quat[3] = nb.d;
+    o.weight = weight;
+    o.class_id = classId;
+    o.instance_id = m.vote_instance[v];
+    o.codeword_id = m.codeword_ids.empty() ? row : m.codeword_ids[row];
+    out.push_back(o);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* A.8  VotingMeanShift::iFindMaxima (voting/voting_mean_shift.cpp:39-177) for one class        */
+/* ------------------------------------------------------------------------------------------- */
+struct ClassVotes {
+  std::vector<int64_t> gidx; /* index into the cloud's vote array */
+  std::vector<float> pos;    /* 3 per vote */
+  std::vector<float> w;      /* working copy (re-weighted in place, voting.cpp:95 copies by value) */
+};
+
+void ms_radius(const ClassVotes& cv, const float* c, float r2, std::vector<Nbr>& out) {
+  out.clear();
+  int n = int(cv.w.size());
+  for (int i = 0; i < n; ++i) {
+    float d2 = sqdist3(c, &cv.pos[3 * i]);
+    if (d2 < r2) out.push_back({d2, i});
+  }
+  std::sort(out.begin(), out.end(), nbr_less);
+}
+
+inline float ms_kernel(int type, float x) {
+  if (type == PCDB_KERNEL_GAUSSIAN) {
+    float profile = std::exp(-0.5 * x); /* :396-400, double exp narrowed */
+    return profile;
+  }
+  return 1;
+}
+inline float ms_kernel_derivative(int type, float x) {
+  if (type == PCDB_KERNEL_GAUSSIAN) {
+    float profile = std::exp(-0.5 * x);
+    float derivative = -0.5f * profile;
+    return derivative;
+  }
+  return 1;
+}
+
+struct Vec3 {
+  float v[3];
+};
+inline float norm3(const float* a, const float* b) {
+  float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+  return std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+}
+
+float ms_density(const pcdb_params& P, float h, ClassVotes& cv, const float* pos, std::vector<int>& members,
+                 bool reweight) {
+  std::vector<Nbr> nb;
+  ms_radius(cv, pos, radius_sq(double(h)), nb);
+  members.clear();
+  if (nb.empty()) return 0;
+  float density = 0;
+  for (const Nbr& n : nb) {
+    float u = n.d2 / (h * h);
+    float weight = ms_kernel(P.ms_kernel, u) * cv.w[n.idx];
+    if (reweight) cv.w[n.idx] = weight;
+    members.push_back(n.idx);
+    density += weight;
+  }
+  return density;
+}
+
+void ms_find_maxima(const pcdb_params& P, ClassVotes& cv, std::vector<Vec3>& maxima,
+                    std::vector<std::vector<int>>& members, std::vector<std::vector<float>>& member_w) {
+  const float h = P.bandwidth; /* BinOrBandwidthType "Config": maxima_handler.cpp:509-513 */
+  const float r2 = radius_sq(double(h));
+  const int n = int(cv.w.size());
+  /* createSeeds :431-481 */
+  const float binSize = (h * 2.0f) / sqrtf(2);
+  struct Key {
+    int x, y, z;
+    bool operator<(const Key& o) const {
+      if (z < o.z) return true;
+      if ((z == o.z) && (y < o.y)) return true;
+      if ((z == o.z) && (y == o.y) && (x < o.x)) return true;
+      return false;
+    }
+  };
+  std::vector<Vec3> seeds;
+  if (binSize == 0) {
+    for (int i = 0; i < n; ++i) seeds.push_back(Vec3{{cv.pos[3 * i], cv.pos[3 * i + 1], cv.pos[3 * i + 2]}});
+  } else {
+    std::map<Key, int> bins;
+    for (int i = 0; i < n; ++i) {
+      Key k{(int)std::floor((cv.pos[3 * i] / binSize) + 0.5), (int)std::floor((cv.pos[3 * i + 1] / binSize) + 0.5),
+            (int)std::floor((cv.pos[3 * i + 2] / binSize) + 0.5)};
+      bins[k]++;
+    }
+    for (auto& kv : bins) seeds.push_back(Vec3{{kv.first.x * binSize, kv.first.y * binSize, kv.first.z * binSize}});
+  }
+  /* iDoMeanShift :201-244 / computeMeanShift :331-376 */
+  std::vector<Vec3> centers;
+  std::vector<Nbr> nb;
+  for (const Vec3& seed : seeds) {
+    float cur[3] = {seed.v[0], seed.v[1], seed.v[2]};
+    int iter = 0;
+    float diff = 0;
+    bool skip = false;
+    do {
+      ms_radius(cv, cur, r2, nb);
+      if (nb.empty()) {
+        skip = true;
+        break;
+      }
+      float shifted[3] = {0, 0, 0};
+      double totalWeight = 0;
+      for (const Nbr& q : nb) {
+        float u = q.d2 / (h * h);
+        float g = -ms_kernel_derivative(P.ms_kernel, u) * cv.w[q.idx];
+        for (int a = 0; a < 3; ++a) shifted[a] += g * cv.pos[3 * q.idx + a];
+        totalWeight += g;
+      }
+      if (totalWeight != 0) {
+        float tw = static_cast<float>(totalWeight); /* Eigen Vector3f /= takes the scalar as float */
+        for (int a = 0; a < 3; ++a) shifted[a] /= tw;
+      }
+      diff = norm3(cur, shifted);
+      for (int a = 0; a < 3; ++a) cur[a] = shifted[a];
+      iter++;
+    } while (diff > P.ms_threshold && iter <= P.ms_max_iter);
+    if (!skip) centers.push_back(Vec3{{cur[0], cur[1], cur[2]}});
+  }
+  /* densities :90-97 */
+  std::vector<float> dens;
+  std::vector<int> mem;
+  for (const Vec3& c : centers) dens.push_back(ms_density(P, h, cv, c.v, mem, false));
+  if (P.maxima_suppression == PCDB_SUPPRESS_AVERAGE) { /* maxima_handler.cpp:94-157 */
+    const int M = int(centers.size());
+    std::vector<std::vector<int>> dup(M);
+    for (int i = 0; i < M; ++i) dup[i].push_back(i);
+    std::vector<bool> isdup(M, false);
+    for (int k = 0; k < M; ++k) {
+      if (isdup[k]) continue;
+      for (int j = k + 1; j < M; ++j) {
+        if (isdup[j]) continue;
+        if (norm3(centers[k].v, centers[j].v) < h) {
+          isdup[j] = true;
+          dup[k].push_back(j);
+        }
+      }
+    }
+    std::vector<Vec3> avg;
+    for (int i = 0; i < M; ++i) {
+      if (dup[i].size() == 1)
+        avg.push_back(centers[dup[i][0]]);
+      else {
+        float a[3] = {0, 0, 0};
+        float sd = 0;
+        for (int j : dup[i]) {
+          for (int t = 0; t < 3; ++t) a[t] += centers[j].v[t] * dens[j];
+          sd += dens[j];
+        }
+        for (int t = 0; t < 3; ++t) a[t] /= sd;
+        avg.push_back(Vec3{{a[0], a[1], a[2]}});
+      }
+    }
+    dens.clear();
+    for (const Vec3& c : avg) dens.push_back(ms_density(P, h, cv, c.v, mem, false));
+    centers = avg;
+  }
+  /* suppressNeighborMaxima maxima_handler.cpp:51-92 */
+  maxima.clear();
+  {
+    std::vector<float> work(dens);
+    while (true) {
+      auto it = std::max_element(work.begin(), work.end());
+      float mx = -1;
+      if (it != work.end()) mx = *it;
+      if (mx != -1) {
+        size_t mi = it - work.begin();
+        Vec3 c = centers[mi];
+        maxima.push_back(c);
+        work[mi] = -1;
+        for (size_t i = 0; i < centers.size(); ++i)
+          if (norm3(c.v, centers[i].v) < h) work[i] = -1;
+      } else
+        break;
+    }
+  }
+  /* estimateDensityAndReweightVotes per maximum, cumulative :161-176,:289-328 */
+  members.clear();
+  member_w.clear();
+  for (const Vec3& mxp : maxima) {
+    ms_density(P, h, cv, mxp.v, mem, true);
+    members.push_back(mem);
+    std::vector<float> w;
+    for (int i : mem) w.push_back(cv.w[i]);
+    member_w.push_back(w);
+  }
+}
+
+/* symmetric 4x4 Jacobi for Utils::quatWeightedAverage (utils/utils.cpp:617-665; the reference uses
+ * Eigen::EigenSolver<Matrix4f>, eigenvector sign is solver dependent -> canonical w >= 0 here) */
+void quat_average(const std::vector<Quat>& qs, const std::vector<float>& ws, Quat& out) {
+  float S[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float value = 0;
+      for (size_t k = 0; k < qs.size(); ++k) {
+        const float qv[4] = {qs[k].a, qs[k].b, qs[k].c, qs[k].d};
+        value += ws[k] * qv[i] * qv[j];
+      }
+      S[i][j] = value;
+    }
+  double A[4][4], V[4][4];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      A[i][j] = S[i][j];
+      V[i][j] = i == j;
+    }
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < 4; ++p)
+      for (int q = p + 1; q < 4; ++q) off += std::fabs(A[p][q]);
+    if (off == 0) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        double apq = A[p][q];
+        if (apq == 0.0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (!std::isfinite(theta)) t = 0.0;
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 4; ++k) {
+          double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 4; ++k) {
+          double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        A[p][q] = A[q][p] = 0.0;
+        for (int k = 0; k < 4; ++k) {
+          double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int best = 0;
+  float maxEv = 0;
+  for (int i = 0; i < 4; ++i)
+    if (float(A[i][i]) > maxEv) {
+      maxEv = float(A[i][i]);
+      best = i;
+    }
+  double sgn = V[0][best] < 0 ? -1.0 : 1.0;
+  out = Quat{float(sgn * V[0][best]), float(sgn * V[1][best]), float(sgn * V[2][best]), float(sgn * V[3][best])};
+}
+
+/* Voting::findMaxima (voting/voting.cpp:79-328) for one cloud */
+void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv, std::vector<pcdb_maximum>& out,
+                       std::vector<int64_t>& member_idx, std::vector<float>& member_w) {
+  out.clear();
+  member_idx.clear();
+  member_w.clear();
+  std::map<unsigned, ClassVotes> by_class;
+  for (int64_t i = 0; i < nv; ++i) {
+    ClassVotes& cv = by_class[votes[i].class_id];
+    cv.gidx.push_back(i);
+    cv.pos.insert(cv.pos.end(), votes[i].position, votes[i].position + 3);
+    cv.w.push_back(votes[i].weight);
+  }
+  struct Tmp {
+    pcdb_maximum m;
+    std::vector<int64_t> idx;
+    std::vector<float> w;
+  };
+  std::vector<Tmp> all;
+  for (auto& kv : by_class) {
+    ClassVotes& cv = kv.second;
+    std::vector<Vec3> maxima;
+    std::vector<std::vector<int>> members;
+    std::vector<std::vector<float>> mw;
+    ms_find_maxima(P, cv, maxima, members, mw);
+    for (size_t i = 0; i < maxima.size(); ++i) {
+      const std::vector<int>& mem = members[i];
+      if ((int)mem.size() < P.min_votes_threshold || mem.empty()) continue;
+      std::map<unsigned, float> inst_w;
+      for (size_t t = 0; t < mem.size(); ++t) {
+        unsigned inst = votes[cv.gidx[mem[t]]].instance_id;
+        auto it = inst_w.find(inst);
+        if (it != inst_w.end())
+          it->second += mw[i][t];
+        else
+          inst_w.insert({inst, mw[i][t]});
+      }
+      unsigned max_id = 0; /* uninitialised in the reference when no weight > 0 */
+      float best_weight = 0;
+      for (auto& iw : inst_w)
+        if (iw.second > best_weight) {
+          best_weight = iw.second;
+          max_id = iw.first;
+        }
+      Tmp t;
+      std::memset(&t.m, 0, sizeof(t.m));
+      t.m.class_id = kv.first;
+      t.m.instance_id = max_id;
+      t.m.instance_weight = inst_w[max_id];
+      for (int a = 0; a < 3; ++a) t.m.position[a] = maxima[i].v[a];
+      std::vector<Quat> quats;
+      std::vector<float> weights;
+      float maxWeight = 0;
+      float size[3] = {0, 0, 0};
+      for (size_t j = 0; j < mem.size(); ++j) {
+        const pcdb_vote& v = votes[cv.gidx[mem[j]]];
+        float nw = mw[i][j];
+        quats.push_back(Quat{v.bbox_quat[0], v.bbox_quat[1], v.bbox_quat[2], v.bbox_quat[3]});
+        weights.push_back(nw);
+        for (int a = 0; a < 3; ++a) size[a] += nw * v.bbox_size[a];
+        maxWeight += nw;
+      }
+      t.m.weight = maxWeight;
+      t.m.raw_weight = maxWeight;
+      for (float& w : weights) w /= maxWeight;
+      for (int a = 0; a < 3; ++a) t.m.bbox_size[a] = size[a] / maxWeight;
+      t.m.bbox_quat[0] = 1; /* VotingMaximum ctor: identity */
+      if (P.average_rotation) {
+        Quat q;
+        quat_average(quats, weights, q);
+        t.m.bbox_quat[0] = q.a;
+        t.m.bbox_quat[1] = q.b;
+        t.m.bbox_quat[2] = q.c;
+        t.m.bbox_quat[3] = q.d;
+      }
+      t.m.n_votes = int(mem.size());
+      for (size_t j = 0; j < mem.size(); ++j) {
+        t.idx.push_back(cv.gidx[mem[j]]);
+        t.w.push_back(mw[i][j]);
+      }
+      all.push_back(std::move(t));
+    }
+  }
+  /* (cross-class filterMaxima, voting.cpp:265-268: MaxFilterType "None" on this path) */
+  std::stable_sort(all.begin(), all.end(), [](const Tmp& a, const Tmp& b) { return a.m.weight > b.m.weight; });
+  float sum = 0, sum_inst = 0; /* normalizeWeights :441-462 */
+  for (const Tmp& t : all) {
+    sum += t.m.weight;
+    sum_inst += t.m.instance_weight;
+  }
+  for (Tmp& t : all) {
+    t.m.weight = sum != 0 ? t.m.weight / sum : 0;
+    t.m.instance_weight = sum_inst != 0 ? t.m.instance_weight / sum_inst : 0;
+  }
+  float thr = P.min_threshold;
+  if (thr < 0) {
+    float mw = all.size() > 0 ? all.front().m.weight : 0.0f;
+    thr = -thr * mw;
+  }
+  std::vector<Tmp> kept;
+  for (Tmp& t : all)
+    if (t.m.weight >= thr) kept.push_back(std::move(t));
+  if (P.best_k > 0 && (int)kept.size() >= P.best_k) kept.resize(P.best_k);
+  for (Tmp& t : kept) {
+    t.m.vote_begin = (int64_t)member_idx.size();
+    member_idx.insert(member_idx.end(), t.idx.begin(), t.idx.end());
+    member_w.insert(member_w.end(), t.w.begin(), t.w.end());
+    out.push_back(t.m);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* per-cloud feature extraction: Features::operator() + removeNaNFeatures                        */
+/* (features/features.cpp:40-116, implicit_shape_model.cpp:733-927,1276-1308)                    */
+/* ------------------------------------------------------------------------------------------- */
+struct CloudFeatures {
+  std::vector<float> xyz, lrf, desc;
+  int64_t n_kp = 0, n_lrf_nb = 0, n_shot_nb = 0;
+};
+
+void compute_features_cloud(const pcdb_params& P, const float* xyz, const float* normals, const uint32_t* rgb,
+                            int n, CloudFeatures& out, double* t_keypoints_ms) {
+  out.xyz.clear();
+  out.lrf.clear();
+  out.desc.clear();
+  const bool color = P.feature_type == PCDB_FEATURE_CSHOT;
+  const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  /* removeNaNFromPointCloud (implicit_shape_model.cpp:611), filterNormals (:1040-1068) */
+  std::vector<float> pts, sxyz, snrm;
+  std::vector<uint32_t> prgb, srgb;
+  for (int i = 0; i < n; ++i) {
+    if (!finite3(xyz + 3 * i)) continue;
+    pts.insert(pts.end(), xyz + 3 * i, xyz + 3 * i + 3);
+    prgb.push_back(rgb ? rgb[i] : 0u);
+    if (!finite3(normals + 3 * i)) continue;
+    sxyz.insert(sxyz.end(), xyz + 3 * i, xyz + 3 * i + 3);
+    snrm.insert(snrm.end(), normals + 3 * i, normals + 3 * i + 3);
+    srgb.push_back(rgb ? rgb[i] : 0u);
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  Keypoints kps;
+  voxel_keypoints(pts.data(), prgb.data(), int(prgb.size()), P.leaf_size, kps);
+  if (t_keypoints_ms)
+    *t_keypoints_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const int Q = int(kps.rgb.size());
+  const int ns = int(srgb.size());
+  out.n_kp = Q;
+  CloudGrid g_lrf, g_shot;
+  g_lrf.build(sxyz.data(), ns, P.lrf_radius);
+  g_shot.build(sxyz.data(), ns, P.feature_radius);
+  std::vector<float> lrf(size_t(Q) * 9), desc(size_t(Q) * D);
+  int64_t n1 = 0, n2 = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : n1, n2)
+  for (int q = 0; q < Q; ++q) {
+    std::vector<Nbr> nb;
+    g_lrf.query(&kps.xyz[3 * q], radius_sq(P.lrf_radius), nb);
+    n1 += (int64_t)nb.size();
+    shot_lrf(sxyz.data(), nb, &kps.xyz[3 * q], P.lrf_radius, &lrf[9 * q]);
+    bool ok = std::isfinite(lrf[9 * q]) && std::isfinite(lrf[9 * q + 3]) && std::isfinite(lrf[9 * q + 6]);
+    if (!ok) {
+      desc[size_t(q) * D] = kNaNf;
+      continue;
+    }
+    g_shot.query(&kps.xyz[3 * q], radius_sq(P.feature_radius), nb);
+    n2 += (int64_t)nb.size();
+    shot_describe(color, sxyz.data(), snrm.data(), srgb.data(), nb, &kps.xyz[3 * q], kps.rgb[q], &lrf[9 * q],
+                  P.feature_radius, &desc[size_t(q) * D]);
+  }
+  out.n_lrf_nb = n1;
+  out.n_shot_nb = n2;
+  for (int q = 0; q < Q; ++q) {
+    bool ok = std::isfinite(lrf[9 * q]) && std::isfinite(lrf[9 * q + 3]) && std::isfinite(lrf[9 * q + 6]);
+    if (!ok) continue;
+    bool nan = false;
+    for (int j = 0; j < D && !nan; ++j) nan = std::isnan(desc[size_t(q) * D + j]);
+    if (nan) continue;
+    out.xyz.insert(out.xyz.end(), &kps.xyz[3 * q], &kps.xyz[3 * q] + 3);
+    out.lrf.insert(out.lrf.end(), &lrf[9 * q], &lrf[9 * q] + 9);
+    out.desc.insert(out.desc.end(), &desc[size_t(q) * D], &desc[size_t(q) * D] + D);
+  }
+}
+
+/* ActivationStrategyKNN::activateKNN for a block of queries (activation_strategy_knn.h:41-126) */
+void activate_block(const Model& m, const float* queries, int64_t Q, int k, int dist_type, bool use_ratio,
+                    float ratio_thr, int32_t* idx_out, float* dist_out, int32_t* count_out) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t q = 0; q < Q; ++q) {
+    const float* qv = queries + q * m.D;
+    int32_t* io = idx_out + q * k;
+    float* dout = dist_out + q * k;
+    for (int j = 0; j < k; ++j) {
+      io[j] = -1;
+      dout[j] = kNaNf;
+    }
+    if (m.N <= k) { /* :50-54 */
+      for (int64_t j = 0; j < m.N; ++j) {
+        io[j] = int(j);
+        dout[j] = dist_fn(dist_type, m.words.data() + j * m.D, qv, m.D);
+      }
+      count_out[q] = int(m.N);
+      continue;
+    }
+    int kk = use_ratio ? k + 1 : k;
+    Cand best[PCDB_MAX_K + 1];
+    int found = 0;
+    knn_one(qv, m.words.data(), m.N, m.D, kk, dist_type, best, found);
+    int use = std::min(found, k);
+    if (use_ratio && k == 1 && found >= 2) {
+      if (best[0].d / best[1].d > ratio_thr) use = 0; /* :75-85 */
+    }
+    for (int j = 0; j < use; ++j) {
+      io[j] = best[j].idx;
+      dout[j] = best[j].d;
+    }
+    count_out[q] = use;
+  }
+}
+
+std::string g_err;
+
+/* trained model arrays kept between orc_train and orc_train_fetch */
+struct Trained {
+  int64_t N = 0, V = 0;
+  int D = 0;
+  std::vector<float> words, vote_xyz, vote_weight, vote_bbox, vote_class_weight, kp_train, sigma2;
+  std::vector<int64_t> vote_off;
+  std::vector<uint32_t> vote_class, vote_instance;
+  std::vector<int32_t> ids;
+} g_trained;
+
+}  // namespace
+
+/* ============================================================================================ */
+/*                                         C interface                                           */
+/* ============================================================================================ */
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+void orc_default_params(pcdb_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->feature_type = PCDB_FEATURE_SHOT;
+  p->feature_radius = 0.1;
+  p->lrf_radius = double(0.2f);
+  p->leaf_size = 0.1f;
+  p->distance_type = PCDB_DIST_EUCLIDEAN;
+  p->knn_k = 1;
+  p->distance_ratio_threshold = 0.95f;
+  p->bandwidth = 0.2f;
+  p->ms_threshold = 1e-3f;
+  p->ms_max_iter = 1000;
+  p->ms_kernel = PCDB_KERNEL_GAUSSIAN;
+  p->maxima_suppression = PCDB_SUPPRESS_AVERAGE;
+  p->min_votes_threshold = 1;
+  p->best_k = -1;
+}
+
+int orc_voxel_keypoints(const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B, float leaf,
+                        float* kp_xyz_out, uint32_t* kp_rgb_out, int64_t* kp_off_out, int64_t kp_capacity) {
+  int64_t total = 0;
+  kp_off_out[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    Keypoints k;
+    int64_t s = cloud_off[b];
+    voxel_keypoints(xyz + 3 * s, rgb ? rgb + s : nullptr, int(cloud_off[b + 1] - s), leaf, k);
+    int64_t q = (int64_t)k.rgb.size();
+    if (total + q > kp_capacity) {
+      g_err = "kp_capacity too small";
+      return PCDB_E_CAPACITY;
+    }
+    std::memcpy(kp_xyz_out + 3 * total, k.xyz.data(), sizeof(float) * 3 * q);
+    if (kp_rgb_out) std::memcpy(kp_rgb_out + total, k.rgb.data(), sizeof(uint32_t) * q);
+    total += q;
+    kp_off_out[b + 1] = total;
+  }
+  return PCDB_OK;
+}
+
+int orc_radius_neighbours(const float* surf_xyz, const int64_t* surf_off, const float* kp_xyz, const int64_t* kp_off,
+                          int32_t B, double radius, int64_t* nbr_off_out, int32_t* nbr_idx_out, float* nbr_d2_out,
+                          int64_t capacity) {
+  int64_t total = 0;
+  nbr_off_out[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    CloudGrid g;
+    g.build(surf_xyz + 3 * surf_off[b], int(surf_off[b + 1] - surf_off[b]), radius);
+    std::vector<Nbr> nb;
+    for (int64_t q = kp_off[b]; q < kp_off[b + 1]; ++q) {
+      g.query(kp_xyz + 3 * q, radius_sq(radius), nb);
+      if (total + (int64_t)nb.size() > capacity) {
+        g_err = "neighbour capacity too small";
+        return PCDB_E_CAPACITY;
+      }
+      for (const Nbr& n : nb) {
+        nbr_idx_out[total] = n.idx;
+        nbr_d2_out[total] = n.d2;
+        ++total;
+      }
+      nbr_off_out[q + 1] = total;
+    }
+  }
+  return PCDB_OK;
+}
+
+int orc_shot_lrf(const float* surf_xyz, const int64_t* surf_off, const float* kp_xyz, const int64_t* kp_off,
+                 int32_t B, double radius, float* lrf9_out) {
+  for (int b = 0; b < B; ++b) {
+    CloudGrid g;
+    const float* surf = surf_xyz + 3 * surf_off[b];
+    g.build(surf, int(surf_off[b + 1] - surf_off[b]), radius);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t q = kp_off[b]; q < kp_off[b + 1]; ++q) {
+      std::vector<Nbr> nb;
+      g.query(kp_xyz + 3 * q, radius_sq(radius), nb);
+      shot_lrf(surf, nb, kp_xyz + 3 * q, radius, lrf9_out + 9 * q);
+    }
+  }
+  return PCDB_OK;
+}
+
+int orc_shot_describe(int32_t feature_type, const float* surf_xyz, const float* surf_normals,
+                      const uint32_t* surf_rgb, const int64_t* surf_off, const float* kp_xyz, const uint32_t* kp_rgb,
+                      const float* kp_lrf9, const int64_t* kp_off, int32_t B, double radius, float* desc_out) {
+  const bool color = feature_type == PCDB_FEATURE_CSHOT;
+  const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  for (int b = 0; b < B; ++b) {
+    CloudGrid g;
+    const int64_t s = surf_off[b];
+    g.build(surf_xyz + 3 * s, int(surf_off[b + 1] - s), radius);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t q = kp_off[b]; q < kp_off[b + 1]; ++q) {
+      std::vector<Nbr> nb;
+      g.query(kp_xyz + 3 * q, radius_sq(radius), nb);
+      shot_describe(color, surf_xyz + 3 * s, surf_normals + 3 * s, surf_rgb ? surf_rgb + s : nullptr, nb,
+                    kp_xyz + 3 * q, kp_rgb ? kp_rgb[q] : 0u, kp_lrf9 + 9 * q, radius, desc_out + q * D);
+    }
+  }
+  return PCDB_OK;
+}
+
+int orc_compute_features(const pcdb_params* prm, const float* xyz, const float* normals, const uint32_t* rgb,
+                         const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
+                         float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity) {
+  const int D = prm->feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  int64_t total = 0;
+  feat_off_out[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    CloudFeatures f;
+    int64_t s = cloud_off[b];
+    compute_features_cloud(*prm, xyz + 3 * s, normals + 3 * s, rgb ? rgb + s : nullptr, int(cloud_off[b + 1] - s), f,
+                           nullptr);
+    int64_t q = (int64_t)f.xyz.size() / 3;
+    if (total + q > feat_capacity) {
+      g_err = "feat_capacity too small";
+      return PCDB_E_CAPACITY;
+    }
+    std::memcpy(feat_xyz_out + 3 * total, f.xyz.data(), sizeof(float) * 3 * q);
+    std::memcpy(feat_lrf9_out + 9 * total, f.lrf.data(), sizeof(float) * 9 * q);
+    std::memcpy(feat_desc_out + D * total, f.desc.data(), sizeof(float) * size_t(D) * q);
+    total += q;
+    feat_off_out[b + 1] = total;
+  }
+  return PCDB_OK;
+}
+
+/* functor values for arbitrary pairs: rows a[i], b[i] */
+int orc_distance(const float* a, const float* b, int64_t n, int32_t D, int32_t dist_type, float* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = dist_fn(dist_type, a + i * D, b + i * D, D);
+  return PCDB_OK;
+}
+
+/* RGB->Lab (normalised L/100, a/120, b/120) and colour distance, for the reference pin */
+int orc_rgb_to_lab_normalized(const uint32_t* rgb, int64_t n, float* lab_out) {
+  for (int64_t i = 0; i < n; ++i) {
+    float L, a, b;
+    rgb2lab(rgb[i], L, a, b);
+    lab_out[3 * i] = L / 100.0f;
+    lab_out[3 * i + 1] = a / 120.0f;
+    lab_out[3 * i + 2] = b / 120.0f;
+  }
+  return PCDB_OK;
+}
+int orc_color_distance(const float* lab, const float* lab_ref, int64_t n, float* out) {
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = float(color_distance(lab[3 * i], lab[3 * i + 1], lab[3 * i + 2], lab_ref[3 * i], lab_ref[3 * i + 1],
+                                  lab_ref[3 * i + 2]));
+  return PCDB_OK;
+}
+int orc_lab_luts(float* srgb256, float* sxyz4000) {
+  std::memcpy(srgb256, lab_lut().srgb, sizeof(float) * 256);
+  std::memcpy(sxyz4000, lab_lut().sxyz, sizeof(float) * 4000);
+  return PCDB_OK;
+}
+
+/* ---- model ---------------------------------------------------------------------------------- */
+void* orc_model_create(const pcdb_params* prm, const float* words, int64_t N, int32_t D, const int64_t* vote_off,
+                       const float* vote_xyz, const float* vote_weight, const uint32_t* vote_class,
+                       const uint32_t* vote_instance, const float* vote_bbox, const float* vote_class_weight,
+                       const float* kp_train, const int32_t* codeword_ids, const float* codeword_weight,
+                       const float* class_sigma2, int32_t n_classes) {
+  Model* m = new Model();
+  m->prm = *prm;
+  m->N = N;
+  m->D = D;
+  m->words.assign(words, words + N * D);
+  m->vote_off.assign(vote_off, vote_off + N + 1);
+  int64_t V = vote_off[N];
+  m->vote_xyz.assign(vote_xyz, vote_xyz + 3 * V);
+  m->vote_weight.assign(vote_weight, vote_weight + V);
+  m->vote_class.assign(vote_class, vote_class + V);
+  m->vote_instance.assign(vote_instance, vote_instance + V);
+  m->vote_bbox.assign(vote_bbox, vote_bbox + 7 * V);
+  if (vote_class_weight) m->vote_class_weight.assign(vote_class_weight, vote_class_weight + V);
+  m->kp_train.assign(kp_train, kp_train + 3 * N);
+  if (codeword_ids) m->codeword_ids.assign(codeword_ids, codeword_ids + N);
+  if (codeword_weight)
+    m->codeword_weight.assign(codeword_weight, codeword_weight + N);
+  else
+    m->codeword_weight.assign(N, 1.0f);
+  m->sigma2.assign(class_sigma2, class_sigma2 + n_classes);
+  return m;
+}
+void orc_model_set_params(void* model, const pcdb_params* prm) { static_cast<Model*>(model)->prm = *prm; }
+void orc_model_destroy(void* model) { delete static_cast<Model*>(model); }
+
+int orc_knn(void* model, const float* queries, int64_t Q, int32_t k, int32_t dist_type, int32_t /*mode*/,
+            int32_t* idx_out, float* dist_out, int32_t* count_out) {
+  const Model& m = *static_cast<Model*>(model);
+  if (k < 1 || k > PCDB_MAX_K) {
+    g_err = "k out of range";
+    return PCDB_E_INVALID;
+  }
+  activate_block(m, queries, Q, k, dist_type, m.prm.use_distance_ratio != 0, m.prm.distance_ratio_threshold, idx_out,
+                 dist_out, count_out);
+  return PCDB_OK;
+}
+
+int orc_cast_votes(void* model, const float* feat_xyz, const float* feat_lrf9, const int64_t* feat_off, int32_t B,
+                   const int32_t* knn_idx, const float* knn_dist, const int32_t* knn_count, int32_t k,
+                   pcdb_vote* votes_out, int64_t* vote_off_out, int64_t vote_capacity) {
+  const Model& m = *static_cast<Model*>(model);
+  int64_t total = 0;
+  vote_off_out[0] = 0;
+  std::vector<pcdb_vote> tmp;
+  for (int b = 0; b < B; ++b) {
+    for (int64_t q = feat_off[b]; q < feat_off[b + 1]; ++q) {
+      for (int j = 0; j < knn_count[q]; ++j) {
+        tmp.clear();
+        cast_votes_one(m, feat_xyz + 3 * q, feat_lrf9 + 9 * q, nullptr, knn_idx[q * k + j], knn_dist[q * k + j], tmp);
+        if (total + (int64_t)tmp.size() > vote_capacity) {
+          g_err = "vote_capacity too small";
+          return PCDB_E_CAPACITY;
+        }
+        for (const pcdb_vote& v : tmp) votes_out[total++] = v;
+      }
+    }
+    vote_off_out[b + 1] = total;
+  }
+  return PCDB_OK;
+}
+
+static std::vector<int64_t> g_member_idx;
+static std::vector<float> g_member_w;
+
+int orc_find_maxima(void* model, const pcdb_vote* votes, const int64_t* vote_off, int32_t B,
+                    pcdb_maximum* maxima_out, int64_t* maxima_off_out, int64_t maxima_capacity) {
+  const Model& m = *static_cast<Model*>(model);
+  g_member_idx.clear();
+  g_member_w.clear();
+  int64_t total = 0;
+  maxima_off_out[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    std::vector<pcdb_maximum> mx;
+    std::vector<int64_t> mi;
+    std::vector<float> mw;
+    find_maxima_cloud(m.prm, votes + vote_off[b], vote_off[b + 1] - vote_off[b], mx, mi, mw);
+    if (total + (int64_t)mx.size() > maxima_capacity) {
+      g_err = "maxima_capacity too small";
+      return PCDB_E_CAPACITY;
+    }
+    for (pcdb_maximum& x : mx) {
+      x.vote_begin += (int64_t)g_member_idx.size();
+      maxima_out[total++] = x;
+    }
+    for (int64_t i : mi) g_member_idx.push_back(i + vote_off[b]);
+    g_member_w.insert(g_member_w.end(), mw.begin(), mw.end());
+    maxima_off_out[b + 1] = total;
+  }
+  return PCDB_OK;
+}
+
+int orc_get_maximum_votes(int64_t* vote_index_out, float* vote_weight_out, int64_t capacity, int64_t* n_out) {
+  *n_out = (int64_t)g_member_idx.size();
+  if (capacity < *n_out) return PCDB_E_CAPACITY;
+  std::memcpy(vote_index_out, g_member_idx.data(), sizeof(int64_t) * g_member_idx.size());
+  std::memcpy(vote_weight_out, g_member_w.data(), sizeof(float) * g_member_w.size());
+  return PCDB_OK;
+}
+
+/* ImplicitShapeModel::detect for B clouds, sequential over clouds as eval_tool does
+ * (src/eval_tool/eval_classification.cpp:347-356); OpenMP inside the stages as the reference:
+ * over keypoints (PCL *OMP estimators), over features (codebook.cpp:483); mean-shift sequential. */
+int orc_classify_batch(void* model, const float* xyz, const float* normals, const uint32_t* rgb,
+                       const int64_t* cloud_off, int32_t B, int32_t* label_out, pcdb_maximum* maxima_out,
+                       int64_t* maxima_off_out, int64_t maxima_capacity, double* times_ms_out, int64_t* counts_out) {
+  const Model& m = *static_cast<Model*>(model);
+  const pcdb_params& P = m.prm;
+  double t_feat = 0, t_kp = 0, t_vote = 0, t_max = 0;
+  int64_t total_max = 0;
+  int64_t c_kp = 0, c_feat = 0, c_nl = 0, c_ns = 0, c_votes = 0;
+  if (maxima_off_out) maxima_off_out[0] = 0;
+  auto T0 = std::chrono::steady_clock::now();
+  for (int b = 0; b < B; ++b) {
+    auto t0 = std::chrono::steady_clock::now();
+    CloudFeatures f;
+    int64_t s = cloud_off[b];
+    double kp_ms = 0;
+    compute_features_cloud(P, xyz + 3 * s, normals + 3 * s, rgb ? rgb + s : nullptr, int(cloud_off[b + 1] - s), f,
+                           &kp_ms);
+    auto t1 = std::chrono::steady_clock::now();
+    t_kp += kp_ms;
+    t_feat += std::chrono::duration<double, std::milli>(t1 - t0).count() - kp_ms;
+    int64_t Q = (int64_t)f.xyz.size() / 3;
+    c_kp += f.n_kp;
+    c_feat += Q;
+    c_nl += f.n_lrf_nb;
+    c_ns += f.n_shot_nb;
+    const int k = P.knn_k;
+    std::vector<int32_t> idx(size_t(Q) * k), cnt(Q);
+    std::vector<float> dist(size_t(Q) * k);
+    std::vector<pcdb_vote> votes;
+    if (m.N > 0 && Q > 0) {
+      activate_block(m, f.desc.data(), Q, k, P.distance_type, P.use_distance_ratio != 0, P.distance_ratio_threshold,
+                     idx.data(), dist.data(), cnt.data());
+      for (int64_t q = 0; q < Q; ++q)
+        for (int j = 0; j < cnt[q]; ++j) {
+          /* castVotes recomputes the functor value (codeword_distribution.cpp:87) — same value */
+          cast_votes_one(m, &f.xyz[3 * q], &f.lrf[9 * q], nullptr, idx[q * k + j], dist[q * k + j], votes);
+        }
+    }
+    c_votes += (int64_t)votes.size();
+    auto t2 = std::chrono::steady_clock::now();
+    t_vote += std::chrono::duration<double, std::milli>(t2 - t1).count();
+    std::vector<pcdb_maximum> mx;
+    std::vector<int64_t> mi;
+    std::vector<float> mw;
+    find_maxima_cloud(P, votes.data(), (int64_t)votes.size(), mx, mi, mw);
+    auto t3 = std::chrono::steady_clock::now();
+    t_max += std::chrono::duration<double, std::milli>(t3 - t2).count();
+    label_out[b] = mx.empty() ? -1 : int32_t(mx[0].class_id); /* eval_classification.cpp:412-417 */
+    if (maxima_out) {
+      if (total_max + (int64_t)mx.size() > maxima_capacity) {
+        g_err = "maxima_capacity too small";
+        return PCDB_E_CAPACITY;
+      }
+      for (const pcdb_maximum& x : mx) maxima_out[total_max++] = x;
+      maxima_off_out[b + 1] = total_max;
+    }
+  }
+  if (times_ms_out) {
+    times_ms_out[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+    times_ms_out[1] = t_feat;
+    times_ms_out[2] = t_kp;
+    times_ms_out[3] = 0;
+    times_ms_out[4] = 0;
+    times_ms_out[5] = t_vote;
+    times_ms_out[6] = t_max;
+  }
+  if (counts_out) {
+    counts_out[0] = c_kp;
+    counts_out[1] = c_feat;
+    counts_out[2] = c_nl;
+    counts_out[3] = c_ns;
+    counts_out[4] = c_votes;
+  }
+  return PCDB_OK;
+}
+
+/* ---- training: ImplicitShapeModel::train + Codebook::activate ------------------------------- */
+/* (implicit_shape_model.cpp:252-500, codebook/codebook.cpp:64-368,                              */
+/*  codebook/codeword_distribution.cpp:37-71,171-243).  Clustering "None", ranking "Uniform".    */
+/* Features must be given class-major (ascending class id, then model, then feature) — the       */
+/* iteration order of the reference's std::map.  cloud_* arrays have one entry per training      */
+/* cloud: class, instance, bbox (pos3, quat wxyz 4, size3).                                      */
+int orc_aabb(const float* xyz, int64_t n, float* bbox10) { /* Utils::computeAABB utils.cpp:221-233 */
+  float mn[3], mx[3];
+  bool any = false;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!finite3(p)) continue;
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = any ? std::min(mn[a], p[a]) : p[a];
+      mx[a] = any ? std::max(mx[a], p[a]) : p[a];
+    }
+    any = true;
+  }
+  if (!any) return PCDB_E_INVALID;
+  for (int a = 0; a < 3; ++a) {
+    float size = mx[a] - mn[a];
+    bbox10[7 + a] = size;
+    bbox10[a] = mn[a] + (size / 2);
+  }
+  bbox10[3] = 1;
+  bbox10[4] = bbox10[5] = bbox10[6] = 0;
+  return PCDB_OK;
+}
+
+int orc_train(const pcdb_params* prm, const float* feat_xyz, const float* feat_lrf9, const float* feat_desc,
+              const int64_t* feat_off, int32_t n_clouds, const uint32_t* cloud_class, const uint32_t* cloud_instance,
+              const float* cloud_bbox10, int32_t n_classes, int64_t* N_out, int64_t* V_out) {
+  const pcdb_params& P = *prm;
+  const int D = P.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  const int64_t F = feat_off[n_clouds];
+  const int k = P.knn_k;
+  for (int c = 1; c < n_clouds; ++c)
+    if (cloud_class[c] < cloud_class[c - 1]) {
+      g_err = "training clouds must be class-major";
+      return PCDB_E_INVALID;
+    }
+  /* codewords = features (clustering None): ids 0..F-1 (codeword.cpp:28-29) */
+  Model cw;
+  cw.prm = P;
+  cw.N = F;
+  cw.D = D;
+  cw.words.assign(feat_desc, feat_desc + F * D);
+  std::vector<int32_t> idx(size_t(F) * k), cnt(F);
+  std::vector<float> dist(size_t(F) * k);
+  /* training-time activation: distance ratio is detection-only (activation_strategy_knn.h:67) */
+  activate_block(cw, feat_desc, F, k, P.distance_type, false, 0.f, idx.data(), dist.data(), cnt.data());
+  struct Entry {
+    std::vector<float> votes, bbox;
+    std::vector<uint32_t> cls, inst;
+    std::vector<int64_t> feat; /* activating feature (for computeWeights) */
+    std::vector<int> cloud;
+  };
+  std::map<int, Entry> distribution;
+  std::vector<float> sigma2(n_classes, 1.0f);
+  std::vector<int> feat_cloud(F);
+  for (int c = 0; c < n_clouds; ++c)
+    for (int64_t f = feat_off[c]; f < feat_off[c + 1]; ++f) feat_cloud[f] = c;
+  int c0 = 0;
+  while (c0 < n_clouds) {
+    int c1 = c0;
+    unsigned cls = cloud_class[c0];
+    while (c1 < n_clouds && cloud_class[c1] == cls) ++c1;
+    int64_t num_features = feat_off[c1] - feat_off[c0];
+    int max_elements = int(std::sqrt(double(num_features)));
+    std::vector<int64_t> allModelFeatures;
+    std::vector<int> allActivated;
+    for (int c = c0; c < c1; ++c) {
+      const float* bb = cloud_bbox10 + 10 * c;
+      for (int64_t f = feat_off[c]; f < feat_off[c + 1]; ++f) {
+        Quat rq = lrf_quat(feat_lrf9 + 9 * f);
+        for (int j = 0; j < cnt[f]; ++j) {
+          Entry& e = distribution[idx[f * k + j]];
+          /* CodewordDistribution::addCodeword :37-71 */
+          float vote[3] = {bb[0] - feat_xyz[3 * f], bb[1] - feat_xyz[3 * f + 1], bb[2] - feat_xyz[3 * f + 2]};
+          float rot[3];
+          quat_rotate(rq, vote, rot);
+          e.votes.insert(e.votes.end(), rot, rot + 3);
+          e.cls.push_back(cls);
+          e.inst.push_back(cloud_instance[c]);
+          Quat bq{bb[3], bb[4], bb[5], bb[6]};
+          Quat nq = qmul(bq, qconj(rq));
+          float nb[7] = {nq.a, nq.b, nq.c, nq.d, bb[7], bb[8], bb[9]};
+          e.bbox.insert(e.bbox.end(), nb, nb + 7);
+          e.feat.push_back(f);
+          e.cloud.push_back(c);
+        }
+        if ((int)allActivated.size() < max_elements)
+          for (int j = 0; j < cnt[f]; ++j) allActivated.push_back(idx[f * k + j]);
+      }
+      if ((int)allModelFeatures.size() < max_elements)
+        for (int64_t f = feat_off[c]; f < feat_off[c + 1]; ++f) allModelFeatures.push_back(f);
+    }
+    /* class variance codebook.cpp:166-193 */
+    float sum = 0;
+    std::vector<float> distances;
+    for (int64_t f : allModelFeatures)
+      for (int w : allActivated) {
+        float d = dist_fn(P.distance_type, feat_desc + f * D, feat_desc + int64_t(w) * D, D);
+        sum += d;
+        distances.push_back(d);
+      }
+    int num = int(allModelFeatures.size() * allActivated.size());
+    float mean = sum / num;
+    float variance = 0;
+    for (float d : distances) {
+      float diff = d - mean;
+      variance += diff * diff;
+    }
+    variance /= num - 1;
+    if (cls < (unsigned)n_classes) sigma2[cls] = variance;
+    c0 = c1;
+  }
+  /* clean-up for KNN k == 1 (codebook.cpp:201-224) */
+  if (k == 1) {
+    for (auto it = distribution.begin(); it != distribution.end();)
+      if (it->second.cls.size() != 1)
+        it = distribution.erase(it);
+      else
+        ++it;
+  }
+  Trained& T = g_trained;
+  T = Trained();
+  T.D = D;
+  T.sigma2 = sigma2;
+  T.vote_off.push_back(0);
+  for (auto& kv : distribution) {
+    const Entry& e = kv.second;
+    const int nv = int(e.cls.size());
+    T.ids.push_back(kv.first);
+    T.words.insert(T.words.end(), feat_desc + int64_t(kv.first) * D, feat_desc + int64_t(kv.first + 1) * D);
+    T.kp_train.insert(T.kp_train.end(), feat_xyz + 3 * int64_t(kv.first), feat_xyz + 3 * int64_t(kv.first) + 3);
+    /* computeWeights codeword_distribution.cpp:171-243 */
+    for (int i = 0; i < nv; ++i) {
+      std::vector<float> lw;
+      const float* bbi = cloud_bbox10 + 10 * e.cloud[i];
+      for (int j = 0; j < nv; ++j) {
+        int64_t f = e.feat[j];
+        Quat rq = lrf_quat(feat_lrf9 + 9 * f);
+        float rot[3];
+        quat_rotate_inv(rq, &e.votes[3 * i], rot);
+        float center[3] = {feat_xyz[3 * f] + rot[0], feat_xyz[3 * f + 1] + rot[1], feat_xyz[3 * f + 2] + rot[2]};
+        float d = norm3(center, bbi);
+        const float sigma = 0.5f;
+        lw.push_back(float(std::exp((-1 * (d * d)) / (sigma * sigma))));
+      }
+      std::sort(lw.begin(), lw.end());
+      float median = lw.size() % 2 == 0 ? (lw[lw.size() / 2 - 1] + lw[lw.size() / 2]) / 2 : lw[lw.size() / 2];
+      T.vote_weight.push_back(median);
+    }
+    T.vote_xyz.insert(T.vote_xyz.end(), e.votes.begin(), e.votes.end());
+    T.vote_bbox.insert(T.vote_bbox.end(), e.bbox.begin(), e.bbox.end());
+    T.vote_class.insert(T.vote_class.end(), e.cls.begin(), e.cls.end());
+    T.vote_instance.insert(T.vote_instance.end(), e.inst.begin(), e.inst.end());
+    T.vote_off.push_back((int64_t)T.vote_class.size());
+  }
+  T.N = (int64_t)T.ids.size();
+  T.V = (int64_t)T.vote_class.size();
+  T.vote_class_weight.assign(T.V, 1.0f); /* statistical weights (codebook.cpp:226-366): UseClassWeight=false on this path */
+  *N_out = T.N;
+  *V_out = T.V;
+  return PCDB_OK;
+}
+
+int orc_train_fetch(float* words, int64_t* vote_off, float* vote_xyz, float* vote_weight, uint32_t* vote_class,
+                    uint32_t* vote_instance, float* vote_bbox, float* vote_class_weight, float* kp_train,
+                    int32_t* codeword_ids, float* class_sigma2, int32_t n_classes) {
+  const Trained& T = g_trained;
+  std::memcpy(words, T.words.data(), sizeof(float) * T.words.size());
+  std::memcpy(vote_off, T.vote_off.data(), sizeof(int64_t) * T.vote_off.size());
+  std::memcpy(vote_xyz, T.vote_xyz.data(), sizeof(float) * T.vote_xyz.size());
+  std::memcpy(vote_weight, T.vote_weight.data(), sizeof(float) * T.vote_weight.size());
+  std::memcpy(vote_class, T.vote_class.data(), sizeof(uint32_t) * T.vote_class.size());
+  std::memcpy(vote_instance, T.vote_instance.data(), sizeof(uint32_t) * T.vote_instance.size());
+  std::memcpy(vote_bbox, T.vote_bbox.data(), sizeof(float) * T.vote_bbox.size());
+  std::memcpy(vote_class_weight, T.vote_class_weight.data(), sizeof(float) * T.vote_class_weight.size());
+  std::memcpy(kp_train, T.kp_train.data(), sizeof(float) * T.kp_train.size());
+  std::memcpy(codeword_ids, T.ids.data(), sizeof(int32_t) * T.ids.size());
+  for (int c = 0; c < n_classes; ++c) class_sigma2[c] = c < (int)T.sigma2.size() ? T.sigma2[c] : 1.0f;
+  return PCDB_OK;
+}
+
+/* Per-shard top-k merge */
+int orc_merge_topk(const int32_t* cand_idx, const float* cand_dist, int32_t S, int64_t Q, int32_t k, int32_t* idx_out,
+                   float* dist_out) {
+  for (int64_t q = 0; q < Q; ++q) {
+    std::vector<Cand> c;
+    for (int s = 0; s < S; ++s)
+      for (int j = 0; j < k; ++j) {
+        int64_t o = (int64_t(s) * Q + q) * k + j;
+        if (cand_idx[o] >= 0) c.push_back({cand_dist[o], cand_idx[o]});
+      }
+    std::sort(c.begin(), c.end(), cand_less);
+    for (int j = 0; j < k; ++j) {
+      idx_out[q * k + j] = j < (int)c.size() ? c[j].idx : -1;
+      dist_out[q * k + j] = j < (int)c.size() ? c[j].d : kNaNf;
+    }
+  }
+  return PCDB_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,637 @@
+// knn_gemm.cu — K6: codebook activation as a dense contraction on the 5th-generation tensor cores.
+//
+// Replaces the FLANN index search behind ActivationStrategyKNN::activateKNN
+// (activation_strategy/activation_strategy_knn.h:57-92; index built at utils/flann_helper.cpp:21-70) for
+// DistanceType "Euclidean":  d(q,c) = |q|^2 + |c|^2 - 2 q.c.  The q.c term is an fp16 x fp16 -> fp32 GEMM issued with
+// tcgen05.mma (cta_group::1, M=128, N=256, K=16) from TMA-staged, 128B-swizzled shared-memory tiles with the
+// accumulator double-buffered in TMEM.  The M x N score matrix is never written: four epilogue warps read each
+// accumulator tile back with tcgen05.ld, add |c|^2 and keep, per query row, every column whose approximate distance
+// is within a RIGOROUS error margin of the running k-th best.  Those candidates are re-ranked with the exact FLANN
+// fp32 arithmetic (knn_scan.cu:k_rerank), so the neighbour set equals the exact scan's.
+//
+// Tiling: one CTA owns a 128-query tile whose fp16 descriptors stay RESIDENT in shared memory for the whole sweep
+// (D=352: 6 K-blocks of 64, the last one half used — the TMA zero-fills columns >= D, and only 2 of its 4 MMAs are
+// issued, so no flop is wasted on padding) while 256-codeword tiles stream through a 4-stage mbarrier ring.  Only the
+// codebook side is streamed, which halves the L2->SM traffic of a textbook 128x256 GEMM.  For D=1344 the query tile
+// does not fit and both operands stream.  All CTAs sweep the codebook in the same order, so each codebook tile is
+// fetched from HBM roughly once and shared through the 126 MB L2.
+//
+// Error margin (DESIGN.md "activation"): with qh = fp16(q), ch = fp16(c),
+//   |q.c - fl(qh.ch)| <= |q-qh| |c| + |qh| |c-ch| + |q-qh| |c-ch| + D 2^-22 |qh| |ch|
+// per-query norms are computed in the query-prep kernel, codebook maxima at upload time.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "stages.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int THREADS = 256;
+constexpr int A_BOX_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_BOX_BYTES = BN * BK * 2;  // 32 KB
+constexpr int KB_RES_MAX = 6;             // resident K-blocks (D <= 384)
+constexpr int CAND_CAP = 64;              // candidates per (query, codebook split)
+constexpr unsigned TMEM_COLS = 512;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must end in a trap (an error the host sees), never in a hung GPU
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_ns() - t0 > 4000000000ull) {  // 4 s
+      printf("pcdb200 knn_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                           unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, float* v) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO in [16,30) (unused for swizzled K-major, set to 1), SBO = 1024 B (8 rows x 128 B) in [32,46), version 1 in
+// [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (unsigned long long)1 << 16;
+  d |= (unsigned long long)(1024 >> 4) << 32;
+  d |= (unsigned long long)1 << 46;
+  d |= (unsigned long long)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major,
+// N>>3 in [17,23), M>>4 in [24,29).
+constexpr unsigned kIdesc = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+
+struct GemmArgs {
+  long long Q, N;
+  int D;
+  int n_mtiles, n_ntiles, tiles_per_split, n_splits;
+  const float* cnorm;    // |c|^2, padded to a multiple of BN with +inf
+  const float* margin;   // per query: 2 * (bound on |approx - exact|)
+  int* cand_idx;         // [Q][S][CAND_CAP]
+  float* cand_apx;
+  int* cand_cnt;         // [S][Q]
+  float* cand_thr;       // [S][Q]
+};
+
+struct __align__(8) Barriers {
+  unsigned long long full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
+  unsigned tmem_base;
+};
+
+template <bool A_RES, int KT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // layout: [A resident: KB_RES_MAX boxes]? [STAGES x (A box if !A_RES) + B box] [barriers]
+  unsigned char* a_res = smem;
+  unsigned char* stage0 = smem + (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0);
+  constexpr int STAGE_BYTES = B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(stage0 + STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = (g.D + BK - 1) / BK;
+  const int k_steps_last = (g.D - (KB - 1) * BK) / UMMA_K;
+  const int n_units = g.n_mtiles * g.n_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    mbar_init(&bars->a_full, 1);
+    mbar_init(&bars->a_empty, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (one elected lane)
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0, a_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int mt = unit % g.n_mtiles, split = unit / g.n_mtiles;
+        const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
+        if (A_RES) {
+          mbar_wait(&bars->a_empty, a_phase ^ 1);  // previous unit's MMAs are done with the resident tile
+          mbar_expect_tx(&bars->a_full, (unsigned)(KB * A_BOX_BYTES));
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_res + kb * A_BOX_BYTES, &map_a, &bars->a_full, kb * BK, mt * BM);
+          a_phase ^= 1;
+        }
+        for (int t = t0; t < t1; ++t)
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            unsigned char* sb = stage0 + stage * STAGE_BYTES;
+            mbar_expect_tx(&bars->full[stage], (unsigned)STAGE_BYTES);
+            tma_load_2d(sb, &map_b, &bars->full[stage], kb * BK, t * BN);
+            if (!A_RES) tma_load_2d(sb + B_BOX_BYTES, &map_a, &bars->full[stage], kb * BK, mt * BM);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one elected lane)
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      unsigned phase = 0, acc_phase = 0, a_phase = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int split = unit / g.n_mtiles;
+        const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
+        if (A_RES) {
+          mbar_wait(&bars->a_full, a_phase);
+          a_phase ^= 1;
+        }
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const unsigned tmem_d = tmem_base + (unsigned)(acc * BN);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            unsigned char* sb = stage0 + stage * STAGE_BYTES;
+            const unsigned a_addr = A_RES ? smem_u32(a_res + kb * A_BOX_BYTES) : smem_u32(sb + B_BOX_BYTES);
+            const unsigned b_addr = smem_u32(sb);
+            const int ks = (kb == KB - 1) ? k_steps_last : (BK / UMMA_K);
+            for (int k = 0; k < ks; ++k) {
+              // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
+              tc_mma_f16(tmem_d, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2),
+                         kIdesc, (kb | k) ? 1u : 0u);
+            }
+            tc_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+        if (A_RES) tc_commit(&bars->a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: TMEM -> registers -> running candidate filter
+    const int grp = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    unsigned acc_phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int mt = unit % g.n_mtiles, split = unit / g.n_mtiles;
+      const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
+      const long long row = (long long)mt * BM + grp * 32 + lane;
+      const bool active = row < g.Q;
+      const float margin = active ? g.margin[row] : 0.f;
+      float best[KT];
+#pragma unroll
+      for (int i = 0; i < KT; ++i) best[i] = __int_as_float(0x7f800000);
+      float thr = __int_as_float(0x7f800000);
+      int cnt = 0;
+      const size_t cbase = active ? ((size_t)row * g.n_splits + split) * CAND_CAP : 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const unsigned taddr = tmem_base + ((unsigned)(grp * 32) << 16) + (unsigned)(acc * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tc_ld_32x32b_x32(taddr + c * 32, v);
+          const int n_base = t * BN + c * 32;
+          const float4* cn4 = reinterpret_cast<const float4*>(g.cnorm + n_base);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cn = __ldg(cn4 + j4);
+            const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d = fmaf(-2.f, v[j4 * 4 + e], cnv[e]);
+              if (d <= thr) {
+                const int n = n_base + j4 * 4 + e;
+                if (active && n < g.N) {
+                  if (cnt < CAND_CAP) {
+                    g.cand_idx[cbase + cnt] = n;
+                    g.cand_apx[cbase + cnt] = d;
+                  }
+                  ++cnt;
+                  float x = d;
+#pragma unroll
+                  for (int i = 0; i < KT; ++i) {
+                    float lo = fminf(best[i], x);
+                    x = fmaxf(best[i], x);
+                    best[i] = lo;
+                  }
+                  thr = best[KT - 1] + margin;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars->tmem_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (active) {
+        g.cand_cnt[(size_t)split * g.Q + row] = cnt;
+        g.cand_thr[(size_t)split * g.Q + row] = thr;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ---- codebook / query preparation ------------------------------------------------------------------------------
+// one warp per row: fp16 copy, |row|^2 (double accumulate), |row|, |row - fp16(row)|
+__global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, __half* xh, float* norm2,
+                            float* norm, float* err) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  double s2 = 0, e2 = 0, h2 = 0;
+  for (int j = lane; j < D; j += 32) {
+    float v = x[r * D + j];
+    __half h = __float2half_rn(v);
+    xh[r * D + j] = h;
+    float hv = __half2float(h);
+    s2 += (double)v * v;
+    h2 += (double)hv * hv;
+    double dd = (double)v - (double)hv;
+    e2 += dd * dd;
+  }
+  s2 = warp_sum(s2);
+  e2 = warp_sum(e2);
+  h2 = warp_sum(h2);
+  if (lane == 0) {
+    if (norm2) norm2[r] = (float)s2;
+    norm[r] = (float)sqrt(h2) * 1.0000002f;   // |fp16(row)|, rounded up
+    err[r] = (float)sqrt(e2) * 1.0000002f;    // |row - fp16(row)|, rounded up
+  }
+}
+
+__global__ void k_pad_inf(float* a, long long from, long long to) {
+  long long i = from + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < to) a[i] = __int_as_float(0x7f800000);
+}
+
+__global__ void k_max2(const float* __restrict__ a, const float* __restrict__ b, long long n, unsigned* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  float va = i < n ? a[i] : 0.f, vb = i < n ? b[i] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, o));
+    vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], __float_as_uint(va));  // non-negative floats order like their bit patterns
+    atomicMax(&out[1], __float_as_uint(vb));
+  }
+}
+
+// margin[q] = 2 * eps_d(q); eps_d = 2 * eps_dot + cnorm rounding
+__global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restrict__ qerr, long long Q, int D,
+                         float cmax_h, float cerr_max, float cmax2, float* margin) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  // |q.c - fl(qh.ch)| <= |q-qh||c| + |qh||c-ch| + accumulation error; |c| <= |ch| + |c-ch|
+  double cmax = (double)cmax_h + (double)cerr_max;
+  double eps_dot = (double)qerr[q] * cmax + (double)qnorm_h[q] * (double)cerr_max +
+                   (double)D * 2.384185791015625e-07 /* 2^-22 */ * (double)qnorm_h[q] * (double)cmax_h;
+  double eps_d = 2.0 * eps_dot + 2.0 * 5.9604644775390625e-08 /* 2^-24 */ * ((double)cmax2 + 2.0);
+  margin[q] = (float)(2.0 * eps_d * 1.0001);
+}
+
+// queries whose candidate list overflowed in some split -> exact-scan fallback list
+__global__ void k_overflow_flags(const int* __restrict__ cand_cnt, int S, long long Q, int cap, int* flag) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q > Q) return;
+  int f = 0;
+  if (q < Q)
+    for (int s = 0; s < S; ++s) f |= cand_cnt[(size_t)s * Q + q] > cap;
+  flag[q] = f;
+}
+__global__ void k_overflow_gather(const int* __restrict__ flag, const int* __restrict__ pos, long long Q, int D,
+                                  const float* __restrict__ queries, int* list, float* out) {
+  const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q || !flag[q]) return;
+  const int o = pos[q];
+  if (lane == 0) list[o] = (int)q;
+  for (int j = lane; j < D; j += 32) out[(size_t)o * D + j] = queries[q * D + j];
+}
+__global__ void k_overflow_scatter(const int* __restrict__ list, int n, int k, const int* __restrict__ idx,
+                                   const float* __restrict__ dist, const int* __restrict__ cnt, int* idx_out,
+                                   float* dist_out, int* cnt_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int q = list[i];
+  for (int j = 0; j < k; ++j) {
+    idx_out[(size_t)q * k + j] = idx[(size_t)i * k + j];
+    dist_out[(size_t)q * k + j] = dist[(size_t)i * k + j];
+  }
+  cnt_out[q] = cnt[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return ctx->fail(PCDB_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx->fail(PCDB_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return PCDB_OK;
+}
+
+struct GemmState {
+  CUtensorMap map_b;
+  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  float cmax_h = 0, cerr_max = 0, cmax2 = 0;
+};
+// one per context, keyed by pointer (contexts are few and long-lived)
+std::vector<std::pair<pcdb_ctx*, GemmState*>> g_states;
+GemmState* state_of(pcdb_ctx* ctx) {
+  for (auto& p : g_states)
+    if (p.first == ctx) return p.second;
+  g_states.push_back({ctx, new GemmState()});
+  return g_states.back().second;
+}
+
+template <bool A_RES, int KT>
+int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, int grid) {
+  const size_t smem = 1024 + (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0) +
+                      (size_t)STAGES * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
+  PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_knn_gemm<A_RES, KT><<<grid, THREADS, smem, ctx->stream>>>(map_a, map_b, g);
+  PCDB_LAUNCH_CHECK();
+  return PCDB_OK;
+}
+
+template <bool A_RES>
+int launch_gemm_kt(pcdb_ctx* ctx, int K, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g,
+                   int grid) {
+  if (K <= 1) return launch_gemm<A_RES, 1>(ctx, map_a, map_b, g, grid);
+  if (K <= 2) return launch_gemm<A_RES, 2>(ctx, map_a, map_b, g, grid);
+  if (K <= 4) return launch_gemm<A_RES, 4>(ctx, map_a, map_b, g, grid);
+  if (K <= 8) return launch_gemm<A_RES, 8>(ctx, map_a, map_b, g, grid);
+  return launch_gemm<A_RES, 17>(ctx, map_a, map_b, g, grid);
+}
+
+}  // namespace
+
+bool gemm_supported(const pcdb_ctx* ctx) { return ctx->cb.gemm_ready; }
+
+// fp16 copy of the codebook, |c|^2, error maxima and the codebook-side tensor map (called by pcdb_set_codebook)
+int gemm_prepare_codebook(pcdb_ctx* ctx) {
+  Codebook_d& cb = ctx->cb;
+  cudaStream_t st = ctx->stream;
+  cb.gemm_ready = false;
+  if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
+  GemmState* gs = state_of(ctx);
+  const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
+  PCDB_CUDA(cb.words_h.ensure(sizeof(__half) * (size_t)cb.N * cb.D + 256));
+  PCDB_CUDA(cb.cnorm.ensure(sizeof(float) * (n_pad + 4)));
+  PCDB_CUDA(gs->cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
+  PCDB_CUDA(gs->cerr.ensure(sizeof(float) * (cb.N + 1)));
+  PCDB_CUDA(ctx->ws.scalars.ensure(256));
+  k_prep_rows<<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, cb.words_h.as<__half>(),
+                                                    cb.cnorm.as<float>(), gs->cnorm_h.as<float>(),
+                                                    gs->cerr.as<float>());
+  PCDB_LAUNCH_CHECK();
+  if (n_pad > cb.N) {
+    k_pad_inf<<<cdiv(n_pad - cb.N, 256), 256, 0, st>>>(cb.cnorm.as<float>(), cb.N, n_pad);
+    PCDB_LAUNCH_CHECK();
+  }
+  unsigned* mx = reinterpret_cast<unsigned*>(ctx->ws.scalars.as<char>() + 128);
+  PCDB_CUDA(cudaMemsetAsync(mx, 0, 16, st));
+  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(gs->cnorm_h.as<float>(), gs->cerr.as<float>(), cb.N, mx);
+  PCDB_LAUNCH_CHECK();
+  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(cb.cnorm.as<float>(), cb.cnorm.as<float>(), cb.N, mx + 2);
+  PCDB_LAUNCH_CHECK();
+  float h[4];
+  PCDB_CUDA(cudaMemcpyAsync(h, mx, 16, cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  gs->cmax_h = h[0];
+  gs->cerr_max = h[1];
+  gs->cmax2 = h[2];
+  if (!std::isfinite(h[0]) || !std::isfinite(h[2])) return PCDB_OK;  // non-finite codewords: scan path only
+  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, cb.D, BN));
+  cb.gemm_ready = true;
+  return PCDB_OK;
+}
+
+int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool use_ratio, float ratio_thr) {
+  Workspace& w = ctx->ws;
+  cudaStream_t st = ctx->stream;
+  const Codebook_d& cb = ctx->cb;
+  GemmState* gs = state_of(ctx);
+  PCDB_CUDA(w.knn_idx.ensure(sizeof(int) * (Q * k + 1)));
+  PCDB_CUDA(w.knn_dist.ensure(sizeof(float) * (Q * k + 1)));
+  PCDB_CUDA(w.knn_cnt.ensure(sizeof(int) * (Q + 1)));
+  if (Q == 0) return PCDB_OK;
+  const int K = use_ratio ? k + 1 : k;
+  const int D = cb.D;
+  // query side: fp16 copy + norms + margins
+  PCDB_CUDA(w.feat_h.ensure(sizeof(__half) * (size_t)Q * D + 256));
+  PCDB_CUDA(gs->qnorm_h.ensure(sizeof(float) * (Q + 1)));
+  PCDB_CUDA(gs->qerr.ensure(sizeof(float) * (Q + 1)));
+  PCDB_CUDA(gs->margin.ensure(sizeof(float) * (Q + 1)));
+  k_prep_rows<<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, w.feat_h.as<__half>(), nullptr,
+                                                 gs->qnorm_h.as<float>(), gs->qerr.as<float>());
+  PCDB_LAUNCH_CHECK();
+  k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, gs->cmax_h,
+                                         gs->cerr_max, gs->cmax2, gs->margin.as<float>());
+  PCDB_LAUNCH_CHECK();
+  CUtensorMap map_a;
+  PCDB_TRY(make_map(ctx, &map_a, w.feat_h.p, Q, D, BM));
+  GemmArgs g;
+  g.Q = Q;
+  g.N = cb.N;
+  g.D = D;
+  g.n_mtiles = (int)cdiv(Q, BM);
+  g.n_ntiles = (int)cdiv(cb.N, BN);
+  // split the codebook sweep when there are fewer query tiles than SMs
+  int S = 1;
+  if (g.n_mtiles < ctx->sm_count) S = std::min(g.n_ntiles, std::max(1, ctx->sm_count / g.n_mtiles));
+  g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
+  S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
+  g.n_splits = S;
+  g.cnorm = cb.cnorm.as<float>();
+  g.margin = gs->margin.as<float>();
+  const size_t nc = (size_t)Q * S * CAND_CAP;
+  PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
+  PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
+  PCDB_CUDA(w.cand_cnt.ensure(sizeof(int) * ((size_t)Q * S + 1)));
+  PCDB_CUDA(w.cand_thr.ensure(sizeof(float) * ((size_t)Q * S + 1)));
+  PCDB_CUDA(w.scalars.ensure(256));
+  PCDB_CUDA(cudaMemsetAsync(w.scalars.as<char>() + 64, 0, 8, st));
+  g.cand_idx = w.cand_idx.as<int>();
+  g.cand_apx = w.cand_apx.as<float>();
+  g.cand_cnt = w.cand_cnt.as<int>();
+  g.cand_thr = w.cand_thr.as<float>();
+  const int grid = std::min(g.n_mtiles * S, ctx->sm_count);
+  const bool a_res = (D + BK - 1) / BK <= KB_RES_MAX;
+  cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
+  PCDB_CUDA(cudaEventRecord(e0, st));
+  if (a_res)
+    PCDB_TRY((launch_gemm_kt<true>(ctx, K, map_a, gs->map_b, g, grid)));
+  else
+    PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, gs->map_b, g, grid)));
+  PCDB_CUDA(cudaEventRecord(e1, st));
+  ctx->gemm_events_valid = true;
+  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S, CAND_CAP, use_ratio, ratio_thr));
+  // overflow fallback: exact scan of the affected queries (still on the GPU)
+  PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
+  PCDB_CUDA(gs->fb_pos.ensure(sizeof(int) * (Q + 2)));
+  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S, Q, CAND_CAP, gs->fb_flag.as<int>());
+  PCDB_LAUNCH_CHECK();
+  PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
+  int n_fb = 0;
+  unsigned long long n_eval = 0;
+  PCDB_CUDA(cudaMemcpyAsync(&n_fb, gs->fb_pos.as<int>() + Q, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaMemcpyAsync(&n_eval, w.scalars.as<char>() + 64, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  ctx->stats.knn_candidates += (int64_t)n_eval;
+  ctx->stats.knn_fallback_queries += n_fb;
+  if (n_fb > 0) {
+    PCDB_CUDA(gs->fb_q.ensure(sizeof(float) * (size_t)n_fb * D));
+    PCDB_CUDA(gs->fb_list.ensure(sizeof(int) * n_fb));
+    PCDB_CUDA(gs->fb_idx.ensure(sizeof(int) * ((size_t)Q * k + 1)));
+    PCDB_CUDA(gs->fb_dist.ensure(sizeof(float) * ((size_t)Q * k + 1)));
+    PCDB_CUDA(gs->fb_cnt.ensure(sizeof(int) * (Q + 1)));
+    k_overflow_gather<<<cdiv(Q * 32, 256), 256, 0, st>>>(gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q, D, queries_d,
+                                                         gs->fb_list.as<int>(), gs->fb_q.as<float>());
+    PCDB_LAUNCH_CHECK();
+    // keep the GEMM results aside, scan the fallback queries into the knn_* buffers, then merge back
+    PCDB_CUDA(cudaMemcpyAsync(gs->fb_idx.p, w.knn_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(gs->fb_dist.p, w.knn_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(gs->fb_cnt.p, w.knn_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
+    PCDB_TRY(stage_knn_scan(ctx, gs->fb_q.as<float>(), n_fb, k, PCDB_DIST_EUCLIDEAN, use_ratio, ratio_thr));
+    k_overflow_scatter<<<cdiv(n_fb, 128), 128, 0, st>>>(gs->fb_list.as<int>(), n_fb, k, w.knn_idx.as<int>(),
+                                                        w.knn_dist.as<float>(), w.knn_cnt.as<int>(),
+                                                        gs->fb_idx.as<int>(), gs->fb_dist.as<float>(),
+                                                        gs->fb_cnt.as<int>());
+    PCDB_LAUNCH_CHECK();
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_idx.p, gs->fb_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_dist.p, gs->fb_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_cnt.p, gs->fb_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
+  }
+  return PCDB_OK;
+}

@@ -1,0 +1,599 @@
+// shot.cu — K3 SHOT local reference frame, K4 SHOT-352, K5 CSHOT-1344, fused with the radius search.
+//
+// Replaces (reference paths under src/implicit_shape_model/):
+//   Features::computeSHOTReferenceFrames    features/features.cpp:238-252  (pcl::SHOTLocalReferenceFrameEstimationOMP;
+//                                           in-repo near-copy third_party/pcl_shot_na_lrf/shot_na_lrf.hpp:48-178)
+//   FeaturesSHOT::iComputeDescriptors       features/features_shot.cpp:28-81   (pcl::SHOTEstimationOMP)
+//   FeaturesCSHOT::iComputeDescriptors      features/features_cshot.cpp:28-103 (pcl::SHOTColorEstimationOMP)
+//   the per-keypoint kd-tree radius searches behind both
+//
+// Work item = one occupied search-grid cell of keypoints.  The 27 surrounding cells (9 contiguous runs of the
+// cell-sorted surface) are staged once into shared memory as float4 (xyz|rgb), float4 (normal|index) [+ float4 Lab]
+// and every keypoint of the cell is processed by one warp from that staged copy: pass A weighted covariance (fp64,
+// warp-shuffle reduction), 3x3 symmetric eigen-solve, pass B sign disambiguation, pass C quadrilinear soft histogram
+// accumulated in 64-bit fixed point in shared memory (integer atomics => bit-reproducible across runs).
+// Geometry follows the reference's float/double choices; membership d^2 < r^2 is bit-exact.
+#include "common.cuh"
+#include "stages.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 1024;               // staged points per chunk
+constexpr double kFixScale = 68719476736.0;  // 2^36
+constexpr double kFixInv = 1.0 / 68719476736.0;
+
+constexpr double PST_RAD_45 = 0.78539816339744830961566084581988;
+constexpr double PST_RAD_90 = 1.5707963267948966192313216916398;
+constexpr double PST_RAD_135 = 2.3561944901923449288469825374596;
+constexpr double PST_RAD_PI_7_8 = 2.7488935718910690836548129603691;
+
+struct ShotArgs {
+  const float4* surfS;
+  const float4* snrmS;
+  const float4* slabS;
+  const unsigned long long* skeys;
+  const long long* surf_off;
+  const float4* kp4;
+  const int* kp_order;
+  const unsigned long long* kp_keys;
+  const int* item_start;
+  const int* n_items_ptr;
+  double r_lrf, r_shot;
+  float r2_lrf, r2_shot;
+  const float* lrf_in;
+  float* lrf_out;
+  float* desc_out;
+  int do_lrf, do_desc;
+  int* work_counter;
+  unsigned long long* nbr_counts;
+  const float* lab_lut;
+};
+
+// cyclic Jacobi, ascending eigenvalues; V columns are eigenvectors (the reference: Eigen::SelfAdjointEigenSolver)
+__device__ void eig3_sym(const double Ain[6], double w[3], double V[3][3]) {
+  double A[3][3] = {{Ain[0], Ain[1], Ain[2]}, {Ain[1], Ain[3], Ain[4]}, {Ain[2], Ain[4], Ain[5]}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = A[p][q];
+        if (apq == 0.0) continue;
+        double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (!isfinite(theta)) t = 0.0;
+        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        A[p][q] = A[q][p] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  double d[3] = {A[0][0], A[1][1], A[2][2]};
+  int o0 = 0, o1 = 1, o2 = 2;
+  // stable ascending sort of three
+  if (d[o1] < d[o0]) { int t = o0; o0 = o1; o1 = t; }
+  if (d[o2] < d[o1]) { int t = o1; o1 = o2; o2 = t; }
+  if (d[o1] < d[o0]) { int t = o0; o0 = o1; o1 = t; }
+  double Vs[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Vs[i][0] = V[i][o0];
+    Vs[i][1] = V[i][o1];
+    Vs[i][2] = V[i][o2];
+  }
+  w[0] = d[o0];
+  w[1] = d[o1];
+  w[2] = d[o2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j];
+}
+
+// PCL RGB2CIELAB with the host-built LUTs, normalised L/100, a/120, b/120
+__device__ __forceinline__ float3 rgb_to_lab_norm(unsigned rgb, const float* __restrict__ lut) {
+  float fr = lut[(rgb >> 16) & 0xFF], fg = lut[(rgb >> 8) & 0xFF], fb = lut[rgb & 0xFF];
+  const float* xyzl = lut + 256;
+  float x = __fadd_rn(__fadd_rn(__fmul_rn(fr, 0.412453f), __fmul_rn(fg, 0.357580f)), __fmul_rn(fb, 0.180423f));
+  float y = __fadd_rn(__fadd_rn(__fmul_rn(fr, 0.212671f), __fmul_rn(fg, 0.715160f)), __fmul_rn(fb, 0.072169f));
+  float z = __fadd_rn(__fadd_rn(__fmul_rn(fr, 0.019334f), __fmul_rn(fg, 0.119193f)), __fmul_rn(fb, 0.950227f));
+  float vx = __fdiv_rn(x, 0.95047f), vy = y, vz = __fdiv_rn(z, 1.08883f);
+  vx = xyzl[min(3999, max(0, (int)__fmul_rn(vx, 4000.f)))];
+  vy = xyzl[min(3999, max(0, (int)__fmul_rn(vy, 4000.f)))];
+  vz = xyzl[min(3999, max(0, (int)__fmul_rn(vz, 4000.f)))];
+  float L = __fsub_rn(__fmul_rn(116.0f, vy), 16.0f);
+  if (L > 100.f) L = 100.0f;
+  float A = __fmul_rn(500.0f, __fsub_rn(vx, vy));
+  if (A > 120.f) A = 120.0f; else if (A < -120.f) A = -120.0f;
+  float B = __fmul_rn(200.0f, __fsub_rn(vy, vz));
+  if (B > 120.f) B = 120.0f; else if (B < -120.f) B = -120.0f;
+  return make_float3(__fdiv_rn(L, 100.0f), __fdiv_rn(A, 120.0f), __fdiv_rn(B, 120.0f));
+}
+
+__global__ void k_lab(const float4* __restrict__ pts, long long n, const float* __restrict__ lut, float4* lab) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float3 l = rgb_to_lab_norm(__float_as_uint(pts[i].w), lut);
+  lab[i] = make_float4(l.x, l.y, l.z, 0.f);
+}
+
+__device__ __forceinline__ void hist_add(long long* hist, int bin, double v) {
+  // the reference narrows every contribution to float before adding it (shot[..] += static_cast<float>(..))
+  long long q = __double2ll_rn((double)(float)v * kFixScale);
+  atomicAdd(reinterpret_cast<unsigned long long*>(hist + bin), (unsigned long long)q);
+}
+
+struct StageView {
+  const float4* pts;
+  const float4* nrm;
+  const float4* lab;
+  int cnt;
+};
+
+template <bool COLOR>
+__global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
+  constexpr int D = COLOR ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_pts = reinterpret_cast<float4*>(smem_raw);
+  float4* s_nrm = s_pts + kChunk;
+  float4* s_lab = s_nrm + kChunk;  // only touched when COLOR
+  long long* s_hist = reinterpret_cast<long long*>(smem_raw + sizeof(float4) * kChunk * (COLOR ? 3 : 2));
+  __shared__ long long s_rbeg[9];
+  __shared__ int s_rlen[9];
+  __shared__ int s_pref[10];
+  __shared__ int s_item;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = *a.n_items_ptr;
+  long long* hist = s_hist + (size_t)warp * D;
+
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int k0 = a.item_start[item], k1 = a.item_start[item + 1];
+    const unsigned long long key = a.kp_keys[k0];
+    const unsigned cloud = (unsigned)(key >> 48);
+    const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
+    if (threadIdx.x < 9) {
+      int y = cy + (int)(threadIdx.x % 3) - 1, z = cz + (int)(threadIdx.x / 3) - 1;
+      long long beg = 0, end = 0;
+      if (y >= 0 && y <= 65535 && z >= 0 && z <= 65535) {
+        long long lo = a.surf_off[cloud], hi = a.surf_off[cloud + 1];
+        beg = lower_bound_u64(a.skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
+        end = lower_bound_u64(a.skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
+      }
+      s_rbeg[threadIdx.x] = beg;
+      s_rlen[threadIdx.x] = (int)(end - beg);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int r = 0; r < 9; ++r) {
+        s_pref[r] = acc;
+        acc += s_rlen[r];
+      }
+      s_pref[9] = acc;
+    }
+    __syncthreads();
+    const int T = s_pref[9];
+    const int n_chunks = (T + kChunk - 1) / kChunk;
+    const bool multi = n_chunks > 1;
+
+    auto stage = [&](int chunk) {
+      const int base = chunk * kChunk;
+      const int cnt = min(kChunk, T - base);
+      for (int e = threadIdx.x; e < cnt; e += kThreads) {
+        int g = base + e;
+        int r = 0;
+        while (g >= s_pref[r + 1]) ++r;
+        long long src = s_rbeg[r] + (g - s_pref[r]);
+        s_pts[e] = a.surfS[src];
+        s_nrm[e] = a.snrmS[src];
+        if (COLOR) s_lab[e] = a.slabS[src];
+      }
+    };
+    if (!multi && T > 0) stage(0);
+    __syncthreads();
+
+    for (int round = k0; round < k1; round += kWarps) {
+      const bool have = round + warp < k1;
+      const int kidx = have ? a.kp_order[round + warp] : -1;
+      float kx = 0.f, ky = 0.f, kz = 0.f;
+      unsigned krgb = 0;
+      if (have) {
+        float4 k4 = a.kp4[kidx];
+        kx = k4.x; ky = k4.y; kz = k4.z;
+        krgb = __float_as_uint(k4.w);
+      }
+      float rf[9];
+      bool lrf_ok = have;
+      // ---------------------------------------------------------------- LRF
+      if (a.do_lrf) {
+        double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, sw = 0;
+        int valid = 0, nall = 0;
+        for (int c = 0; c < max(n_chunks, 1); ++c) {
+          if (multi) {
+            __syncthreads();
+            stage(c);
+            __syncthreads();
+          }
+          const int cnt = min(kChunk, T - c * kChunk);
+          if (have)
+            for (int e = lane; e < cnt; e += 32) {
+              float4 p = s_pts[e];
+              float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+              if (d2 < a.r2_lrf) {
+                ++nall;
+                if (!(p.x == kx && p.y == ky && p.z == kz)) {
+                  double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                         vz = (double)__fsub_rn(p.z, kz);
+                  double wgt = a.r_lrf - sqrt((double)d2);
+                  c00 += wgt * (vx * vx);
+                  c01 += wgt * (vx * vy);
+                  c02 += wgt * (vx * vz);
+                  c11 += wgt * (vy * vy);
+                  c12 += wgt * (vy * vz);
+                  c22 += wgt * (vz * vz);
+                  sw += wgt;
+                  ++valid;
+                }
+              }
+            }
+        }
+        c00 = warp_sum(c00); c01 = warp_sum(c01); c02 = warp_sum(c02);
+        c11 = warp_sum(c11); c12 = warp_sum(c12); c22 = warp_sum(c22);
+        sw = warp_sum(sw);
+        valid = warp_sum(valid);
+        nall = warp_sum(nall);
+        if (have && lane == 0 && a.nbr_counts) atomicAdd(&a.nbr_counts[0], (unsigned long long)nall);
+        double x[3] = {0, 0, 0}, z[3] = {0, 0, 0};
+        lrf_ok = have && valid >= 5;
+        if (lrf_ok) {
+          double cov[6] = {c00 / sw, c01 / sw, c02 / sw, c11 / sw, c12 / sw, c22 / sw};
+          double ev[3], V[3][3];
+          eig3_sym(cov, ev, V);
+          if (!isfinite(ev[0]) || !isfinite(ev[1]) || !isfinite(ev[2])) lrf_ok = false;
+          x[0] = V[0][2]; x[1] = V[1][2]; x[2] = V[2][2];
+          z[0] = V[0][0]; z[1] = V[1][0]; z[2] = V[2][0];
+        }
+        // pass B: sign disambiguation
+        int plusX = 0, plusZ = 0;
+        for (int c = 0; c < max(n_chunks, 1); ++c) {
+          if (multi) {
+            __syncthreads();
+            stage(c);
+            __syncthreads();
+          }
+          const int cnt = min(kChunk, T - c * kChunk);
+          if (lrf_ok)
+            for (int e = lane; e < cnt; e += 32) {
+              float4 p = s_pts[e];
+              float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+              if (d2 < a.r2_lrf && !(p.x == kx && p.y == ky && p.z == kz)) {
+                double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                       vz = (double)__fsub_rn(p.z, kz);
+                if (vx * x[0] + vy * x[1] + vz * x[2] >= 0) ++plusX;
+                if (vx * z[0] + vy * z[1] + vz * z[2] >= 0) ++plusZ;
+              }
+            }
+        }
+        plusX = warp_sum(plusX);
+        plusZ = warp_sum(plusZ);
+        if (lrf_ok) {
+          int sx = 2 * plusX - valid, sz = 2 * plusZ - valid;
+          if (sx == 0 || sz == 0) {
+            // Rare tie: the reference looks at the 5 neighbours around the median of the (d^2, index)-sorted valid
+            // list (shot_na_lrf.hpp:141-153).  Rank by counting, straight from global memory.
+            const int m = valid / 2;
+            int cntX = 0, cntZ = 0;
+            for (int r = 0; r < 9; ++r)
+              for (int e = lane; e < s_rlen[r]; e += 32) {
+                float4 p = a.surfS[s_rbeg[r] + e];
+                float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+                if (!(d2 < a.r2_lrf) || (p.x == kx && p.y == ky && p.z == kz)) continue;
+                int idx = __float_as_int(a.snrmS[s_rbeg[r] + e].w);
+                int rank = 0;
+                for (int r2 = 0; r2 < 9; ++r2)
+                  for (int e2 = 0; e2 < s_rlen[r2]; ++e2) {
+                    float4 q = a.surfS[s_rbeg[r2] + e2];
+                    float q2 = sqdist3_rn(kx, ky, kz, q.x, q.y, q.z);
+                    if (!(q2 < a.r2_lrf) || (q.x == kx && q.y == ky && q.z == kz)) continue;
+                    int qi = __float_as_int(a.snrmS[s_rbeg[r2] + e2].w);
+                    if (q2 < d2 || (q2 == d2 && qi < idx)) ++rank;
+                  }
+                if (rank >= m - 2 && rank <= m + 2) {
+                  double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                         vz = (double)__fsub_rn(p.z, kz);
+                  if (vx * x[0] + vy * x[1] + vz * x[2] > 0) ++cntX;
+                  if (vx * z[0] + vy * z[1] + vz * z[2] > 0) ++cntZ;
+                }
+              }
+            cntX = warp_sum(cntX);
+            cntZ = warp_sum(cntZ);
+            if (sx == 0) sx = (cntX < 3) ? -1 : 1;
+            if (sz == 0) sz = (cntZ < 3) ? -1 : 1;
+          }
+          if (sx < 0) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; }
+          if (sz < 0) { z[0] = -z[0]; z[1] = -z[1]; z[2] = -z[2]; }
+          rf[0] = (float)x[0]; rf[1] = (float)x[1]; rf[2] = (float)x[2];
+          rf[6] = (float)z[0]; rf[7] = (float)z[1]; rf[8] = (float)z[2];
+          rf[3] = __fsub_rn(__fmul_rn(rf[7], rf[2]), __fmul_rn(rf[8], rf[1]));
+          rf[4] = __fsub_rn(__fmul_rn(rf[8], rf[0]), __fmul_rn(rf[6], rf[2]));
+          rf[5] = __fsub_rn(__fmul_rn(rf[6], rf[1]), __fmul_rn(rf[7], rf[0]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) rf[i] = __int_as_float(0x7fc00000);
+        }
+        if (have && a.lrf_out && lane < 9) {
+          float v = rf[0];
+#pragma unroll
+          for (int i = 1; i < 9; ++i)
+            if (lane == i) v = rf[i];
+          a.lrf_out[(size_t)kidx * 9 + lane] = v;
+        }
+      } else if (have) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) rf[i] = a.lrf_in[(size_t)kidx * 9 + i];
+      }
+      if (!a.do_desc) continue;
+      // Features::operator() drops keypoints whose frame is not finite (features.cpp:64-76)
+      const bool frame_ok = have && isfinite(rf[0]) && isfinite(rf[3]) && isfinite(rf[6]);
+      // ---------------------------------------------------------------- SHOT / CSHOT
+      for (int j = lane; j < D; j += 32) hist[j] = 0;
+      __syncwarp();
+      float LRef = 0.f, aRef = 0.f, bRef = 0.f;
+      if (COLOR && frame_ok) {
+        float3 l = rgb_to_lab_norm(krgb, a.lab_lut);
+        LRef = l.x; aRef = l.y; bRef = l.z;
+      }
+      const double r34 = (a.r_shot * 3) / 4, r14 = a.r_shot / 4, r12 = a.r_shot / 2;
+      int nshot = 0;
+      for (int c = 0; c < max(n_chunks, 1); ++c) {
+        if (multi) {
+          __syncthreads();
+          stage(c);
+          __syncthreads();
+        }
+        const int cnt = min(kChunk, T - c * kChunk);
+        if (!frame_ok) continue;
+        for (int e = lane; e < cnt; e += 32) {
+          float4 p = s_pts[e];
+          float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+          if (!(d2 < a.r2_shot)) continue;
+          ++nshot;
+          float4 nr = s_nrm[e];
+          if (!finite3(nr.x, nr.y, nr.z)) continue;
+          double cosineDesc = (double)dot3_rn(nr.x, nr.y, nr.z, rf[6], rf[7], rf[8]);
+          cosineDesc = fmin(1.0, fmax(-1.0, cosineDesc));
+          double bdS = ((1.0 + cosineDesc) * 10) / 2;
+          double distance = sqrt((double)d2);
+          if (fabs(distance) < 1E-15) continue;
+          float dx = __fsub_rn(p.x, kx), dy = __fsub_rn(p.y, ky), dz = __fsub_rn(p.z, kz);
+          double xIn = (double)dot3_rn(dx, dy, dz, rf[0], rf[1], rf[2]);
+          double yIn = (double)dot3_rn(dx, dy, dz, rf[3], rf[4], rf[5]);
+          double zIn = (double)dot3_rn(dx, dy, dz, rf[6], rf[7], rf[8]);
+          if (fabs(yIn) < 1E-30) yIn = 0;
+          if (fabs(xIn) < 1E-30) xIn = 0;
+          if (fabs(zIn) < 1E-30) zIn = 0;
+          int bit4 = ((yIn > 0) || ((yIn == 0.0) && (xIn < 0))) ? 1 : 0;
+          int bit3 = ((xIn > 0) || ((xIn == 0.0) && (yIn > 0))) ? !bit4 : bit4;
+          int di = ((bit4 << 3) + (bit3 << 2)) << 1;
+          if ((xIn * yIn > 0) || (xIn == 0.0))
+            di += (fabs(xIn) >= fabs(yIn)) ? 0 : 4;
+          else
+            di += (fabs(xIn) > fabs(yIn)) ? 4 : 0;
+          di += zIn > 0 ? 1 : 0;
+          di += (distance > r12) ? 2 : 0;
+
+          int stepS = (int)floor(bdS + 0.5);
+          const int volS = di * 11;
+          bdS -= stepS;
+          double wS = 1 - fabs(bdS);
+          if (bdS > 0)
+            hist_add(hist, volS + ((stepS + 1) % 10), bdS);
+          else
+            hist_add(hist, volS + ((stepS - 1 + 10) % 10), -bdS);
+          int stepC = 0, volC = 0;
+          double wC = 0;
+          if (COLOR) {
+            float4 lb = s_lab[e];
+            float cdist = __fdiv_rn(
+                __fadd_rn(fabsf(__fsub_rn(LRef, lb.x)),
+                          __fdiv_rn(__fadd_rn(fabsf(__fsub_rn(aRef, lb.y)), fabsf(__fsub_rn(bRef, lb.z))), 2.0f)),
+                3.0f);
+            double cd = fmin(1.0, fmax(0.0, (double)cdist));
+            double bdC = cd * 30;
+            stepC = (int)floor(bdC + 0.5);
+            volC = 352 + di * 31;
+            bdC -= stepC;
+            wC = 1 - fabs(bdC);
+            if (bdC > 0)
+              hist_add(hist, volC + ((stepC + 1) % 30), bdC);
+            else
+              hist_add(hist, volC + ((stepC - 1 + 30) % 30), -bdC);
+          }
+#define SHOT_NEIGHBOUR(DI, VAL)                                     \
+  do {                                                              \
+    hist_add(hist, (DI) * 11 + stepS, (VAL));                       \
+    if (COLOR) hist_add(hist, 352 + (DI) * 31 + stepC, (VAL));      \
+  } while (0)
+          double wAdd = 0;
+          if (distance > r12) {
+            double rd = (distance - r34) / r12;
+            if (distance > r34)
+              wAdd += 1 - rd;
+            else {
+              wAdd += 1 + rd;
+              SHOT_NEIGHBOUR(di - 2, -rd);
+            }
+          } else {
+            double rd = (distance - r14) / r12;
+            if (distance < r14)
+              wAdd += 1 + rd;
+            else {
+              wAdd += 1 - rd;
+              SHOT_NEIGHBOUR(di + 2, rd);
+            }
+          }
+          // NB: the reference adds the four terms to intWeight one after the other; the order is kept below by
+          // accumulating them into wS / wC sequentially.
+          wS += wAdd;
+          wC += wAdd;
+          double incl = acos(fmin(1.0, fmax(-1.0, zIn / distance)));
+          if (incl > PST_RAD_90 || (fabs(incl - PST_RAD_90) < 1e-30 && zIn <= 0)) {
+            double id = (incl - PST_RAD_135) / PST_RAD_90;
+            if (incl > PST_RAD_135) {
+              wS += 1 - id;
+              wC += 1 - id;
+            } else {
+              wS += 1 + id;
+              wC += 1 + id;
+              SHOT_NEIGHBOUR(di + 1, -id);
+            }
+          } else {
+            double id = (incl - PST_RAD_45) / PST_RAD_90;
+            if (incl < PST_RAD_45) {
+              wS += 1 + id;
+              wC += 1 + id;
+            } else {
+              wS += 1 - id;
+              wC += 1 - id;
+              SHOT_NEIGHBOUR(di - 1, id);
+            }
+          }
+          if (yIn != 0.0 || xIn != 0.0) {
+            double az = atan2(yIn, xIn);
+            int sel = di >> 2;
+            double ad = (az - (-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) / PST_RAD_45;
+            ad = fmax(-0.5, fmin(ad, 0.5));
+            if (ad > 0) {
+              wS += 1 - ad;
+              wC += 1 - ad;
+              SHOT_NEIGHBOUR((di + 4) % 32, ad);
+            } else {
+              wS += 1 + ad;
+              wC += 1 + ad;
+              SHOT_NEIGHBOUR((di - 4 + 32) % 32, -ad);
+            }
+          }
+#undef SHOT_NEIGHBOUR
+          hist_add(hist, volS + stepS, wS);
+          if (COLOR) hist_add(hist, volC + stepC, wC);
+        }
+      }
+      nshot = warp_sum(nshot);
+      if (have && lane == 0 && a.nbr_counts && frame_ok) atomicAdd(&a.nbr_counts[1], (unsigned long long)nshot);
+      __syncwarp();
+      if (have) {
+        float* out = a.desc_out + (size_t)kidx * D;
+        if (!frame_ok || nshot < 5) {
+          for (int j = lane; j < D; j += 32) out[j] = __int_as_float(0x7fc00000);
+        } else {
+          double acc = 0.0;
+          for (int j = lane; j < D; j += 32) {
+            float s = (float)((double)hist[j] * kFixInv);
+            acc += (double)__fmul_rn(s, s);
+          }
+          acc = warp_sum(acc);
+          float nrm = (float)sqrt(acc);
+          for (int j = lane; j < D; j += 32) out[j] = __fdiv_rn((float)((double)hist[j] * kFixInv), nrm);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace
+
+size_t shot_smem_bytes(bool color) {
+  const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(long long) * (size_t)kWarps * D;
+}
+
+// Runs the fused LRF + descriptor kernel over the keypoint items prepared by stage_grid.
+int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lrf, double r_shot, bool do_lrf,
+               bool do_desc, const float* lrf_in_d, float* lrf_out_d, float* desc_out_d) {
+  Workspace& w = ctx->ws;
+  cudaStream_t st = ctx->stream;
+  if (Q == 0) return PCDB_OK;
+  PCDB_CUDA(w.scalars.ensure(256));
+  PCDB_CUDA(cudaMemsetAsync(w.scalars.p, 0, 256, st));
+  if (color && do_desc) {
+    PCDB_CUDA(w.slabS4.ensure(sizeof(float4) * (n_surf + 1)));
+    if (n_surf > 0) {
+      k_lab<<<cdiv(n_surf, 256), 256, 0, st>>>(w.surfS4.as<float4>(), n_surf, ctx->lab_lut_d, w.slabS4.as<float4>());
+      PCDB_LAUNCH_CHECK();
+    }
+  }
+  ShotArgs a;
+  a.surfS = w.surfS4.as<float4>();
+  a.snrmS = w.snrmS4.as<float4>();
+  a.slabS = w.slabS4.as<float4>();
+  a.skeys = w.gkeys2.as<unsigned long long>();
+  a.surf_off = w.surf_off.as<long long>();
+  a.kp4 = w.kp4.as<float4>();
+  a.kp_order = w.kvals2.as<int>();
+  a.kp_keys = w.kkeys2.as<unsigned long long>();
+  a.item_start = w.item_start.as<int>();
+  a.n_items_ptr = w.item_id.as<int>() + Q;
+  a.r_lrf = r_lrf;
+  a.r_shot = r_shot;
+  a.r2_lrf = (float)(r_lrf * r_lrf);    // pcl::KdTreeFLANN::radiusSearch: float(radius*radius)
+  a.r2_shot = (float)(r_shot * r_shot);
+  a.lrf_in = lrf_in_d;
+  a.lrf_out = lrf_out_d;
+  a.desc_out = desc_out_d;
+  a.do_lrf = do_lrf ? 1 : 0;
+  a.do_desc = do_desc ? 1 : 0;
+  a.work_counter = w.scalars.as<int>();
+  a.nbr_counts = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 16);
+  a.lab_lut = ctx->lab_lut_d;
+  const size_t smem = shot_smem_bytes(color);
+  // persistent grid: a multiple of the SM count, bounded by the number of keypoints
+  int per_sm = color ? 1 : 3;
+  int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, Q);
+  if (color) {
+    PCDB_CUDA(cudaFuncSetAttribute(k_shot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_shot<true><<<grid, kThreads, smem, st>>>(a);
+  } else {
+    PCDB_CUDA(cudaFuncSetAttribute(k_shot<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_shot<false><<<grid, kThreads, smem, st>>>(a);
+  }
+  PCDB_LAUNCH_CHECK();
+  return PCDB_OK;
+}
+
+int stage_shot_counts(pcdb_ctx* ctx, unsigned long long out[2]) {
+  PCDB_CUDA(cudaMemcpyAsync(out, ctx->ws.scalars.as<char>() + 16, sizeof(unsigned long long) * 2,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PCDB_OK;
+}

@@ -1,0 +1,35 @@
+// stages.h — internal stage drivers of libpcdb200 (device-resident data, asynchronous on ctx->stream unless noted).
+#pragma once
+#include "common.cuh"
+
+// prep.cu
+int stage_compact(pcdb_ctx* ctx, int B, int64_t P, bool has_normals, bool has_rgb);
+int stage_cloud_setup(pcdb_ctx* ctx, int B, int64_t n_pts, const float4* extra_kp, const int* extra_kp_cloud,
+                      int64_t n_extra, float leaf, double grid_radius);
+int stage_voxel_keypoints(pcdb_ctx* ctx, int B, int64_t n_pts, float leaf, int64_t* Q_out);  // syncs
+int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color);
+
+// shot.cu
+size_t shot_smem_bytes(bool color);
+int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lrf, double r_shot, bool do_lrf,
+               bool do_desc, const float* lrf_in_d, float* lrf_out_d, float* desc_out_d);
+int stage_shot_counts(pcdb_ctx* ctx, unsigned long long out[2]);  // syncs
+
+// knn_scan.cu
+int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
+                   float ratio_thr);
+int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int K, int S, int cap, bool use_ratio,
+                     float ratio_thr);
+
+// knn_gemm.cu
+int gemm_prepare_codebook(pcdb_ctx* ctx);  // fp16 copy, norms, error bounds, tensor map (after words upload)
+int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool use_ratio, float ratio_thr);
+bool gemm_supported(const pcdb_ctx* ctx);
+
+// votes.cu
+int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_lrf_d, const long long* feat_off_d,
+                     const int* feat_cloud_d, int B, int64_t F, int k, int64_t* V_out);  // syncs
+
+// meanshift.cu
+int stage_votes_unpack(pcdb_ctx* ctx, int B, int64_t V);
+int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* members_out);  // syncs
