@@ -176,6 +176,11 @@ int pcdb_compute_features(pcdb_ctx* ctx, const float* xyz, const float* normals,
 int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t dist_type, int32_t mode,
              int32_t* idx_out, float* dist_out, int32_t* count_out);
 
+/* Distance functor values for n explicit (a[i], b[i]) row pairs — ism3d::Distance::operator() (utils/distance.cpp:27-52),
+ * used by training for the class variances (codebook/codebook.cpp:166-193).  a, b: n x D. */
+int pcdb_distance_pairs(pcdb_ctx* ctx, const float* a, const float* b, int64_t n, int32_t D, int32_t dist_type,
+                        float* out);
+
 /* Codebook::castVotes + CodewordDistribution::castVotes/castVote (codebook/codebook.cpp:403-555,
  * codebook/codeword_distribution.cpp:73-167).  Votes are emitted per cloud in (feature, activation rank,
  * stored vote) order.  vote_off_out has B+1 entries. */

@@ -735,6 +735,23 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
   return PCDB_OK;
 }
 
+int pcdb_distance_pairs(pcdb_ctx* ctx, const float* a, const float* b, int64_t n, int32_t D, int32_t dist_type,
+                        float* out) {
+  if (!ctx) return PCDB_E_INVALID;
+  PCDB_CUDA(cudaSetDevice(ctx->device));
+  if (n < 0 || D <= 0) return ctx->fail(PCDB_E_INVALID, "bad arguments");
+  if (dist_type != PCDB_DIST_EUCLIDEAN && dist_type != PCDB_DIST_CHISQUARED)
+    return ctx->fail(PCDB_E_INVALID, "invalid distance type %d", dist_type);
+  Workspace& w = ctx->ws;
+  PCDB_TRY(upload(ctx, w.merge_a, a, sizeof(float) * (size_t)n * D));
+  PCDB_TRY(upload(ctx, w.merge_b, b, sizeof(float) * (size_t)n * D));
+  PCDB_CUDA(w.knn_dist.ensure(sizeof(float) * (n + 1)));
+  PCDB_TRY(stage_pair_distances(ctx, w.merge_a.as<float>(), w.merge_b.as<float>(), n, D, dist_type, w.knn_dist.as<float>()));
+  PCDB_TRY(download(ctx, out, w.knn_dist.p, sizeof(float) * n));
+  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PCDB_OK;
+}
+
 int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9, const int64_t* feat_off, int32_t B,
                     const int32_t* knn_idx, const float* knn_dist, const int32_t* knn_count, int32_t k,
                     pcdb_vote* votes_out, int64_t* vote_off_out, int64_t vote_capacity) {

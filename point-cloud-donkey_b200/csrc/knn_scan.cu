@@ -291,7 +291,44 @@ __global__ void k_all_rows(const float* __restrict__ queries, long long Q, const
   dist_out[t] = acc;
 }
 
+template <int DIST>
+__global__ void k_pair_dist(const float* __restrict__ a, const float* __restrict__ b, long long n, int D, float* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  int e = 0;
+  for (; e + 3 < D; e += 4)
+    acc = accum4<DIST>(acc, *reinterpret_cast<const float4*>(b + i * D + e),
+                       *reinterpret_cast<const float4*>(a + i * D + e));
+  for (; e < D; ++e) {  // FLANN's tail loop
+    float x = a[i * D + e], y = b[i * D + e];
+    if (DIST == PCDB_DIST_EUCLIDEAN) {
+      float d = __fsub_rn(x, y);
+      acc = __fadd_rn(acc, __fmul_rn(d, d));
+    } else {
+      float s = __fadd_rn(x, y);
+      if (s > 0.f) {
+        float d = __fsub_rn(x, y);
+        acc = __fadd_rn(acc, __fdiv_rn(__fmul_rn(d, d), s));
+      }
+    }
+  }
+  out[i] = acc;
+}
+
 }  // namespace
+
+int stage_pair_distances(pcdb_ctx* ctx, const float* a_d, const float* b_d, int64_t n, int D, int dist_type,
+                         float* out_d) {
+  if (n == 0) return PCDB_OK;
+  if (D % 4 != 0) return ctx->fail(PCDB_E_UNSUPPORTED, "row length must be a multiple of 4");
+  if (dist_type == PCDB_DIST_CHISQUARED)
+    k_pair_dist<PCDB_DIST_CHISQUARED><<<cdiv(n, 128), 128, 0, ctx->stream>>>(a_d, b_d, n, D, out_d);
+  else
+    k_pair_dist<PCDB_DIST_EUCLIDEAN><<<cdiv(n, 128), 128, 0, ctx->stream>>>(a_d, b_d, n, D, out_d);
+  PCDB_LAUNCH_CHECK();
+  return PCDB_OK;
+}
 
 // Exact scan of queries_d (Q x D, device) against the uploaded codebook; results to ws.knn_* (device).
 int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,

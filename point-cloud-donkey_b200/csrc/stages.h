@@ -21,6 +21,9 @@ int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
 int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int K, int S, int cap, bool use_ratio,
                      float ratio_thr);
 
+int stage_pair_distances(pcdb_ctx* ctx, const float* a_d, const float* b_d, int64_t n, int D, int dist_type,
+                         float* out_d);
+
 // knn_gemm.cu
 int gemm_prepare_codebook(pcdb_ctx* ctx);  // fp16 copy, norms, error bounds, tensor map (after words upload)
 int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool use_ratio, float ratio_thr);

@@ -20,7 +20,7 @@ F, I64, I32, U32, D = C.c_float, C.c_int64, C.c_int32, C.c_uint32, C.c_double
 SYMBOLS = [
     "pcdb_abi_version", "pcdb_create", "pcdb_destroy", "pcdb_last_error", "pcdb_default_params", "pcdb_set_params",
     "pcdb_set_stream", "pcdb_set_codebook", "pcdb_voxel_keypoints", "pcdb_radius_neighbours", "pcdb_shot_lrf",
-    "pcdb_shot_describe", "pcdb_compute_features", "pcdb_knn", "pcdb_cast_votes", "pcdb_find_maxima",
+    "pcdb_shot_describe", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
     "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
     "pcdb_get_stats", "pcdb_reset_stats",
 ]
@@ -46,7 +46,7 @@ def lib():
 
 
 class Context:
-    """One pcdb_ctx (one GPU).  Method names mirror oracle_py.Model so parity tests read symmetrically."""
+    """One pcdb_ctx (one GPU).  Method names follow the reference hooks (one per stage) so parity tests read symmetrically."""
 
     def __init__(self, prm: Params = None, cb: Codebook = None, device=0, row_base=0):
         self.h = C.c_void_p()
@@ -161,6 +161,13 @@ class Context:
         self._check(lib().pcdb_knn(self.h, ptr(queries, F), I64(Q), k, dist_type, mode, ptr(idx, I32), ptr(dist, F),
                                    ptr(cnt, I32)))
         return idx, dist, cnt
+
+    def distance_pairs(self, a, b, dist_type):
+        a, b = f32(a), f32(b)
+        out = np.empty(a.shape[0], np.float32)
+        self._check(lib().pcdb_distance_pairs(self.h, ptr(a, F), ptr(b, F), I64(a.shape[0]), a.shape[1], dist_type,
+                                              ptr(out, F)))
+        return out
 
     def cast_votes(self, feat_xyz, feat_lrf, feat_off, knn_idx, knn_dist, knn_count):
         feat_xyz, feat_lrf, feat_off = f32(feat_xyz), f32(feat_lrf), i64(feat_off)

@@ -144,11 +144,13 @@ WORKLOADS = {
     "c1": dict(n_classes=5, P=5000, scale=250.0, train_per_class=1, n_test=5, cshot=False,
                radius=60.0, lrf_radius=50.0, leaf=50.0, bandwidth=50.0, dist=DIST_CHISQUARED, n_words=None),
     # C2: ModelNet10-shaped
+    # radii as shipped in config/default.ism (Radius 0.40, ReferenceFrameRadius 0.30) on unit-size objects;
+    # LeafSize 0.08 gives ~256 keypoints per 2k-point cloud, Bandwidth 0.30
     "c2": dict(n_classes=10, P=2048, scale=1.0, train_per_class=None, n_test=1000, cshot=False,
-               radius=0.20, lrf_radius=0.15, leaf=0.10, bandwidth=0.30, dist=DIST_EUCLIDEAN, n_words=200_000),
+               radius=0.40, lrf_radius=0.30, leaf=0.08, bandwidth=0.30, dist=DIST_EUCLIDEAN, n_words=200_000),
     # C3: ModelNet40-shaped
     "c3": dict(n_classes=40, P=2048, scale=1.0, train_per_class=None, n_test=4096, cshot=False,
-               radius=0.20, lrf_radius=0.15, leaf=0.10, bandwidth=0.30, dist=DIST_EUCLIDEAN, n_words=1_000_000),
+               radius=0.40, lrf_radius=0.30, leaf=0.08, bandwidth=0.30, dist=DIST_EUCLIDEAN, n_words=1_000_000),
     # C4: Washington-shaped CSHOT (default_config_kinect.ism radii at object scale 0.2 m)
     "c4": dict(n_classes=51, P=8192, scale=0.2, train_per_class=None, n_test=512, cshot=True,
                radius=0.05, lrf_radius=0.05, leaf=0.02, bandwidth=0.045, dist=DIST_EUCLIDEAN, n_words=1_000_000),
