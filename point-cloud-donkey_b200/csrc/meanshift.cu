@@ -97,11 +97,13 @@ __global__ void k_seg_info(const int* __restrict__ head, const int* __restrict__
   }
 }
 
-__global__ void k_gather_segkey(const int* __restrict__ t1, const int* __restrict__ seg_id, long long V,
-                                unsigned* segkey, int* ident) {
+// group of sorted vote t = (number of heads up to and including t) - 1; seg_id is the EXCLUSIVE scan of the heads
+__global__ void k_gather_segkey(const int* __restrict__ t1, const int* __restrict__ seg_id,
+                                const int* __restrict__ head, long long V, unsigned* segkey, int* ident) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= V) return;
-  segkey[i] = (unsigned)seg_id[t1[i]];
+  const int t = t1[i];
+  segkey[i] = (unsigned)(seg_id[t] + head[t] - 1);
   ident[i] = (int)i;
 }
 
@@ -729,7 +731,8 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   // seeds: sort bin keys, then stable by group
   PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.seed_k0.as<unsigned long long>(), w.seed_k1.as<unsigned long long>(),
                                    w.seed_i0.as<int>(), w.seed_i1.as<int>(), V, 63));
-  k_gather_segkey<<<gV, 256, 0, st>>>(w.seed_i1.as<int>(), w.seg2_id.as<int>(), V, w.seed_s0.as<unsigned>(),
+  k_gather_segkey<<<gV, 256, 0, st>>>(w.seed_i1.as<int>(), w.seg2_id.as<int>(), w.seg2_head.as<int>(), V,
+                                      w.seed_s0.as<unsigned>(),
                                       w.seed_i2.as<int>());
   PCDB_LAUNCH_CHECK();
   int sbits = 1;

@@ -11,7 +11,7 @@
 // cell-sorted surface) are staged once into shared memory as float4 (xyz|rgb), float4 (normal|index) [+ float4 Lab]
 // and every keypoint of the cell is processed by one warp from that staged copy: pass A weighted covariance (fp64,
 // warp-shuffle reduction), 3x3 symmetric eigen-solve, pass B sign disambiguation, pass C quadrilinear soft histogram
-// accumulated in 64-bit fixed point in shared memory (integer atomics => bit-reproducible across runs).
+// accumulated in 32-bit fixed point in shared memory (native integer atomics => bit-reproducible across runs).
 // Geometry follows the reference's float/double choices; membership d^2 < r^2 is bit-exact.
 #include "common.cuh"
 #include "stages.h"
@@ -20,9 +20,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 1024;               // staged points per chunk
-constexpr double kFixScale = 68719476736.0;  // 2^36
-constexpr double kFixInv = 1.0 / 68719476736.0;
+constexpr int kChunk = 2048;               // staged points per chunk
 
 constexpr double PST_RAD_45 = 0.78539816339744830961566084581988;
 constexpr double PST_RAD_90 = 1.5707963267948966192313216916398;
@@ -141,10 +139,13 @@ __global__ void k_lab(const float4* __restrict__ pts, long long n, const float* 
   lab[i] = make_float4(l.x, l.y, l.z, 0.f);
 }
 
-__device__ __forceinline__ void hist_add(long long* hist, int bin, double v) {
+// Histogram bins are 32-bit unsigned fixed point in shared memory: native ATOMS.ADD (a 64-bit shared atomic is a CAS
+// spin loop on sm_100 and serialises badly when many neighbours hit one bin), and integer adds commute, so the
+// descriptor is bit-reproducible from run to run.  Every contribution is >= 0 and <= 4, a bin receives at most one
+// such contribution per staged point, hence scale = 2^floor(log2(2^32 / (4 T + 4))) cannot overflow.
+__device__ __forceinline__ void hist_add(unsigned* hist, int bin, double v, float scale) {
   // the reference narrows every contribution to float before adding it (shot[..] += static_cast<float>(..))
-  long long q = __double2ll_rn((double)(float)v * kFixScale);
-  atomicAdd(reinterpret_cast<unsigned long long*>(hist + bin), (unsigned long long)q);
+  atomicAdd(hist + bin, __float2uint_rn(__fmul_rn((float)v, scale)));
 }
 
 struct StageView {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   float4* s_pts = reinterpret_cast<float4*>(smem_raw);
   float4* s_nrm = s_pts + kChunk;
   float4* s_lab = s_nrm + kChunk;  // only touched when COLOR
-  long long* s_hist = reinterpret_cast<long long*>(smem_raw + sizeof(float4) * kChunk * (COLOR ? 3 : 2));
+  unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(float4) * kChunk * (COLOR ? 3 : 2));
   __shared__ long long s_rbeg[9];
   __shared__ int s_rlen[9];
   __shared__ int s_pref[10];
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = *a.n_items_ptr;
-  long long* hist = s_hist + (size_t)warp * D;
+  unsigned* hist = s_hist + (size_t)warp * D;
 
   while (true) {
     __syncthreads();
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
     }
     __syncthreads();
     const int T = s_pref[9];
+    const float fix_scale = exp2f(floorf(log2f(4294967296.0f / (4.0f * (float)T + 4.0f))));
+    const float fix_inv = 1.0f / fix_scale;
     const int n_chunks = (T + kChunk - 1) / kChunk;
     const bool multi = n_chunks > 1;
 
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         LRef = l.x; aRef = l.y; bRef = l.z;
       }
       const double r34 = (a.r_shot * 3) / 4, r14 = a.r_shot / 4, r12 = a.r_shot / 2;
+      const double inv_r12 = 1.0 / r12, inv_90 = 1.0 / PST_RAD_90, inv_45 = 1.0 / PST_RAD_45;
       int nshot = 0;
       for (int c = 0; c < max(n_chunks, 1); ++c) {
         if (multi) {
@@ -417,9 +421,9 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           bdS -= stepS;
           double wS = 1 - fabs(bdS);
           if (bdS > 0)
-            hist_add(hist, volS + ((stepS + 1) % 10), bdS);
+            hist_add(hist, volS + ((stepS + 1) % 10), bdS, fix_scale);
           else
-            hist_add(hist, volS + ((stepS - 1 + 10) % 10), -bdS);
+            hist_add(hist, volS + ((stepS - 1 + 10) % 10), -bdS, fix_scale);
           int stepC = 0, volC = 0;
           double wC = 0;
           if (COLOR) {
@@ -435,18 +439,18 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             bdC -= stepC;
             wC = 1 - fabs(bdC);
             if (bdC > 0)
-              hist_add(hist, volC + ((stepC + 1) % 30), bdC);
+              hist_add(hist, volC + ((stepC + 1) % 30), bdC, fix_scale);
             else
-              hist_add(hist, volC + ((stepC - 1 + 30) % 30), -bdC);
+              hist_add(hist, volC + ((stepC - 1 + 30) % 30), -bdC, fix_scale);
           }
 #define SHOT_NEIGHBOUR(DI, VAL)                                     \
   do {                                                              \
-    hist_add(hist, (DI) * 11 + stepS, (VAL));                       \
-    if (COLOR) hist_add(hist, 352 + (DI) * 31 + stepC, (VAL));      \
+    hist_add(hist, (DI) * 11 + stepS, (VAL), fix_scale);                       \
+    if (COLOR) hist_add(hist, 352 + (DI) * 31 + stepC, (VAL), fix_scale);      \
   } while (0)
           double wAdd = 0;
           if (distance > r12) {
-            double rd = (distance - r34) / r12;
+            double rd = (distance - r34) * inv_r12;
             if (distance > r34)
               wAdd += 1 - rd;
             else {
@@ -454,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
               SHOT_NEIGHBOUR(di - 2, -rd);
             }
           } else {
-            double rd = (distance - r14) / r12;
+            double rd = (distance - r14) * inv_r12;
             if (distance < r14)
               wAdd += 1 + rd;
             else {
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           wC += wAdd;
           double incl = acos(fmin(1.0, fmax(-1.0, zIn / distance)));
           if (incl > PST_RAD_90 || (fabs(incl - PST_RAD_90) < 1e-30 && zIn <= 0)) {
-            double id = (incl - PST_RAD_135) / PST_RAD_90;
+            double id = (incl - PST_RAD_135) * inv_90;
             if (incl > PST_RAD_135) {
               wS += 1 - id;
               wC += 1 - id;
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
               SHOT_NEIGHBOUR(di + 1, -id);
             }
           } else {
-            double id = (incl - PST_RAD_45) / PST_RAD_90;
+            double id = (incl - PST_RAD_45) * inv_90;
             if (incl < PST_RAD_45) {
               wS += 1 + id;
               wC += 1 + id;
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           if (yIn != 0.0 || xIn != 0.0) {
             double az = atan2(yIn, xIn);
             int sel = di >> 2;
-            double ad = (az - (-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) / PST_RAD_45;
+            double ad = (az - (-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) * inv_45;
             ad = fmax(-0.5, fmin(ad, 0.5));
             if (ad > 0) {
               wS += 1 - ad;
@@ -504,8 +508,8 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             }
           }
 #undef SHOT_NEIGHBOUR
-          hist_add(hist, volS + stepS, wS);
-          if (COLOR) hist_add(hist, volC + stepC, wC);
+          hist_add(hist, volS + stepS, wS, fix_scale);
+          if (COLOR) hist_add(hist, volC + stepC, wC, fix_scale);
         }
       }
       nshot = warp_sum(nshot);
@@ -518,12 +522,12 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         } else {
           double acc = 0.0;
           for (int j = lane; j < D; j += 32) {
-            float s = (float)((double)hist[j] * kFixInv);
+            float s = __fmul_rn((float)hist[j], fix_inv);
             acc += (double)__fmul_rn(s, s);
           }
           acc = warp_sum(acc);
           float nrm = (float)sqrt(acc);
-          for (int j = lane; j < D; j += 32) out[j] = __fdiv_rn((float)((double)hist[j] * kFixInv), nrm);
+          for (int j = lane; j < D; j += 32) out[j] = __fdiv_rn(__fmul_rn((float)hist[j], fix_inv), nrm);
         }
       }
       __syncwarp();
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
 
 size_t shot_smem_bytes(bool color) {
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
-  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(long long) * (size_t)kWarps * D;
+  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D;
 }
 
 // Runs the fused LRF + descriptor kernel over the keypoint items prepared by stage_grid.
@@ -578,7 +582,7 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   a.lab_lut = ctx->lab_lut_d;
   const size_t smem = shot_smem_bytes(color);
   // persistent grid: a multiple of the SM count, bounded by the number of keypoints
-  int per_sm = color ? 1 : 3;
+  int per_sm = color ? 1 : 2;
   int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, Q);
   if (color) {
     PCDB_CUDA(cudaFuncSetAttribute(k_shot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

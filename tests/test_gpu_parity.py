@@ -88,7 +88,7 @@ def _compare_lrf(a, b):
     err = np.abs(a[ok] - b[ok]).max(1)
     # degenerate neighbourhoods (two nearly equal eigenvalues) are solver dependent; the bulk must agree tightly
     assert (err < 1e-4).mean() > 0.98, "LRF mismatch: %g of frames off, worst %g" % ((err >= 1e-4).mean(), err.max())
-    return ok & np.pad(err < 1e-4, (0, 0)) if False else ok
+    return ok
 
 
 def test_shot_lrf_parity(ctx, orc):
@@ -105,8 +105,11 @@ def test_shot_lrf_parity(ctx, orc):
 def test_shot_lrf_tie_break_and_degenerate(ctx, orc):
     """A mirror-symmetric neighbourhood makes the sign votes tie: the 5-around-the-median rule must kick in
     (shot_na_lrf.hpp:141-153).  Fewer than 5 neighbours -> NaN frame."""
-    g = np.linspace(-0.2, 0.2, 9, dtype=np.float32)
-    X, Y = np.meshgrid(g, g)
+    # 8 columns (no x = 0 column) x 9 rows: exactly half of the neighbours project positively on the x axis and on
+    # the (tilted) z axis, robustly -> both sign votes tie and the median rule decides
+    gx = np.array([-0.2, -0.15, -0.1, -0.05, 0.05, 0.1, 0.15, 0.2], np.float32)
+    gy = np.linspace(-0.2, 0.2, 9, dtype=np.float32)
+    X, Y = np.meshgrid(gx, gy)
     plane = np.stack([X.ravel(), Y.ravel() * 0.6, 0.01 * np.sin(7 * X.ravel())], 1).astype(np.float32)
     few = np.array([[5, 5, 5], [5.01, 5, 5], [5, 5.01, 5]], np.float32)
     pts = np.concatenate([plane, few])
@@ -312,7 +315,10 @@ def _blob_votes(centres, n_per, sigma, rng, cls=0, inst=0):
     return votes
 
 
-def _compare_maxima(a, b, pos_tol=1e-3):
+def _compare_maxima(a, b, pos_tol=3e-3):
+    # mean shift stops when a step is <= Voting.Threshold (1e-3): the stopping iteration, hence the position, is only
+    # reproducible to about that threshold under a different float summation order (votes are unordered in the
+    # reference too, voting.cpp:73-76)
     mxa, offa, mia, mwa = a
     mxb, offb, mib, mwb = b
     assert np.array_equal(offa, offb), (offa, offb)
