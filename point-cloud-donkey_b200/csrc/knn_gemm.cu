@@ -28,7 +28,8 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int STAGES = 4;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int EPI_THREADS = 256;        // two epilogue warps per TMEM lane quarter, one per 128-column half
 constexpr int A_BOX_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_BOX_BYTES = BN * BK * 2;  // 32 KB
 constexpr int KB_RES_MAX = 6;             // resident K-blocks (D <= 384)
@@ -101,8 +102,8 @@ __device__ __forceinline__ void tc_mma_f16(unsigned tmem_d, unsigned long long a
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, float* v) {
-  unsigned r[32];
+// issue only; the registers are valid after tc_ld_wait()
+__device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, unsigned* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -113,10 +114,9 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO in [16,30) (unused for swizzled K-major, set to 1), SBO = 1024 B (8 rows x 128 B) in [32,46), version 1 in
@@ -140,13 +140,14 @@ struct GemmArgs {
   int n_mtiles, n_ntiles, tiles_per_split, n_splits;
   const float* cnorm;    // |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
-  int* cand_idx;         // [Q][S][CAND_CAP]
+  int* cand_idx;         // [Q][2 S][CAND_CAP]   (2 column halves per codebook split)
   float* cand_apx;
-  int* cand_cnt;         // [S][Q]
-  float* cand_thr;       // [S][Q]
+  int* cand_cnt;         // [2 S][Q]
+  float* cand_thr;       // [2 S][Q]
 };
 
-struct __align__(8) Barriers {
+struct __align__(16) Barriers {
+  float cn[2][BN];  // |c|^2 of the tile in each accumulator buffer, staged by the epilogue warps
   unsigned long long full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   unsigned tmem_base;
 };
@@ -154,8 +155,8 @@ struct __align__(8) Barriers {
 template <bool A_RES, int KT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   // layout: [A resident: KB_RES_MAX boxes]? [STAGES x (A box if !A_RES) + B box] [barriers]
   unsigned char* a_res = smem;
   unsigned char* stage0 = smem + (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0);
@@ -178,7 +179,7 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     mbar_init(&bars->a_empty, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 128);
+      mbar_init(&bars->tmem_empty[a], EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -265,7 +266,9 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: TMEM -> registers -> running candidate filter
-    const int grp = warp & 3;  // TMEM lane quarter this warp may access
+    const int grp = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which 128 columns of the 256-wide accumulator this warp filters
+    const int epi_tid = (warp - 4) * 32 + lane;
     int acc = 0;
     unsigned acc_phase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -279,45 +282,70 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       for (int i = 0; i < KT; ++i) best[i] = __int_as_float(0x7f800000);
       float thr = __int_as_float(0x7f800000);
       int cnt = 0;
-      const size_t cbase = active ? ((size_t)row * g.n_splits + split) * CAND_CAP : 0;
+      const int slice = split * 2 + half;
+      const size_t cbase = active ? ((size_t)row * (2 * g.n_splits) + slice) * CAND_CAP : 0;
+      // software-prefetched |c|^2: each of the 256 epilogue threads owns one column of the tile
+      float cn_next = __ldg(g.cnorm + (size_t)t0 * BN + epi_tid);
       for (int t = t0; t < t1; ++t) {
+        // publish this tile's |c|^2; the barrier also orders it after every thread's reads of tile t-2
+        bars->cn[acc][epi_tid] = cn_next;
+        if (t + 1 < t1) cn_next = __ldg(g.cnorm + (size_t)(t + 1) * BN + epi_tid);
+        epi_bar_sync();
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
-        const unsigned taddr = tmem_base + ((unsigned)(grp * 32) << 16) + (unsigned)(acc * BN);
+        const int col0 = half * (BN / 2);
+        const unsigned taddr = tmem_base + ((unsigned)(grp * 32) << 16) + (unsigned)(acc * BN + col0);
+        const float* cn_s = bars->cn[acc] + col0;
+        unsigned ra[32], rb[32];
+        tc_ld_32x32b_x32(taddr, ra);
+        // Branch-free common path: 32 distances, one min-tree, ONE compare per 32 columns; the per-column scan only runs
+        // when some column of the chunk can still be among the k best (rare after the first tiles of a sweep).
+#define PCDB_FILTER_CHUNK(REG, C)                                                                  \
+  {                                                                                                \
+    float dv[32];                                                                                  \
+    _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4) {                                             \
+      const float4 cn = *reinterpret_cast<const float4*>(cn_s + (C) * 32 + j4 * 4);                \
+      dv[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 0]), cn.x);                         \
+      dv[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 1]), cn.y);                         \
+      dv[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 2]), cn.z);                         \
+      dv[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 3]), cn.w);                         \
+    }                                                                                              \
+    float m16[16];                                                                                 \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i) m16[i] = fminf(dv[i], dv[i + 16]);              \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) m16[i] = fminf(m16[i], m16[i + 8]);              \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) m16[i] = fminf(m16[i], m16[i + 4]);              \
+    const float mn = fminf(fminf(m16[0], m16[1]), fminf(m16[2], m16[3]));                          \
+    if (mn <= thr) {                                                                               \
+      const int n_base = t * BN + col0 + (C) * 32;                                                 \
+      _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                             \
+        const float d = dv[e];                                                                     \
+        if (d <= thr && active && n_base + e < g.N) {                                              \
+          if (cnt < CAND_CAP) {                                                                    \
+            g.cand_idx[cbase + cnt] = n_base + e;                                                  \
+            g.cand_apx[cbase + cnt] = d;                                                           \
+          }                                                                                        \
+          ++cnt;                                                                                   \
+          float x = d;                                                                             \
+          _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                         \
+            float lo = fminf(best[i], x);                                                          \
+            x = fmaxf(best[i], x);                                                                 \
+            best[i] = lo;                                                                          \
+          }                                                                                        \
+          thr = best[KT - 1] + margin;                                                             \
+        }                                                                                          \
+      }                                                                                            \
+    }                                                                                              \
+  }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          tc_ld_32x32b_x32(taddr + c * 32, v);
-          const int n_base = t * BN + c * 32;
-          const float4* cn4 = reinterpret_cast<const float4*>(g.cnorm + n_base);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cn = __ldg(cn4 + j4);
-            const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float d = fmaf(-2.f, v[j4 * 4 + e], cnv[e]);
-              if (d <= thr) {
-                const int n = n_base + j4 * 4 + e;
-                if (active && n < g.N) {
-                  if (cnt < CAND_CAP) {
-                    g.cand_idx[cbase + cnt] = n;
-                    g.cand_apx[cbase + cnt] = d;
-                  }
-                  ++cnt;
-                  float x = d;
-#pragma unroll
-                  for (int i = 0; i < KT; ++i) {
-                    float lo = fminf(best[i], x);
-                    x = fmaxf(best[i], x);
-                    best[i] = lo;
-                  }
-                  thr = best[KT - 1] + margin;
-                }
-              }
-            }
-          }
+        for (int c = 0; c < BN / 64; c += 2) {
+          tc_ld_wait();                                  // chunk c is in ra
+          tc_ld_32x32b_x32(taddr + (c + 1) * 32, rb);    // chunk c+1 in flight while c is filtered
+          PCDB_FILTER_CHUNK(ra, c)
+          tc_ld_wait();
+          if (c + 2 < BN / 64) tc_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
+          PCDB_FILTER_CHUNK(rb, c + 1)
         }
+#undef PCDB_FILTER_CHUNK
         tc_fence_before();
         mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == 2) {
@@ -326,8 +354,8 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
       }
       if (active) {
-        g.cand_cnt[(size_t)split * g.Q + row] = cnt;
-        g.cand_thr[(size_t)split * g.Q + row] = thr;
+        g.cand_cnt[(size_t)slice * g.Q + row] = cnt;
+        g.cand_thr[(size_t)slice * g.Q + row] = thr;
       }
     }
   }
@@ -476,7 +504,7 @@ GemmState* state_of(pcdb_ctx* ctx) {
 
 template <bool A_RES, int KT>
 int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, int grid) {
-  const size_t smem = 1024 + (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0) +
+  const size_t smem = (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0) +
                       (size_t)STAGES * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
   PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_knn_gemm<A_RES, KT><<<grid, THREADS, smem, ctx->stream>>>(map_a, map_b, g);
@@ -575,11 +603,12 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.n_splits = S;
   g.cnorm = cb.cnorm.as<float>();
   g.margin = gs->margin.as<float>();
-  const size_t nc = (size_t)Q * S * CAND_CAP;
+  const int S2 = 2 * S;  // two column halves per split
+  const size_t nc = (size_t)Q * S2 * CAND_CAP;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
   PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
-  PCDB_CUDA(w.cand_cnt.ensure(sizeof(int) * ((size_t)Q * S + 1)));
-  PCDB_CUDA(w.cand_thr.ensure(sizeof(float) * ((size_t)Q * S + 1)));
+  PCDB_CUDA(w.cand_cnt.ensure(sizeof(int) * ((size_t)Q * S2 + 1)));
+  PCDB_CUDA(w.cand_thr.ensure(sizeof(float) * ((size_t)Q * S2 + 1)));
   PCDB_CUDA(w.scalars.ensure(256));
   PCDB_CUDA(cudaMemsetAsync(w.scalars.as<char>() + 64, 0, 8, st));
   g.cand_idx = w.cand_idx.as<int>();
@@ -596,11 +625,11 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
     PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, gs->map_b, g, grid)));
   PCDB_CUDA(cudaEventRecord(e1, st));
   ctx->gemm_events_valid = true;
-  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S, CAND_CAP, use_ratio, ratio_thr));
+  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S2, CAND_CAP, use_ratio, ratio_thr));
   // overflow fallback: exact scan of the affected queries (still on the GPU)
   PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
   PCDB_CUDA(gs->fb_pos.ensure(sizeof(int) * (Q + 2)));
-  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S, Q, CAND_CAP, gs->fb_flag.as<int>());
+  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, CAND_CAP, gs->fb_flag.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
   int n_fb = 0;
