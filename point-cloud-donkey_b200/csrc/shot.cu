@@ -312,34 +312,56 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         if (lrf_ok) {
           int sx = 2 * plusX - valid, sz = 2 * plusZ - valid;
           if (sx == 0 || sz == 0) {
-            // Rare tie: the reference looks at the 5 neighbours around the median of the (d^2, index)-sorted valid
-            // list (shot_na_lrf.hpp:141-153).  Rank by counting, straight from global memory.
-            const int m = valid / 2;
-            int cntX = 0, cntZ = 0;
-            for (int r = 0; r < 9; ++r)
-              for (int e = lane; e < s_rlen[r]; e += 32) {
-                float4 p = a.surfS[s_rbeg[r] + e];
-                float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-                if (!(d2 < a.r2_lrf) || (p.x == kx && p.y == ky && p.z == kz)) continue;
-                int idx = __float_as_int(a.snrmS[s_rbeg[r] + e].w);
-                int rank = 0;
-                for (int r2 = 0; r2 < 9; ++r2)
-                  for (int e2 = 0; e2 < s_rlen[r2]; ++e2) {
-                    float4 q = a.surfS[s_rbeg[r2] + e2];
-                    float q2 = sqdist3_rn(kx, ky, kz, q.x, q.y, q.z);
-                    if (!(q2 < a.r2_lrf) || (q.x == kx && q.y == ky && q.z == kz)) continue;
-                    int qi = __float_as_int(a.snrmS[s_rbeg[r2] + e2].w);
-                    if (q2 < d2 || (q2 == d2 && qi < idx)) ++rank;
-                  }
-                if (rank >= m - 2 && rank <= m + 2) {
-                  double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
-                         vz = (double)__fsub_rn(p.z, kz);
-                  if (vx * x[0] + vy * x[1] + vz * x[2] > 0) ++cntX;
-                  if (vx * z[0] + vy * z[1] + vz * z[2] > 0) ++cntZ;
-                }
+            // Tie (about 2% of real keypoints): the reference looks at the 5 neighbours around the median of the
+            // (d^2, index)-sorted valid list (shot_na_lrf.hpp:141-153).  Rank selection by bisection on the 63-bit
+            // key (d^2 bits << 32 | index): 63 counting passes over the staged points + 5 successive-minimum passes.
+            auto scan = [&](auto&& f) {
+              if (!multi) {
+                for (int e = lane; e < T; e += 32) f(s_pts[e], __float_as_int(s_nrm[e].w));
+              } else {
+                for (int r = 0; r < 9; ++r)
+                  for (int e = lane; e < s_rlen[r]; e += 32)
+                    f(a.surfS[s_rbeg[r] + e], __float_as_int(a.snrmS[s_rbeg[r] + e].w));
               }
-            cntX = warp_sum(cntX);
-            cntZ = warp_sum(cntZ);
+            };
+            const unsigned long long kInvalid = ~0ull;
+            auto key_of = [&](const float4& p, int idx) -> unsigned long long {
+              float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+              if (!(d2 < a.r2_lrf) || (p.x == kx && p.y == ky && p.z == kz)) return kInvalid;
+              return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)idx;
+            };
+            const int m = valid / 2;
+            unsigned long long lo = 0, hi = 0x7f80000000000000ull;  // every valid key is below hi
+            while (lo < hi) {  // smallest K with #{key <= K} >= m - 1  ==  key of 0-based rank m - 2
+              const unsigned long long mid = lo + ((hi - lo) >> 1);
+              int c = 0;
+              scan([&](const float4& p, int idx) { c += key_of(p, idx) <= mid ? 1 : 0; });
+              c = warp_sum(c);
+              if (c >= m - 1) hi = mid; else lo = mid + 1;
+            }
+            int cntX = 0, cntZ = 0;
+            unsigned long long prev = lo;  // first of the five
+            for (int j = 0; j < 5; ++j) {
+              unsigned long long bk = kInvalid;
+              float bx = 0.f, by = 0.f, bz = 0.f;
+              scan([&](const float4& p, int idx) {
+                unsigned long long k = key_of(p, idx);
+                bool take = (j == 0) ? (k >= prev) : (k > prev);
+                if (take && k < bk) { bk = k; bx = p.x; by = p.y; bz = p.z; }
+              });
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o),
+                      oz = __shfl_xor_sync(0xffffffffu, bz, o);
+                if (ok < bk) { bk = ok; bx = ox; by = oy; bz = oz; }
+              }
+              if (bk == kInvalid) break;
+              prev = bk;
+              double vx = (double)__fsub_rn(bx, kx), vy = (double)__fsub_rn(by, ky), vz = (double)__fsub_rn(bz, kz);
+              if (vx * x[0] + vy * x[1] + vz * x[2] > 0) ++cntX;
+              if (vx * z[0] + vy * z[1] + vz * z[2] > 0) ++cntZ;
+            }
             if (sx == 0) sx = (cntX < 3) ? -1 : 1;
             if (sz == 0) sz = (cntZ < 3) ? -1 : 1;
           }
