@@ -183,7 +183,8 @@ int pcdb_distance_pairs(pcdb_ctx* ctx, const float* a, const float* b, int64_t n
 
 /* Codebook::castVotes + CodewordDistribution::castVotes/castVote (codebook/codebook.cpp:403-555,
  * codebook/codeword_distribution.cpp:73-167).  Votes are emitted per cloud in (feature, activation rank,
- * stored vote) order.  vote_off_out has B+1 entries. */
+ * stored vote) order.  vote_off_out has B+1 entries.  Entries of knn_idx that are negative are skipped (rows owned by
+ * another shard of a row-sharded codebook). */
 int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9, const int64_t* feat_off,
                     int32_t B, const int32_t* knn_idx, const float* knn_dist, const int32_t* knn_count,
                     int32_t k, pcdb_vote* votes_out, int64_t* vote_off_out, int64_t vote_capacity);

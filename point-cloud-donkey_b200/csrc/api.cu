@@ -765,6 +765,7 @@ int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9
   const int64_t F = feat_off[B];
   for (int64_t i = 0; i < F; ++i)
     for (int j = 0; j < knn_count[i] && j < k; ++j) {
+      if (knn_idx[i * k + j] < 0) continue;  // masked: the row lives in another codebook shard
       int64_t r = (int64_t)knn_idx[i * k + j] - ctx->cb.row_base;
       if (r < 0 || r >= ctx->cb.N) return ctx->fail(PCDB_E_INVALID, "activated row %d outside this codebook shard", knn_idx[i * k + j]);
     }

@@ -116,7 +116,7 @@ __global__ void k_vote_count(VoteArgs a, int* cnt) {
   long long f = t / a.k;
   int j = (int)(t % a.k);
   int c = 0;
-  if (j < a.knn_cnt[f]) {
+  if (j < a.knn_cnt[f] && a.knn_idx[t] >= 0) {  // negative = activated row owned by another codebook shard
     long long row = (long long)a.knn_idx[t] - a.row_base;
     float dist = a.knn_dist[t];
     for (long long v = a.vote_off[row]; v < a.vote_off[row + 1]; ++v) {
@@ -133,7 +133,7 @@ __global__ void k_vote_write(VoteArgs a, const int* __restrict__ pos, const int*
   if (t >= a.F * a.k) return;
   long long f = t / a.k;
   int j = (int)(t % a.k);
-  if (j >= a.knn_cnt[f]) return;
+  if (j >= a.knn_cnt[f] || a.knn_idx[t] < 0) return;
   long long row = (long long)a.knn_idx[t] - a.row_base;
   float dist = a.knn_dist[t];
   int o = pos[t];
