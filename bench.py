@@ -155,6 +155,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1 and args.impl == "b200":
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("PCDB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = api.Context(device=local_rank)
@@ -171,6 +172,7 @@ def main():
     # -------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
         from oracle import oracle_py as orc
+        orc.set_num_threads(os.cpu_count() or 1)
         model = orc.Model(prm, cb)
         cores = orc.num_threads()
         x, n, c, o, _ = test_batch(wl, 16, 0, 0)
@@ -282,6 +284,7 @@ def main():
     cpu_base = None
     if rank == 0:
         from oracle import oracle_py as orc
+        orc.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
         model = orc.Model(prm, cb)
         x, n, c, o, _ = batches[0]
         gl = ctx.classify_batch(x[:o[2]], n[:o[2]], c[:o[2]], o[:3], want_maxima=False)[0]
@@ -327,6 +330,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # rank 0 checks labels against the oracle after the timed region; leave together
         dist.destroy_process_group()
     ctx.close()
     return 0
