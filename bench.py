@@ -87,7 +87,7 @@ def build_world(name, n_words_override, ctx, rank_log=True):
     t0 = time.time()
     # probe keypoints per cloud, then size the training set for ~n_words codewords
     x, n, c, o = synth.make_clouds(list(range(min(n_cls, 8))), [10_000 + i for i in range(min(n_cls, 8))], P,
-                                   scale=wl["scale"], jitter=0.002 * wl["scale"])
+                                   scale=wl["scale"], jitter=0.002)
     per_cloud = max(1.0, ctx.compute_features(x, n, c, o)[0].shape[0] / min(n_cls, 8))
     per_class = max(1, int(round(n_words / per_cloud / n_cls)))
     tr_cls = [cc for cc in range(n_cls) for _ in range(per_class)]
@@ -96,7 +96,7 @@ def build_world(name, n_words_override, ctx, rank_log=True):
     chunk = 256
     for s in range(0, len(tr_cls), chunk):
         x, n, c, o = synth.make_clouds(tr_cls[s:s + chunk], seeds[s:s + chunk], P, scale=wl["scale"],
-                                       jitter=0.002 * wl["scale"])
+                                       jitter=0.002)
         a = ctx.compute_features(x, n, c, o)
         fx.append(a[0]), fl.append(a[1]), fd.append(a[2]), counts.append(np.diff(a[3]))
         bbs.extend(train.aabb(x[o[i]:o[i + 1]]) for i in range(len(o) - 1))
@@ -114,7 +114,7 @@ def build_world(name, n_words_override, ctx, rank_log=True):
 def test_batch(wl, batch, rank, step):
     cls = [(rank * 7919 + step * 104729 + i) % wl["n_classes"] for i in range(batch)]
     seeds = [50_000_000 + rank * 10_000_000 + step * 100_000 + i for i in range(batch)]
-    x, n, c, o = synth.make_clouds(cls, seeds, wl["P"], scale=wl["scale"], jitter=0.002 * wl["scale"])
+    x, n, c, o = synth.make_clouds(cls, seeds, wl["P"], scale=wl["scale"], jitter=0.002)
     return x, n, c, o, np.asarray(cls)
 
 
@@ -306,6 +306,21 @@ def main():
 
     if rank == 0:
         fm = np.mean(np.array(stage_ms), axis=0) if stage_ms else np.zeros(4)
+        # HBM-side stages, algorithmic bytes from the measured neighbour / vote counts
+        per = 1.0 / max(1, args.steps)
+        color = cb.D == 1344
+        feat_bytes = per * (st["n_points"] * 40.0 + st["n_neighbours_lrf"] * 16.0 + st["n_keypoints"] * 36.0
+                            + st["n_neighbours_shot"] * (36.0 if color else 32.0) + st["n_features"] * (cb.D * 4.0 + 36.0))
+        vote_bytes = per * st["n_votes"] * (52.0 + 80.0)
+        stage_roofs = {
+            "features (voxel grid + LRF + SHOT)": {
+                "bound": "hbm", "bytes_per_step": feat_bytes, "ms_per_step": float(fm[0]),
+                "achieved": feat_bytes / (float(fm[0]) / 1e3) / 1e9 if fm[0] > 0 else None, "peak": pk["hbm"],
+                "unit": "GB/s", "note": "neighbourhood gathers hit L2/smem; the stage is bound by the fp64 geometry and "
+                                        "shared-memory histogram atomics, not HBM (see DESIGN.md)"},
+            "votes": {"bound": "hbm", "bytes_per_step": vote_bytes, "ms_per_step": float(fm[2]),
+                      "achieved": vote_bytes / (float(fm[2]) / 1e3) / 1e9 if fm[2] > 0 else None, "peak": pk["hbm"],
+                      "unit": "GB/s"}}
         line = {
             "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -320,6 +335,7 @@ def main():
                          "peak_source": pk["src"], "flop_per_launch": flop_per_launch, "ms_per_launch": avg_gemm_ms,
                          "share_of_step": avg_gemm_ms / (ms_total / args.steps) if ms_total else None},
             "cpu_baseline": cpu_base,
+            "roofline_stages": stage_roofs,
             "clocks": sampler.summary(),
             "stage_ms_per_step": {"features": float(fm[0]), "activation": float(fm[1]), "votes": float(fm[2]),
                                   "maxima": float(fm[3])},

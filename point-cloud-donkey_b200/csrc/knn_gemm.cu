@@ -3,18 +3,26 @@
 // Replaces the FLANN index search behind ActivationStrategyKNN::activateKNN
 // (activation_strategy/activation_strategy_knn.h:57-92; index built at utils/flann_helper.cpp:21-70) for
 // DistanceType "Euclidean":  d(q,c) = |q|^2 + |c|^2 - 2 q.c.  The q.c term is an fp16 x fp16 -> fp32 GEMM issued with
-// tcgen05.mma (cta_group::1, M=128, N=256, K=16) from TMA-staged, 128B-swizzled shared-memory tiles with the
-// accumulator double-buffered in TMEM.  The M x N score matrix is never written: four epilogue warps read each
-// accumulator tile back with tcgen05.ld, add |c|^2 and keep, per query row, every column whose approximate distance
-// is within a RIGOROUS error margin of the running k-th best.  Those candidates are re-ranked with the exact FLANN
-// fp32 arithmetic (knn_scan.cu:k_rerank), so the neighbour set equals the exact scan's.
+// tcgen05.mma (cta_group::2: a CTA pair on one TPC computes a 256 x 256 tile, M=256, N=256, K=16) from TMA-staged,
+// 128B-swizzled shared-memory tiles with the accumulator double-buffered in TMEM.  The M x N score matrix is never
+// written: eight epilogue warps per CTA read each accumulator tile back with tcgen05.ld, add |c|^2 and keep, per query
+// row, every column whose approximate distance is within a RIGOROUS error margin of the running k-th best.  Those
+// candidates are re-ranked with the exact FLANN fp32 arithmetic (knn_scan.cu:k_rerank), so the neighbour set equals
+// the exact scan's.
 //
-// Tiling: one CTA owns a 128-query tile whose fp16 descriptors stay RESIDENT in shared memory for the whole sweep
-// (D=352: 6 K-blocks of 64, the last one half used — the TMA zero-fills columns >= D, and only 2 of its 4 MMAs are
-// issued, so no flop is wasted on padding) while 256-codeword tiles stream through a 4-stage mbarrier ring.  Only the
-// codebook side is streamed, which halves the L2->SM traffic of a textbook 128x256 GEMM.  For D=1344 the query tile
-// does not fit and both operands stream.  All CTAs sweep the codebook in the same order, so each codebook tile is
-// fetched from HBM roughly once and shared through the 126 MB L2.
+// Tiling: each CTA of a pair owns 128 queries whose fp16 descriptors stay RESIDENT in its shared memory for the whole
+// sweep (D=352: 6 K-blocks of 64, the last one half used — the TMA zero-fills columns >= D, and only 2 of its 4 MMAs
+// are issued, so no flop is wasted on padding) while 256-codeword tiles stream through a 7-stage mbarrier ring, each
+// CTA fetching HALF of every codebook tile (128 rows).  Per SM that is 256 flop per streamed byte: a single-CTA
+// 128-row tile needs 64 B/clk/SM from L2 at full tensor rate, i.e. 9.5 KB/clk chip-wide against a measured L2 cap of
+// about 6.3 KB/clk (the first version of this kernel sat exactly on that cap, profiles/r01_gemm_c3_1cta.txt); the pair
+// needs half.  For D=1344 the query tile does not fit and both operands stream.  All pairs sweep the codebook in the
+// same order, so codebook tiles are shared through the 126 MB L2.
+//
+// Pair protocol (leader = even CTA of the cluster): both CTAs issue their TMA loads with .cta_group::2 so the bytes
+// are counted on the LEADER's "full" barrier; the leader's elected thread issues every MMA; tcgen05.commit
+// ...multicast::cluster arrives on the "empty"/"tmem_full" barriers of BOTH CTAs; the epilogue warps of both CTAs
+// release an accumulator by arriving on the leader's "tmem_empty" barrier.
 //
 // Error margin (DESIGN.md "activation"): with qh = fp16(q), ch = fp16(c),
 //   |q.c - fl(qh.ch)| <= |q-qh| |c| + |qh| |c-ch| + |q-qh| |c-ch| + D 2^-22 |qh| |ch|
@@ -27,11 +35,14 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int BN_HALF = BN / 2;         // codebook rows each CTA of a pair stages per tile
 constexpr int THREADS = 384;            // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_THREADS = 256;        // two epilogue warps per TMEM lane quarter, one per 128-column half
-constexpr int A_BOX_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_BOX_BYTES = BN * BK * 2;  // 32 KB
+constexpr int EPI_WARPS = EPI_THREADS / 32;
+constexpr int A_BOX_BYTES = BM * BK * 2;       // 16 KB
+constexpr int B_BOX_BYTES = BN_HALF * BK * 2;  // 16 KB per CTA
+constexpr int MAX_STAGES = 7;
+constexpr unsigned kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
 constexpr int KB_RES_MAX = 6;             // resident K-blocks (D <= 384)
 constexpr int CAND_CAP = 64;              // candidates per (query, codebook split)
 constexpr unsigned TMEM_COLS = 512;
@@ -84,21 +95,55 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// pair load: lands in the issuing CTA's shared memory, transaction bytes are counted on the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_id_x() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned n_clusters_x() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(unsigned long long* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
                                            unsigned idesc, unsigned accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -131,13 +176,13 @@ __device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major,
-// N>>3 in [17,23), M>>4 in [24,29).
-constexpr unsigned kIdesc = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+// N>>3 in [17,23), M>>4 in [24,29); M is the pair's 256 rows.
+constexpr unsigned kIdesc = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
 
 struct GemmArgs {
   long long Q, N;
   int D;
-  int n_mtiles, n_ntiles, tiles_per_split, n_splits;
+  int n_mpairs, n_ntiles, tiles_per_split, n_splits;  // n_mpairs: 256-query tile pairs
   const float* cnorm;    // |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
   int* cand_idx;         // [Q][2 S][CAND_CAP]   (2 column halves per codebook split)
@@ -148,72 +193,79 @@ struct GemmArgs {
 
 struct __align__(16) Barriers {
   float cn[2][BN];  // |c|^2 of the tile in each accumulator buffer, staged by the epilogue warps
-  unsigned long long full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
+  unsigned long long full[MAX_STAGES], empty[MAX_STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   unsigned tmem_base;
 };
 
 template <bool A_RES, int KT>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  // layout: [A resident: KB_RES_MAX boxes]? [STAGES x (A box if !A_RES) + B box] [barriers]
+  // layout (identical in both CTAs of the pair — the MMA addresses both through one descriptor):
+  //   [A resident: KB_RES_MAX boxes]? [STAGES x (B half box + A box if !A_RES)] [barriers]
+  constexpr int STAGES = A_RES ? 7 : 6;
+  constexpr int STAGE_BYTES = B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES);
   unsigned char* a_res = smem;
   unsigned char* stage0 = smem + (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0);
-  constexpr int STAGE_BYTES = B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(stage0 + STAGES * STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const bool leader = rank == 0;
+  const int pair_id = (int)cluster_id_x(), n_pairs = (int)n_clusters_x();
   const int KB = (g.D + BK - 1) / BK;
   const int k_steps_last = (g.D - (KB - 1) * BK) / UMMA_K;
-  const int n_units = g.n_mtiles * g.n_splits;
+  const int n_units = g.n_mpairs * g.n_splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->full[s], 1);   // leader's producer (arrive.expect_tx); bytes come from both CTAs
+      mbar_init(&bars->empty[s], 1);  // multicast tcgen05.commit
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], EPI_THREADS);
+      mbar_init(&bars->tmem_empty[a], 2 * EPI_WARPS);  // one arrival per epilogue warp of both CTAs (leader's copy)
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+  if (warp == 2) {  // the same warp of both CTAs: the pair allocation is collective
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
                  "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers initialised and TMEM allocated in both CTAs before anyone signals across
   tc_fence_after();
   const unsigned tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================================================== TMA producer (one elected lane)
+    // ===================================================== TMA producer (one elected lane in each CTA)
     if (lane == 0) {
       int stage = 0;
       unsigned phase = 0, a_phase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int mt = unit % g.n_mtiles, split = unit / g.n_mtiles;
+      for (int unit = pair_id; unit < n_units; unit += n_pairs) {
+        const int mp = unit % g.n_mpairs, split = unit / g.n_mpairs;
         const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
+        const int q_row0 = (mp * 2 + (int)rank) * BM;
         if (A_RES) {
           mbar_wait(&bars->a_empty, a_phase ^ 1);  // previous unit's MMAs are done with the resident tile
-          mbar_expect_tx(&bars->a_full, (unsigned)(KB * A_BOX_BYTES));
-          for (int kb = 0; kb < KB; ++kb) tma_load_2d(a_res + kb * A_BOX_BYTES, &map_a, &bars->a_full, kb * BK, mt * BM);
+          if (leader) mbar_expect_tx(&bars->a_full, (unsigned)(2 * KB * A_BOX_BYTES));
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d_pair(a_res + kb * A_BOX_BYTES, &map_a, &bars->a_full, kb * BK, q_row0);
           a_phase ^= 1;
         }
         for (int t = t0; t < t1; ++t)
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             unsigned char* sb = stage0 + stage * STAGE_BYTES;
-            mbar_expect_tx(&bars->full[stage], (unsigned)STAGE_BYTES);
-            tma_load_2d(sb, &map_b, &bars->full[stage], kb * BK, t * BN);
-            if (!A_RES) tma_load_2d(sb + B_BOX_BYTES, &map_a, &bars->full[stage], kb * BK, mt * BM);
+            if (leader) mbar_expect_tx(&bars->full[stage], (unsigned)(2 * STAGE_BYTES));
+            tma_load_2d_pair(sb, &map_b, &bars->full[stage], kb * BK, t * BN + (int)rank * BN_HALF);
+            if (!A_RES) tma_load_2d_pair(sb + B_BOX_BYTES, &map_a, &bars->full[stage], kb * BK, q_row0);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -222,19 +274,19 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one elected lane)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (one elected lane of the leader CTA)
+    if (lane == 0 && leader) {
       int stage = 0, acc = 0;
       unsigned phase = 0, acc_phase = 0, a_phase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int split = unit / g.n_mtiles;
+      for (int unit = pair_id; unit < n_units; unit += n_pairs) {
+        const int split = unit / g.n_mpairs;
         const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
         if (A_RES) {
           mbar_wait(&bars->a_full, a_phase);
           a_phase ^= 1;
         }
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator
           tc_fence_after();
           const unsigned tmem_d = tmem_base + (unsigned)(acc * BN);
           for (int kb = 0; kb < KB; ++kb) {
@@ -249,19 +301,19 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
               tc_mma_f16(tmem_d, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2),
                          kIdesc, (kb | k) ? 1u : 0u);
             }
-            tc_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+            tc_commit_pair(&bars->empty[stage]);  // frees the slot in both CTAs once these MMAs have read it
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          tc_commit_pair(&bars->tmem_full[acc]);  // accumulator complete -> both epilogues
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        if (A_RES) tc_commit(&bars->a_empty);
+        if (A_RES) tc_commit_pair(&bars->a_empty);
       }
     }
   } else if (warp >= 4) {
@@ -271,10 +323,10 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const int epi_tid = (warp - 4) * 32 + lane;
     int acc = 0;
     unsigned acc_phase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int mt = unit % g.n_mtiles, split = unit / g.n_mtiles;
+    for (int unit = pair_id; unit < n_units; unit += n_pairs) {
+      const int mp = unit % g.n_mpairs, split = unit / g.n_mpairs;
       const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
-      const long long row = (long long)mt * BM + grp * 32 + lane;
+      const long long row = (long long)(mp * 2 + (int)rank) * BM + grp * 32 + lane;
       const bool active = row < g.Q;
       const float margin = active ? g.margin[row] : 0.f;
       float best[KT];
@@ -347,7 +399,8 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
 #undef PCDB_FILTER_CHUNK
         tc_fence_before();
-        mbar_arrive(&bars->tmem_empty[acc]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -360,10 +413,10 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // every MMA has completed and been read back in both CTAs; no remote arrival is still in flight
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -505,8 +558,29 @@ GemmState* state_of(pcdb_ctx* ctx) {
 template <bool A_RES, int KT>
 int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, int grid) {
   const size_t smem = (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0) +
-                      (size_t)STAGES * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
-  PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                      (size_t)(A_RES ? 7 : 6) * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
+  // co-resident CTA pairs: GPCs with an odd number of usable SMs leave one SM without a partner, and a pair that
+  // cannot be resident from the start would run after the others and double the sweep time
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    PCDB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_knn_gemm<A_RES, KT>, &cfg));
+    if (n < 1) return ctx->fail(PCDB_E_CUDA, "no CTA pair of k_knn_gemm can be resident on this device");
+    max_clusters = n;
+  }
+  grid = 2 * std::min(grid / 2, max_clusters);
   k_knn_gemm<A_RES, KT><<<grid, THREADS, smem, ctx->stream>>>(map_a, map_b, g);
   PCDB_LAUNCH_CHECK();
   return PCDB_OK;
@@ -560,7 +634,7 @@ int gemm_prepare_codebook(pcdb_ctx* ctx) {
   gs->cerr_max = h[1];
   gs->cmax2 = h[2];
   if (!std::isfinite(h[0]) || !std::isfinite(h[2])) return PCDB_OK;  // non-finite codewords: scan path only
-  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, cb.D, BN));
+  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, cb.D, BN_HALF));
   cb.gemm_ready = true;
   return PCDB_OK;
 }
@@ -593,11 +667,12 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.Q = Q;
   g.N = cb.N;
   g.D = D;
-  g.n_mtiles = (int)cdiv(Q, BM);
+  g.n_mpairs = (int)cdiv(Q, 2 * BM);
   g.n_ntiles = (int)cdiv(cb.N, BN);
-  // split the codebook sweep when there are fewer query tiles than SMs
+  // split the codebook sweep when there are fewer 256-query tile pairs than CTA pairs
+  const int max_pairs = std::max(1, ctx->sm_count / 2);
   int S = 1;
-  if (g.n_mtiles < ctx->sm_count) S = std::min(g.n_ntiles, std::max(1, ctx->sm_count / g.n_mtiles));
+  if (g.n_mpairs < max_pairs) S = std::min(g.n_ntiles, std::max(1, max_pairs / g.n_mpairs));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
   g.n_splits = S;
@@ -615,7 +690,7 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.cand_apx = w.cand_apx.as<float>();
   g.cand_cnt = w.cand_cnt.as<int>();
   g.cand_thr = w.cand_thr.as<float>();
-  const int grid = std::min(g.n_mtiles * S, ctx->sm_count);
+  const int grid = 2 * std::min(g.n_mpairs * S, max_pairs);  // CTA pairs (cluster of 2)
   const bool a_res = (D + BK - 1) / BK <= KB_RES_MAX;
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
   PCDB_CUDA(cudaEventRecord(e0, st));

@@ -138,6 +138,38 @@ def make_clouds(class_ids, seeds, P, proto_seed=0, scale=1.0, jitter=0.002, rota
     return np.concatenate(xs), np.concatenate(ns), np.concatenate(cs), np.asarray(off, np.int64)
 
 
+def make_scene(class_ids, seed, P_obj, spacing=2.5, plane_points=6000, clutter_points=1500, scale=1.0, jitter=0.002):
+    """C5-shaped cluttered scene: object instances on a grid above a table plane plus uniform clutter.
+    Returns xyz, normals, rgb and the ground truth (class id, instance centre) per object."""
+    rng = np.random.default_rng([int(seed), 15485863])
+    xs, ns, cs, truth = [], [], [], []
+    side = int(np.ceil(np.sqrt(len(class_ids))))
+    for i, cid in enumerate(class_ids):
+        x, n, c = Prototype(cid, 0).sample(P_obj, np.random.default_rng([int(seed) + i, 104729]), jitter=jitter,
+                                           rotate=True, scale=scale)
+        shift = np.array([(i % side) * spacing, (i // side) * spacing, 0.0], np.float32) * scale
+        lo, hi = x.min(0), x.max(0)
+        shift[2] = -lo[2]  # rest on the table z = 0
+        xs.append((x + shift).astype(np.float32))
+        ns.append(n)
+        cs.append(c)
+        truth.append((cid, (0.5 * (lo + hi) + shift).astype(np.float32)))
+    ext = side * spacing * scale
+    pl = np.zeros((plane_points, 3), np.float32)
+    pl[:, :2] = rng.uniform(-0.5 * spacing * scale, ext, (plane_points, 2))
+    pl[:, 2] = rng.normal(0, jitter * scale, plane_points)
+    xs.append(pl)
+    ns.append(np.tile(np.array([0, 0, 1], np.float32), (plane_points, 1)))
+    cs.append(np.full(plane_points, 0x808080, np.uint32))
+    cl = rng.uniform([-0.5 * spacing * scale] * 2 + [0], [ext, ext, scale], (clutter_points, 3)).astype(np.float32)
+    cn = rng.normal(size=(clutter_points, 3)).astype(np.float32)
+    cn /= np.linalg.norm(cn, axis=1, keepdims=True)
+    xs.append(cl)
+    ns.append(cn)
+    cs.append(rng.integers(0, 1 << 24, clutter_points).astype(np.uint32))
+    return np.concatenate(xs), np.concatenate(ns), np.concatenate(cs), truth
+
+
 # ---- workload definitions (SURVEY.md 8d; configs of BASELINE.json) -------------------------------------
 WORKLOADS = {
     # C1: quick-start stand-in; radii of config/qs_input_config.ism (mm-like scale x250)

@@ -412,17 +412,96 @@ def test_classify_batch_chi2_quickstart_shape(api, orc):
     prm = synth.workload_params("c1")
     tr_cls = list(range(wl["n_classes"]))
     xyz, nrm, rgb, off = synth.make_clouds(tr_cls, [100 + c for c in tr_cls], wl["P"], scale=wl["scale"],
-                                           jitter=0.002 * wl["scale"])
+                                           jitter=0.002)
     fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
     bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
     cb = orc.train(prm, fx, fl, fd, foff, tr_cls, tr_cls, bb, wl["n_classes"])
     xt, nt, rt, ot = synth.make_clouds(tr_cls, [200 + c for c in tr_cls], wl["P"], scale=wl["scale"],
-                                       jitter=0.002 * wl["scale"])
+                                       jitter=0.002)
     c = api.Context(prm, cb)
     m = orc.Model(prm, cb)
     la, _, _ = c.classify_batch(xt, nt, rt, ot)
     lb, _, _ = m.classify_batch(xt, nt, rt, ot)
     assert np.array_equal(la, lb)
+    c.close()
+
+
+def _train_world(orc, prm, n_cls, n_train, P, scale=1.0, seed0=1000):
+    tr_cls = [c for c in range(n_cls) for _ in range(n_train)]
+    xyz, nrm, rgb, off = synth.make_clouds(tr_cls, [seed0 + i for i in range(len(tr_cls))], P, scale=scale)
+    fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
+    bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    return orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bb, n_cls)
+
+
+@pytest.mark.parametrize("dist_type", [DIST_EUCLIDEAN, DIST_CHISQUARED])
+def test_classify_batch_cshot_kinect_shape(api, orc, dist_type):
+    """C4 stand-in: CSHOT-1344 with the default_config_kinect.ism radii at object scale 0.2 m, both distances."""
+    wl = synth.WORKLOADS["c4"]
+    prm = synth.workload_params("c4", distance_type=dist_type)
+    n_cls = 4
+    cb = _train_world(orc, prm, n_cls, 2, 4096, scale=wl["scale"])
+    assert cb.D == 1344
+    te = [c for c in range(n_cls) for _ in range(2)]
+    xt, nt, rt, ot = synth.make_clouds(te, [7000 + i for i in range(len(te))], 4096, scale=wl["scale"])
+    c = api.Context(prm, cb)
+    m = orc.Model(prm, cb)
+    la, mxa, offa = c.classify_batch(xt, nt, rt, ot)
+    lb, mxb, offb = m.classify_batch(xt, nt, rt, ot)
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb)
+    assert np.array_equal(mxa["class_id"], mxb["class_id"]) and np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    assert np.allclose(mxa["weight"], mxb["weight"], rtol=2e-3, atol=1e-5)
+    assert np.allclose(mxa["position"], mxb["position"], atol=2e-3 * wl["scale"])
+    assert c.stats()["n_votes"] == m.last_counts["votes"] > 0
+    c.close()
+
+
+def test_classify_batch_through_gemm_activation(api, orc):
+    """A codebook above the GEMM threshold (>= 8192 words): the fused path takes the tcgen05 candidate filter and must
+    still return the oracle's labels, maxima and vote counts."""
+    prm = synth.workload_params("c2")
+    n_cls = 5
+    cb = _train_world(orc, prm, n_cls, 7, 2048)
+    assert cb.N >= 8192
+    te = [c for c in range(n_cls) for _ in range(2)]
+    xt, nt, rt, ot = synth.make_clouds(te, [8000 + i for i in range(len(te))], 2048)
+    c = api.Context(prm, cb)
+    m = orc.Model(prm, cb)
+    la, mxa, offa = c.classify_batch(xt, nt, rt, ot)
+    lb, mxb, offb = m.classify_batch(xt, nt, rt, ot)
+    st = c.stats()
+    assert st["knn_gemm_ms"] > 0 and st["knn_candidates"] > 0
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb)
+    assert np.array_equal(mxa["class_id"], mxb["class_id"]) and np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    assert st["n_votes"] == m.last_counts["votes"]
+    c.close()
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_scene_multi_object_maxima_parity(api, orc, k):
+    """C5 stand-in: one cluttered scene, SingleObjectMode=false: the full ranked maxima list (class, instance, member
+    votes, weights, positions) must match the oracle's, and the six objects are found where they were placed."""
+    prm = synth.workload_params("c2", single_object_mode=0, knn_k=k, min_votes_threshold=3)
+    cb = _train_world(orc, prm, 4, 3, 1536)
+    classes = [0, 1, 2, 3, 1, 2]
+    x, n, col, truth = synth.make_scene(classes, 77, 1536)
+    off = np.array([0, len(x)], np.int64)
+    c = api.Context(prm, cb)
+    m = orc.Model(prm, cb)
+    la, mxa, offa = c.classify_batch(x, n, col, off)
+    lb, mxb, offb = m.classify_batch(x, n, col, off)
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb) and offa[1] >= len(classes)
+    assert np.array_equal(mxa["class_id"], mxb["class_id"])
+    assert np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    assert np.array_equal(mxa["instance_id"], mxb["instance_id"])
+    assert np.allclose(mxa["weight"], mxb["weight"], rtol=2e-3, atol=1e-6)
+    assert np.allclose(mxa["position"], mxb["position"], atol=3e-3)
+    assert c.stats()["n_votes"] == m.last_counts["votes"]
+    top = mxa[: len(classes)]
+    for cid, centre in truth:
+        d = np.linalg.norm(top["position"] - centre, axis=1)
+        j = int(np.argmin(d))
+        assert d[j] < 0.25 and top["class_id"][j] == cid
     c.close()
 
 
