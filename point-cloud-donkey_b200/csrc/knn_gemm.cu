@@ -175,6 +175,16 @@ __device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr
   d |= (unsigned long long)2 << 61;
   return d;
 }
+__device__ __forceinline__ unsigned long long desc64(unsigned lo, unsigned hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {  // the same lane every time for a full warp
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major,
 // N>>3 in [17,23), M>>4 in [24,29); M is the pair's 256 rows.
 constexpr unsigned kIdesc = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
@@ -274,10 +284,17 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one elected lane of the leader CTA)
-    if (lane == 0 && leader) {
+    // ===================================================== MMA issuer (leader CTA; the warp stays converged and one
+    // elected lane issues, so every loop variable is warp-uniform and the descriptors live in uniform registers: the
+    // issue loop must stay well under the 128 clk an M=256 x N=256 x K=16 MMA takes, or it becomes the bottleneck)
+    if (leader) {
       int stage = 0, acc = 0;
       unsigned phase = 0, acc_phase = 0, a_phase = 0;
+      // descriptor halves: hi = SBO | version | SWIZZLE_128B (constant), lo = (address >> 4) | LBO; a K step of 16
+      // halves (32 bytes) inside the 128-byte swizzle atom adds 2 to lo
+      constexpr unsigned kDescHi = (unsigned)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const unsigned a_lo0 = ((smem_u32(a_res) & 0x3FFFFu) >> 4) | (1u << 16);
+      const unsigned s_lo0 = ((smem_u32(stage0) & 0x3FFFFu) >> 4) | (1u << 16);
       for (int unit = pair_id; unit < n_units; unit += n_pairs) {
         const int split = unit / g.n_mpairs;
         const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
@@ -292,28 +309,37 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
-            unsigned char* sb = stage0 + stage * STAGE_BYTES;
-            const unsigned a_addr = A_RES ? smem_u32(a_res + kb * A_BOX_BYTES) : smem_u32(sb + B_BOX_BYTES);
-            const unsigned b_addr = smem_u32(sb);
-            const int ks = (kb == KB - 1) ? k_steps_last : (BK / UMMA_K);
-            for (int k = 0; k < ks; ++k) {
-              // advance along K inside the 128-byte swizzle atom: +32 bytes per UMMA_K
-              tc_mma_f16(tmem_d, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2),
-                         kIdesc, (kb | k) ? 1u : 0u);
+            const unsigned b_lo = s_lo0 + (unsigned)(stage * (STAGE_BYTES >> 4));
+            const unsigned a_lo = A_RES ? a_lo0 + (unsigned)(kb * (A_BOX_BYTES >> 4)) : b_lo + (B_BOX_BYTES >> 4);
+            if (elect_one()) {
+              if (kb < KB - 1 || k_steps_last == BK / UMMA_K) {
+                tc_mma_f16(tmem_d, desc64(a_lo, kDescHi), desc64(b_lo, kDescHi), kIdesc, kb ? 1u : 0u);
+                tc_mma_f16(tmem_d, desc64(a_lo + 2, kDescHi), desc64(b_lo + 2, kDescHi), kIdesc, 1u);
+                tc_mma_f16(tmem_d, desc64(a_lo + 4, kDescHi), desc64(b_lo + 4, kDescHi), kIdesc, 1u);
+                tc_mma_f16(tmem_d, desc64(a_lo + 6, kDescHi), desc64(b_lo + 6, kDescHi), kIdesc, 1u);
+              } else {
+                for (int k = 0; k < k_steps_last; ++k)
+                  tc_mma_f16(tmem_d, desc64(a_lo + 2 * k, kDescHi), desc64(b_lo + 2 * k, kDescHi), kIdesc,
+                             (kb | k) ? 1u : 0u);
+              }
+              tc_commit_pair(&bars->empty[stage]);  // frees the slot in both CTAs once these MMAs have read it
+              if (kb == KB - 1) tc_commit_pair(&bars->tmem_full[acc]);  // accumulator complete -> both epilogues
             }
-            tc_commit_pair(&bars->empty[stage]);  // frees the slot in both CTAs once these MMAs have read it
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          tc_commit_pair(&bars->tmem_full[acc]);  // accumulator complete -> both epilogues
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
           }
         }
-        if (A_RES) tc_commit_pair(&bars->a_empty);
+        if (A_RES) {
+          if (elect_one()) tc_commit_pair(&bars->a_empty);
+          __syncwarp();
+        }
       }
     }
   } else if (warp >= 4) {
