@@ -13,6 +13,8 @@
 // warp-shuffle reduction), 3x3 symmetric eigen-solve, pass B sign disambiguation, pass C quadrilinear soft histogram
 // accumulated in 32-bit fixed point in shared memory (native integer atomics => bit-reproducible across runs).
 // Geometry follows the reference's float/double choices; membership d^2 < r^2 is bit-exact.
+#include <cmath>
+
 #include "common.cuh"
 #include "stages.h"
 
@@ -40,6 +42,7 @@ struct ShotArgs {
   const int* n_items_ptr;
   double r_lrf, r_shot;
   float r2_lrf, r2_shot;
+  float t2_gt_r12, t2_gt_r34, t2_ge_r14;  // float thresholds on d^2 equivalent to the fp64 shell tests (see stage_shot)
   const float* lrf_in;
   float* lrf_out;
   float* desc_out;
@@ -143,9 +146,9 @@ __global__ void k_lab(const float4* __restrict__ pts, long long n, const float* 
 // spin loop on sm_100 and serialises badly when many neighbours hit one bin), and integer adds commute, so the
 // descriptor is bit-reproducible from run to run.  Every contribution is >= 0 and <= 4, a bin receives at most one
 // such contribution per staged point, hence scale = 2^floor(log2(2^32 / (4 T + 4))) cannot overflow.
-__device__ __forceinline__ void hist_add(unsigned* hist, int bin, double v, float scale) {
+__device__ __forceinline__ void hist_add(unsigned* hist, int bin, float v, float scale) {
   // the reference narrows every contribution to float before adding it (shot[..] += static_cast<float>(..))
-  atomicAdd(hist + bin, __float2uint_rn(__fmul_rn((float)v, scale)));
+  atomicAdd(hist + bin, __float2uint_rn(__fmul_rn(v, scale)));
 }
 
 struct StageView {
@@ -163,6 +166,8 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   float4* s_nrm = s_pts + kChunk;
   float4* s_lab = s_nrm + kChunk;  // only touched when COLOR
   unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(float4) * kChunk * (COLOR ? 3 : 2));
+  // per-warp compacted list of the staged points inside the current search radius (positions in the chunk)
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_hist + (size_t)kWarps * D);
   __shared__ long long s_rbeg[9];
   __shared__ int s_rlen[9];
   __shared__ int s_pref[10];
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = *a.n_items_ptr;
   unsigned* hist = s_hist + (size_t)warp * D;
+  unsigned short* list = s_list + (size_t)warp * kChunk;
 
   while (true) {
     __syncthreads();
@@ -235,12 +241,32 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         kx = k4.x; ky = k4.y; kz = k4.z;
         krgb = __float_as_uint(k4.w);
       }
+      // Radius filter first, heavy math second: the in-radius points of the chunk are compacted into this warp's list
+      // (ballot + popc, order = staging order), so the fp64 passes below run with all 32 lanes busy instead of
+      // diverging on the 30-50 % of the 27-cell neighbourhood that lies inside the sphere.
+      auto compact = [&](int cnt, float r2) -> int {
+        int n = 0;
+        if (have)
+          for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            bool in = false;
+            if (e < cnt) {
+              const float4 p = s_pts[e];
+              in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+            n += __popc(m);
+          }
+        __syncwarp();
+        return n;
+      };
       float rf[9];
       bool lrf_ok = have;
       // ---------------------------------------------------------------- LRF
       if (a.do_lrf) {
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, sw = 0;
-        int valid = 0, nall = 0;
+        int valid = 0, nall = 0, n_lrf = 0;
         for (int c = 0; c < max(n_chunks, 1); ++c) {
           if (multi) {
             __syncthreads();
@@ -248,11 +274,12 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             __syncthreads();
           }
           const int cnt = min(kChunk, T - c * kChunk);
+          n_lrf = compact(cnt, a.r2_lrf);
           if (have)
-            for (int e = lane; e < cnt; e += 32) {
-              float4 p = s_pts[e];
+            for (int i = lane; i < n_lrf; i += 32) {
+              float4 p = s_pts[list[i]];
               float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-              if (d2 < a.r2_lrf) {
+              {
                 ++nall;
                 if (!(p.x == kx && p.y == ky && p.z == kz)) {
                   double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
@@ -295,11 +322,11 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             __syncthreads();
           }
           const int cnt = min(kChunk, T - c * kChunk);
+          if (multi) n_lrf = compact(cnt, a.r2_lrf);  // single chunk: pass A's list is still valid
           if (lrf_ok)
-            for (int e = lane; e < cnt; e += 32) {
-              float4 p = s_pts[e];
-              float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-              if (d2 < a.r2_lrf && !(p.x == kx && p.y == ky && p.z == kz)) {
+            for (int i = lane; i < n_lrf; i += 32) {
+              float4 p = s_pts[list[i]];
+              if (!(p.x == kx && p.y == ky && p.z == kz)) {
                 double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
                        vz = (double)__fsub_rn(p.z, kz);
                 if (vx * x[0] + vy * x[1] + vz * x[2] >= 0) ++plusX;
@@ -316,8 +343,8 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             // (d^2, index)-sorted valid list (shot_na_lrf.hpp:141-153).  Rank selection by bisection on the 63-bit
             // key (d^2 bits << 32 | index): 63 counting passes over the staged points + 5 successive-minimum passes.
             auto scan = [&](auto&& f) {
-              if (!multi) {
-                for (int e = lane; e < T; e += 32) f(s_pts[e], __float_as_int(s_nrm[e].w));
+              if (!multi) {  // the LRF-radius list of passes A/B
+                for (int i = lane; i < n_lrf; i += 32) f(s_pts[list[i]], __float_as_int(s_nrm[list[i]].w));
               } else {
                 for (int r = 0; r < 9; ++r)
                   for (int e = lane; e < s_rlen[r]; e += 32)
@@ -398,8 +425,14 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         float3 l = rgb_to_lab_norm(krgb, a.lab_lut);
         LRef = l.x; aRef = l.y; bRef = l.z;
       }
-      const double r34 = (a.r_shot * 3) / 4, r14 = a.r_shot / 4, r12 = a.r_shot / 2;
-      const double inv_r12 = 1.0 / r12, inv_90 = 1.0 / PST_RAD_90, inv_45 = 1.0 / PST_RAD_45;
+      // Discrete decisions (volume index, histogram bin, which neighbour bin) are taken exactly as the reference takes
+      // them: on float-exact quantities, on fp64 bdS/bdC, and on the radial shells through float thresholds on d^2
+      // that are equivalent to the reference's fp64 "sqrt(d^2) > r/2" tests (computed on the host, stage_shot).  The
+      // CONTINUOUS interpolation weights (radial, inclination, azimuth) are evaluated in fp32: their error (~1e-7) is
+      // far inside the 1e-4 descriptor bar and saves the software fp64 sqrt / acos / atan2 that dominated this loop.
+      const float r34f = (float)((a.r_shot * 3) / 4), r14f = (float)(a.r_shot / 4);
+      const float inv_r12f = (float)(1.0 / (a.r_shot / 2));
+      const float inv_90f = (float)(1.0 / PST_RAD_90), inv_45f = (float)(1.0 / PST_RAD_45);
       int nshot = 0;
       for (int c = 0; c < max(n_chunks, 1); ++c) {
         if (multi) {
@@ -408,46 +441,49 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           __syncthreads();
         }
         const int cnt = min(kChunk, T - c * kChunk);
-        if (!frame_ok) continue;
-        for (int e = lane; e < cnt; e += 32) {
+        if (!frame_ok) continue;  // warp-uniform
+        const int n_in = compact(cnt, a.r2_shot);
+        for (int i = lane; i < n_in; i += 32) {
+          const int e = list[i];
           float4 p = s_pts[e];
           float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-          if (!(d2 < a.r2_shot)) continue;
           ++nshot;
           float4 nr = s_nrm[e];
           if (!finite3(nr.x, nr.y, nr.z)) continue;
           double cosineDesc = (double)dot3_rn(nr.x, nr.y, nr.z, rf[6], rf[7], rf[8]);
           cosineDesc = fmin(1.0, fmax(-1.0, cosineDesc));
           double bdS = ((1.0 + cosineDesc) * 10) / 2;
-          double distance = sqrt((double)d2);
-          if (fabs(distance) < 1E-15) continue;
+          if (d2 < 1E-30f) continue;  // reference: fabs(sqrt(d2)) < 1e-15
+          const float distance = __fsqrt_rn(d2);
           float dx = __fsub_rn(p.x, kx), dy = __fsub_rn(p.y, ky), dz = __fsub_rn(p.z, kz);
-          double xIn = (double)dot3_rn(dx, dy, dz, rf[0], rf[1], rf[2]);
-          double yIn = (double)dot3_rn(dx, dy, dz, rf[3], rf[4], rf[5]);
-          double zIn = (double)dot3_rn(dx, dy, dz, rf[6], rf[7], rf[8]);
-          if (fabs(yIn) < 1E-30) yIn = 0;
-          if (fabs(xIn) < 1E-30) xIn = 0;
-          if (fabs(zIn) < 1E-30) zIn = 0;
-          int bit4 = ((yIn > 0) || ((yIn == 0.0) && (xIn < 0))) ? 1 : 0;
-          int bit3 = ((xIn > 0) || ((xIn == 0.0) && (yIn > 0))) ? !bit4 : bit4;
+          float xIn = dot3_rn(dx, dy, dz, rf[0], rf[1], rf[2]);
+          float yIn = dot3_rn(dx, dy, dz, rf[3], rf[4], rf[5]);
+          float zIn = dot3_rn(dx, dy, dz, rf[6], rf[7], rf[8]);
+          if (fabsf(yIn) < 1E-30f) yIn = 0.f;
+          if (fabsf(xIn) < 1E-30f) xIn = 0.f;
+          if (fabsf(zIn) < 1E-30f) zIn = 0.f;
+          const bool same_sign = (xIn > 0.f && yIn > 0.f) || (xIn < 0.f && yIn < 0.f);  // xIn * yIn > 0 in fp64
+          int bit4 = ((yIn > 0.f) || ((yIn == 0.f) && (xIn < 0.f))) ? 1 : 0;
+          int bit3 = ((xIn > 0.f) || ((xIn == 0.f) && (yIn > 0.f))) ? !bit4 : bit4;
           int di = ((bit4 << 3) + (bit3 << 2)) << 1;
-          if ((xIn * yIn > 0) || (xIn == 0.0))
-            di += (fabs(xIn) >= fabs(yIn)) ? 0 : 4;
+          if (same_sign || (xIn == 0.f))
+            di += (fabsf(xIn) >= fabsf(yIn)) ? 0 : 4;
           else
-            di += (fabs(xIn) > fabs(yIn)) ? 4 : 0;
-          di += zIn > 0 ? 1 : 0;
-          di += (distance > r12) ? 2 : 0;
+            di += (fabsf(xIn) > fabsf(yIn)) ? 4 : 0;
+          di += zIn > 0.f ? 1 : 0;
+          const bool outer = d2 >= a.t2_gt_r12;  // sqrt((double)d2) > r/2
+          di += outer ? 2 : 0;
 
           int stepS = (int)floor(bdS + 0.5);
           const int volS = di * 11;
           bdS -= stepS;
-          double wS = 1 - fabs(bdS);
+          float wS = (float)(1 - fabs(bdS));
           if (bdS > 0)
-            hist_add(hist, volS + ((stepS + 1) % 10), bdS, fix_scale);
+            hist_add(hist, volS + ((stepS + 1) % 10), (float)bdS, fix_scale);
           else
-            hist_add(hist, volS + ((stepS - 1 + 10) % 10), -bdS, fix_scale);
+            hist_add(hist, volS + ((stepS - 1 + 10) % 10), (float)-bdS, fix_scale);
           int stepC = 0, volC = 0;
-          double wC = 0;
+          float wC = 0.f;
           if (COLOR) {
             float4 lb = s_lab[e];
             float cdist = __fdiv_rn(
@@ -459,73 +495,72 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             stepC = (int)floor(bdC + 0.5);
             volC = 352 + di * 31;
             bdC -= stepC;
-            wC = 1 - fabs(bdC);
+            wC = (float)(1 - fabs(bdC));
             if (bdC > 0)
-              hist_add(hist, volC + ((stepC + 1) % 30), bdC, fix_scale);
+              hist_add(hist, volC + ((stepC + 1) % 30), (float)bdC, fix_scale);
             else
-              hist_add(hist, volC + ((stepC - 1 + 30) % 30), -bdC, fix_scale);
+              hist_add(hist, volC + ((stepC - 1 + 30) % 30), (float)-bdC, fix_scale);
           }
-#define SHOT_NEIGHBOUR(DI, VAL)                                     \
-  do {                                                              \
-    hist_add(hist, (DI) * 11 + stepS, (VAL), fix_scale);                       \
-    if (COLOR) hist_add(hist, 352 + (DI) * 31 + stepC, (VAL), fix_scale);      \
+#define SHOT_NEIGHBOUR(DI, VAL)                                           \
+  do {                                                                    \
+    hist_add(hist, (DI) * 11 + stepS, (VAL), fix_scale);                  \
+    if (COLOR) hist_add(hist, 352 + (DI) * 31 + stepC, (VAL), fix_scale); \
   } while (0)
-          double wAdd = 0;
-          if (distance > r12) {
-            double rd = (distance - r34) * inv_r12;
-            if (distance > r34)
-              wAdd += 1 - rd;
+          float wAdd = 0.f;
+          if (outer) {
+            float rd = (distance - r34f) * inv_r12f;
+            if (d2 >= a.t2_gt_r34)  // sqrt((double)d2) > 3r/4
+              wAdd += 1.f - rd;
             else {
-              wAdd += 1 + rd;
+              wAdd += 1.f + rd;
               SHOT_NEIGHBOUR(di - 2, -rd);
             }
           } else {
-            double rd = (distance - r14) * inv_r12;
-            if (distance < r14)
-              wAdd += 1 + rd;
+            float rd = (distance - r14f) * inv_r12f;
+            if (d2 < a.t2_ge_r14)  // sqrt((double)d2) < r/4
+              wAdd += 1.f + rd;
             else {
-              wAdd += 1 - rd;
+              wAdd += 1.f - rd;
               SHOT_NEIGHBOUR(di + 2, rd);
             }
           }
-          // NB: the reference adds the four terms to intWeight one after the other; the order is kept below by
-          // accumulating them into wS / wC sequentially.
           wS += wAdd;
           wC += wAdd;
-          double incl = acos(fmin(1.0, fmax(-1.0, zIn / distance)));
-          if (incl > PST_RAD_90 || (fabs(incl - PST_RAD_90) < 1e-30 && zIn <= 0)) {
-            double id = (incl - PST_RAD_135) * inv_90;
-            if (incl > PST_RAD_135) {
-              wS += 1 - id;
-              wC += 1 - id;
+          // the reference branches on acos(z/d) > 90 deg (ties: z <= 0), which is z <= 0 for every representable input
+          const float incl = acosf(fminf(1.f, fmaxf(-1.f, __fdiv_rn(zIn, distance))));
+          if (zIn <= 0.f) {
+            float id = (incl - (float)PST_RAD_135) * inv_90f;
+            if (id > 0.f) {
+              wS += 1.f - id;
+              wC += 1.f - id;
             } else {
-              wS += 1 + id;
-              wC += 1 + id;
+              wS += 1.f + id;
+              wC += 1.f + id;
               SHOT_NEIGHBOUR(di + 1, -id);
             }
           } else {
-            double id = (incl - PST_RAD_45) * inv_90;
-            if (incl < PST_RAD_45) {
-              wS += 1 + id;
-              wC += 1 + id;
+            float id = (incl - (float)PST_RAD_45) * inv_90f;
+            if (id < 0.f) {
+              wS += 1.f + id;
+              wC += 1.f + id;
             } else {
-              wS += 1 - id;
-              wC += 1 - id;
+              wS += 1.f - id;
+              wC += 1.f - id;
               SHOT_NEIGHBOUR(di - 1, id);
             }
           }
-          if (yIn != 0.0 || xIn != 0.0) {
-            double az = atan2(yIn, xIn);
+          if (yIn != 0.f || xIn != 0.f) {
+            float az = atan2f(yIn, xIn);
             int sel = di >> 2;
-            double ad = (az - (-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) * inv_45;
-            ad = fmax(-0.5, fmin(ad, 0.5));
-            if (ad > 0) {
-              wS += 1 - ad;
-              wC += 1 - ad;
+            float ad = (az - (float)(-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) * inv_45f;
+            ad = fmaxf(-0.5f, fminf(ad, 0.5f));
+            if (ad > 0.f) {
+              wS += 1.f - ad;
+              wC += 1.f - ad;
               SHOT_NEIGHBOUR((di + 4) % 32, ad);
             } else {
-              wS += 1 + ad;
-              wC += 1 + ad;
+              wS += 1.f + ad;
+              wC += 1.f + ad;
               SHOT_NEIGHBOUR((di - 4 + 32) % 32, -ad);
             }
           }
@@ -561,10 +596,20 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
 
 size_t shot_smem_bytes(bool color) {
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
-  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D;
+  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D +
+         sizeof(unsigned short) * (size_t)kWarps * kChunk;
 }
 
 // Runs the fused LRF + descriptor kernel over the keypoint items prepared by stage_grid.
+// smallest float f with sqrt((double)f) > r (strict) or >= r: "sqrt((double)d2) > r"  <=>  d2 >= f for float d2
+static float shell_threshold(double r, bool strict) {
+  auto pass = [&](float f) { double s = std::sqrt((double)f); return strict ? s > r : s >= r; };
+  float f = (float)(r * r);
+  while (f > 0.f && pass(f)) f = std::nextafterf(f, 0.f);
+  while (!pass(f)) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
 int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lrf, double r_shot, bool do_lrf,
                bool do_desc, const float* lrf_in_d, float* lrf_out_d, float* desc_out_d) {
   Workspace& w = ctx->ws;
@@ -594,6 +639,9 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   a.r_shot = r_shot;
   a.r2_lrf = (float)(r_lrf * r_lrf);    // pcl::KdTreeFLANN::radiusSearch: float(radius*radius)
   a.r2_shot = (float)(r_shot * r_shot);
+  a.t2_gt_r12 = shell_threshold(r_shot / 2, true);
+  a.t2_gt_r34 = shell_threshold((r_shot * 3) / 4, true);
+  a.t2_ge_r14 = shell_threshold(r_shot / 4, false);
   a.lrf_in = lrf_in_d;
   a.lrf_out = lrf_out_d;
   a.desc_out = desc_out_d;
