@@ -261,6 +261,13 @@ def main():
     avg_gemm_ms = float(np.mean(gemm_ms)) if gemm_ms else 0.0
     achieved = flop_per_launch / (avg_gemm_ms / 1e3) / 1e12 if avg_gemm_ms > 0 else 0.0
     pk = peaks()
+    traffic = None  # DRAM bytes per GEMM launch from the committed ncu capture of this very workload, else null
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
+        if tr["workload"] == args.workload and tr["batch_clouds"] == args.batch and not args.words:
+            traffic = tr["traffic_bytes_per_launch"]
+    except Exception:
+        pass
 
     # end to end through the host-buffer C-ABI call ---------------------------------------------------------------
     for i in range(min(2, args.warmup)):
@@ -331,7 +338,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "k_knn_gemm (tcgen05 activation GEMM + candidate filter)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": None,
+                         "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": traffic,
+                         "traffic_unit": "DRAM bytes per launch (ncu, profiles/gemm_traffic.json)",
                          "peak_source": pk["src"], "flop_per_launch": flop_per_launch, "ms_per_launch": avg_gemm_ms,
                          "share_of_step": avg_gemm_ms / (ms_total / args.steps) if ms_total else None},
             "cpu_baseline": cpu_base,
