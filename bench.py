@@ -155,7 +155,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1 and args.impl == "b200":
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("PCDB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION prints a banner on stdout; keep it to the JSON line
+        if os.environ.get("PCDB_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = os.environ["PCDB_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = api.Context(device=local_rank)
