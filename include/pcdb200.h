@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PCDB_ABI_VERSION 1
+#define PCDB_ABI_VERSION 2
 
 typedef enum pcdb_status {
   PCDB_OK = 0,
@@ -45,6 +45,7 @@ enum { PCDB_FEATURE_SHOT = 0, PCDB_FEATURE_CSHOT = 1 };           /* features_fa
 enum { PCDB_DIST_EUCLIDEAN = 0, PCDB_DIST_CHISQUARED = 1 };       /* utils/distance.h:42-75 (squared L2 / chi^2) */
 enum { PCDB_KERNEL_GAUSSIAN = 0, PCDB_KERNEL_UNIFORM = 1 };       /* voting_mean_shift.cpp:378-417 */
 enum { PCDB_SUPPRESS_AVERAGE = 0, PCDB_SUPPRESS_SUPPRESS = 1 };   /* voting_mean_shift.cpp:98-122 */
+enum { PCDB_MAXFILTER_NONE = 0, PCDB_MAXFILTER_SIMPLE = 1, PCDB_MAXFILTER_MERGE = 2 }; /* maxima_handler.cpp:272-383 */
 enum { PCDB_KNN_AUTO = 0, PCDB_KNN_SCAN = 1, PCDB_KNN_GEMM = 2 }; /* which exact-kNN kernel family */
 
 #define PCDB_SHOT_DIM 352
@@ -79,6 +80,12 @@ typedef struct pcdb_params {
   int32_t best_k;         /* Voting.BestK (<=0: keep all) */
   int32_t average_rotation;    /* Voting.AverageRotation */
   int32_t single_object_mode;  /* Voting.SingleObjectMode (only gates cross-class filtering on this path) */
+  /* Normals, used when a call is given no normals (implicit_shape_model.cpp:110-112, 940-1037) */
+  float normal_radius;               /* Parameters.NormalRadius */
+  int32_t consistent_normals_method; /* Parameters.ConsistentNormalsMethod: 0 towards the origin, 1 away from the
+                                        centroid, 2 inverted SHOT-LRF z axis (the code default) */
+  /* Cross-class maxima filtering when !single_object_mode (voting.cpp:265-268, maxima_handler.cpp:272-383) */
+  int32_t max_filter_type;           /* PCDB_MAXFILTER_*; Voting.MaxFilterType */
 } pcdb_params;
 
 /* One Hough vote — ism3d::Vote, voting/voting_maximum.h:25-42 (80 bytes). */
@@ -162,6 +169,15 @@ int pcdb_shot_describe(pcdb_ctx* ctx, int32_t feature_type, const float* surf_xy
                        const uint32_t* surf_rgb, const int64_t* surf_off, const float* kp_xyz,
                        const uint32_t* kp_rgb, const float* kp_lrf9, const int64_t* kp_off, int32_t B,
                        double radius, float* desc_out);
+
+/* ImplicitShapeModel::computeNormals for unorganized clouds (implicit_shape_model.cpp:940-1037 ->
+ * NormalEstimationOMPWithEigVals, third_party/pcl_normal_3d_omp_with_eigenvalues/; NormalOrientation::processSHOTLRF,
+ * utils/normal_orientation.cpp:48-110), with the context's normal_radius / consistent_normals_method.
+ * normals_out: P x 3 aligned with xyz (NaN for non-finite points and where the reference yields NaN);
+ * curvature_out: P or NULL.  The same estimation runs inside pcdb_compute_features / pcdb_classify_batch(_d) when
+ * they are called with normals == NULL (the reference's hasNormals == false path). */
+int pcdb_compute_normals(pcdb_ctx* ctx, const float* xyz, const int64_t* cloud_off, int32_t B, float* normals_out,
+                         float* curvature_out);
 
 /* Features::operator() + removeNaNFeatures (features/features.cpp:40-116, implicit_shape_model.cpp:1276-1308):
  * keypoints -> LRF -> drop invalid -> descriptor -> drop NaN; uses the context's params.  Outputs are the

@@ -109,6 +109,17 @@ def shot_describe(feature_type, surf_xyz, surf_normals, surf_rgb, surf_off, kp_x
     return out
 
 
+def compute_normals(prm, xyz, cloud_off):
+    """ImplicitShapeModel::computeNormals for unorganized clouds: (normals (P,3), curvature (P,)), NaN where the
+    reference yields NaN; uses prm.normal_radius / prm.consistent_normals_method."""
+    xyz, cloud_off = f32(xyz), i64(cloud_off)
+    nrm = np.empty((xyz.shape[0], 3), np.float32)
+    curv = np.empty(xyz.shape[0], np.float32)
+    _check(lib().orc_compute_normals(C.byref(prm), ptr(xyz, F), ptr(cloud_off, I64), len(cloud_off) - 1, ptr(nrm, F),
+                                     ptr(curv, F)))
+    return nrm, curv
+
+
 def compute_features(prm, xyz, normals, rgb, cloud_off):
     xyz, normals, rgb, cloud_off = f32(xyz), f32(normals), u32(rgb), i64(cloud_off)
     B = len(cloud_off) - 1

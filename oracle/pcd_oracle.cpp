@@ -347,6 +347,199 @@ void shot_lrf(const float* surf, const std::vector<Nbr>& nb, const float* kp, do
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Normals — ImplicitShapeModel::computeNormals implicit_shape_model.cpp:940-1037, */
+/* unorganized clouds.  NormalEstimationOMPWithEigVals::computeFeature                           */
+/* third_party/pcl_normal_3d_omp_with_eigenvalues/normal_3d_omp_with_eigenvalues.hpp:63-141,     */
+/* computePointNormalMod / eigen33Mod / flipNormalTowardsViewpointMod .h:60-181,                 */
+/* NormalOrientation::processSHOTLRF utils/normal_orientation.cpp:48-110.                        */
+/* pcl::computeMeanAndCovarianceMatrix and pcl::computeRoots are PCL 1.10 (not in the reference  */
+/* tree): restated from the published sources -> "parity unpinned".                              */
+/* ------------------------------------------------------------------------------------------- */
+inline void compute_roots2(float b, float c, float roots[3]) { /* pcl/common/impl/eigen.hpp computeRoots2 */
+  roots[0] = 0.0f;
+  float d = float(b * b - 4.0 * c);
+  if (d < 0.0) d = 0.0f;
+  float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+inline void compute_roots(const float m[3][3], float roots[3]) { /* pcl/common/impl/eigen.hpp computeRoots */
+  float c0 = m[0][0] * m[1][1] * m[2][2] + 2.0f * m[0][1] * m[0][2] * m[1][2] - m[0][0] * m[1][2] * m[1][2] -
+             m[1][1] * m[0][2] * m[0][2] - m[2][2] * m[0][1] * m[0][1];
+  float c1 = m[0][0] * m[1][1] - m[0][1] * m[0][1] + m[0][0] * m[2][2] - m[0][2] * m[0][2] + m[1][1] * m[2][2] -
+             m[1][2] * m[1][2];
+  float c2 = m[0][0] + m[1][1] + m[2][2];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+    compute_roots2(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = float(1.0 / 3.0);
+  const float s_sqrt3 = std::sqrt(3.0f);
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.0f) q = 0.0f;
+  float rho = std::sqrt(-a_over_3);
+  float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  float cos_theta = std::cos(theta);
+  float sin_theta = std::sin(theta);
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    std::swap(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0) compute_roots2(c2, c1, roots);
+}
+
+/* eigen33Mod (.h:60-95): eigenvalues ascending + eigenvector of the smallest one */
+inline void eigen33_mod(const float mat[3][3], float evals[3], float evec[3]) {
+  float scale = 0.f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(mat[i][j]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float sm[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) sm[i][j] = mat[i][j] / scale;
+  float rt[3];
+  compute_roots(sm, rt);
+  for (int i = 0; i < 3; ++i) evals[i] = rt[i] * scale;
+  for (int i = 0; i < 3; ++i) sm[i][i] -= rt[0];
+  auto cross = [](const float* a, const float* b, float* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  float v1[3], v2[3], v3[3];
+  cross(sm[0], sm[1], v1);
+  cross(sm[0], sm[2], v2);
+  cross(sm[1], sm[2], v3);
+  float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+  float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+  float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float* v;
+  float l;
+  if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; }
+  else { v = v3; l = l3; }
+  float inv = std::sqrt(l);
+  for (int a = 0; a < 3; ++a) evec[a] = v[a] / inv;
+}
+
+/* computePointNormalMod (.h:112-150) over the neighbour list in radius-search order; float accumulators as
+ * pcl::computeMeanAndCovarianceMatrix<PointT, float> has them */
+bool pca_normal(const float* pts, const std::vector<Nbr>& nb, float n[3], float* curvature) {
+  if (nb.size() < 3) {
+    n[0] = n[1] = n[2] = *curvature = kNaNf;
+    return false;
+  }
+  float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (const Nbr& e : nb) {
+    const float* p = pts + 3 * e.idx;
+    accu[0] += p[0] * p[0];
+    accu[1] += p[0] * p[1];
+    accu[2] += p[0] * p[2];
+    accu[3] += p[1] * p[1];
+    accu[4] += p[1] * p[2];
+    accu[5] += p[2] * p[2];
+    accu[6] += p[0];
+    accu[7] += p[1];
+    accu[8] += p[2];
+  }
+  const float cnt = float(nb.size());
+  for (float& a : accu) a /= cnt;
+  float cov[3][3];
+  cov[0][0] = accu[0] - accu[6] * accu[6];
+  cov[0][1] = accu[1] - accu[6] * accu[7];
+  cov[0][2] = accu[2] - accu[6] * accu[8];
+  cov[1][1] = accu[3] - accu[7] * accu[7];
+  cov[1][2] = accu[4] - accu[7] * accu[8];
+  cov[2][2] = accu[5] - accu[8] * accu[8];
+  cov[1][0] = cov[0][1];
+  cov[2][0] = cov[0][2];
+  cov[2][1] = cov[1][2];
+  float ev[3];
+  eigen33_mod(cov, ev, n);
+  float eig_sum = cov[0][0] + cov[1][1] + cov[2][2];
+  *curvature = eig_sum != 0 ? std::fabs(ev[0] / eig_sum) : 0.f;
+  return true;
+}
+
+inline void flip_towards_viewpoint(const float* p, float vx, float vy, float vz, float n[3]) { /* .h:162-181 */
+  vx -= p[0];
+  vy -= p[1];
+  vz -= p[2];
+  float cos_theta = (vx * n[0] + vy * n[1] + vz * n[2]);
+  if (cos_theta < 0) {
+    n[0] *= -1;
+    n[1] *= -1;
+    n[2] *= -1;
+  }
+}
+
+/* pts: the cloud after removeNaNFromPointCloud (n finite points).  normals_out n x 3, curvature_out n (may be NULL). */
+void compute_normals_cloud(const pcdb_params& P, const float* pts, int n, float* normals_out, float* curvature_out) {
+  const double radius = double(P.normal_radius); /* float member -> setRadiusSearch(double) */
+  const float r2 = radius_sq(radius);
+  const int method = P.consistent_normals_method;
+  std::vector<float> shifted;
+  const float* src = pts;
+  if (method == 1) { /* :987-1014: remove the centroid (pcl::compute3DCentroid, float accumulators), flip, invert */
+    float c[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) c[a] += pts[3 * i + a];
+    for (int a = 0; a < 3; ++a) c[a] /= float(n);
+    shifted.resize(size_t(n) * 3);
+    for (int i = 0; i < n; ++i)
+      for (int a = 0; a < 3; ++a) shifted[3 * i + a] = pts[3 * i + a] - c[a];
+    src = shifted.data();
+  }
+  CloudGrid g;
+  g.build(src, n, radius);
+  std::vector<float> curv(n);
+  std::vector<unsigned char> lrf_bad(n, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < n; ++i) {
+    std::vector<Nbr> nb;
+    g.query(src + 3 * i, r2, nb);
+    float* no = normals_out + 3 * i;
+    if (pca_normal(src, nb, no, &curv[i])) flip_towards_viewpoint(src + 3 * i, 0.f, 0.f, 0.f, no);
+    if (method == 1)
+      for (int a = 0; a < 3; ++a) no[a] *= -1;
+    if (method == 2) { /* :1015-1019 + normal_orientation.cpp:56-82: normal = inverted z axis of the SHOT LRF */
+      float rf[9];
+      shot_lrf(src, nb, src + 3 * i, radius, rf);
+      if (std::isfinite(rf[0]) && std::isfinite(rf[3]) && std::isfinite(rf[6])) {
+        no[0] = -rf[6];
+        no[1] = -rf[7];
+        no[2] = -rf[8];
+      } else
+        lrf_bad[i] = 1;
+    }
+  }
+  if (method == 2) {
+    /* normal_orientation.cpp:85-107, kept as written: the loop recomputes the normals of points 0..n_invalid-1
+     * (pointCloud->at(idx), orientedNormals->at(idx)) instead of the invalid ones, without viewpoint flip, and the
+     * pcl::Normal(x,y,z) constructor zeroes their curvature */
+    int n_invalid = 0;
+    for (int i = 0; i < n; ++i) n_invalid += lrf_bad[i];
+    for (int idx = 0; idx < n_invalid; ++idx) {
+      std::vector<Nbr> nb;
+      g.query(src + 3 * idx, r2, nb);
+      float c;
+      pca_normal(src, nb, normals_out + 3 * idx, &c);
+      curv[idx] = 0.f;
+    }
+  }
+  if (curvature_out) std::memcpy(curvature_out, curv.data(), sizeof(float) * n);
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* A.5  RGB -> CIELab (features/features_cshot.cpp:52-71 LUTs,                                   */
 /*      third_party/pcl_color_conversion/color_conversion.cpp:19-94)                             */
 /* ------------------------------------------------------------------------------------------- */
@@ -1200,15 +1393,25 @@ void compute_features_cloud(const pcdb_params& P, const float* xyz, const float*
   const bool color = P.feature_type == PCDB_FEATURE_CSHOT;
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   /* removeNaNFromPointCloud (implicit_shape_model.cpp:611), filterNormals (:1040-1068) */
-  std::vector<float> pts, sxyz, snrm;
+  std::vector<float> pts, sxyz, snrm, est;
   std::vector<uint32_t> prgb, srgb;
+  if (!normals) { /* hasNormals == false: computeNormals on the NaN-free cloud (implicit_shape_model.cpp:852-858) */
+    for (int i = 0; i < n; ++i)
+      if (finite3(xyz + 3 * i)) pts.insert(pts.end(), xyz + 3 * i, xyz + 3 * i + 3);
+    est.resize(pts.size());
+    compute_normals_cloud(P, pts.data(), int(pts.size() / 3), est.data(), nullptr);
+    pts.clear();
+  }
+  int fi = 0;
   for (int i = 0; i < n; ++i) {
     if (!finite3(xyz + 3 * i)) continue;
+    const float* nrm_i = normals ? normals + 3 * i : &est[3 * size_t(fi)];
+    ++fi;
     pts.insert(pts.end(), xyz + 3 * i, xyz + 3 * i + 3);
     prgb.push_back(rgb ? rgb[i] : 0u);
-    if (!finite3(normals + 3 * i)) continue;
+    if (!finite3(nrm_i)) continue;
     sxyz.insert(sxyz.end(), xyz + 3 * i, xyz + 3 * i + 3);
-    snrm.insert(snrm.end(), normals + 3 * i, normals + 3 * i + 3);
+    snrm.insert(snrm.end(), nrm_i, nrm_i + 3);
     srgb.push_back(rgb ? rgb[i] : 0u);
   }
   auto t0 = std::chrono::steady_clock::now();
@@ -1341,6 +1544,9 @@ void orc_default_params(pcdb_params* p) {
   p->maxima_suppression = PCDB_SUPPRESS_AVERAGE;
   p->min_votes_threshold = 1;
   p->best_k = -1;
+  p->normal_radius = 0.05f;
+  p->consistent_normals_method = 2;
+  p->max_filter_type = PCDB_MAXFILTER_NONE;
 }
 
 int orc_voxel_keypoints(const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B, float leaf,
@@ -1426,6 +1632,31 @@ int orc_shot_describe(int32_t feature_type, const float* surf_xyz, const float* 
   return PCDB_OK;
 }
 
+/* normals_out P x 3 aligned with the input (NaN for non-finite points); curvature_out P or NULL */
+int orc_compute_normals(const pcdb_params* prm, const float* xyz, const int64_t* cloud_off, int32_t B,
+                        float* normals_out, float* curvature_out) {
+  for (int b = 0; b < B; ++b) {
+    const int64_t s = cloud_off[b], e = cloud_off[b + 1];
+    std::vector<float> pts, nrm, cv;
+    std::vector<int64_t> where;
+    for (int64_t i = s; i < e; ++i) {
+      for (int a = 0; a < 3; ++a) normals_out[3 * i + a] = kNaNf;
+      if (curvature_out) curvature_out[i] = kNaNf;
+      if (!finite3(xyz + 3 * i)) continue;
+      pts.insert(pts.end(), xyz + 3 * i, xyz + 3 * i + 3);
+      where.push_back(i);
+    }
+    nrm.resize(pts.size());
+    cv.resize(where.size());
+    compute_normals_cloud(*prm, pts.data(), int(where.size()), nrm.data(), cv.data());
+    for (size_t j = 0; j < where.size(); ++j) {
+      std::memcpy(normals_out + 3 * where[j], &nrm[3 * j], sizeof(float) * 3);
+      if (curvature_out) curvature_out[where[j]] = cv[j];
+    }
+  }
+  return PCDB_OK;
+}
+
 int orc_compute_features(const pcdb_params* prm, const float* xyz, const float* normals, const uint32_t* rgb,
                          const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
                          float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity) {
@@ -1435,8 +1666,8 @@ int orc_compute_features(const pcdb_params* prm, const float* xyz, const float* 
   for (int b = 0; b < B; ++b) {
     CloudFeatures f;
     int64_t s = cloud_off[b];
-    compute_features_cloud(*prm, xyz + 3 * s, normals + 3 * s, rgb ? rgb + s : nullptr, int(cloud_off[b + 1] - s), f,
-                           nullptr);
+    compute_features_cloud(*prm, xyz + 3 * s, normals ? normals + 3 * s : nullptr, rgb ? rgb + s : nullptr,
+                           int(cloud_off[b + 1] - s), f, nullptr);
     int64_t q = (int64_t)f.xyz.size() / 3;
     if (total + q > feat_capacity) {
       g_err = "feat_capacity too small";
@@ -1603,8 +1834,8 @@ int orc_classify_batch(void* model, const float* xyz, const float* normals, cons
     CloudFeatures f;
     int64_t s = cloud_off[b];
     double kp_ms = 0;
-    compute_features_cloud(P, xyz + 3 * s, normals + 3 * s, rgb ? rgb + s : nullptr, int(cloud_off[b + 1] - s), f,
-                           &kp_ms);
+    compute_features_cloud(P, xyz + 3 * s, normals ? normals + 3 * s : nullptr, rgb ? rgb + s : nullptr,
+                           int(cloud_off[b + 1] - s), f, &kp_ms);
     auto t1 = std::chrono::steady_clock::now();
     t_kp += kp_ms;
     t_feat += std::chrono::duration<double, std::milli>(t1 - t0).count() - kp_ms;

@@ -418,6 +418,9 @@ void pcdb_default_params(pcdb_params* p) {
   p->maxima_suppression = PCDB_SUPPRESS_AVERAGE;
   p->min_votes_threshold = 1;
   p->best_k = -1;
+  p->normal_radius = 0.05f;
+  p->consistent_normals_method = 2;
+  p->max_filter_type = PCDB_MAXFILTER_NONE;
 }
 
 int pcdb_create(pcdb_ctx** out, int device) {
@@ -686,21 +689,38 @@ int pcdb_shot_describe(pcdb_ctx* ctx, int32_t feature_type, const float* surf_xy
   return PCDB_OK;
 }
 
+int pcdb_compute_normals(pcdb_ctx* ctx, const float* xyz, const int64_t* cloud_off, int32_t B, float* normals_out,
+                         float* curvature_out) {
+  if (!ctx) return PCDB_E_INVALID;
+  PCDB_CUDA(cudaSetDevice(ctx->device));
+  PCDB_TRY(check_offsets(ctx, cloud_off, B, "cloud_off"));
+  if (!normals_out) return ctx->fail(PCDB_E_INVALID, "normals_out is required");
+  Workspace& w = ctx->ws;
+  const int64_t P = cloud_off[B];
+  PCDB_TRY(upload(ctx, w.in_xyz, xyz, sizeof(float) * 3 * P));
+  PCDB_TRY(upload(ctx, w.cloud_off, cloud_off, sizeof(int64_t) * (B + 1)));
+  PCDB_CUDA(w.nrm_curv.ensure(sizeof(float) * (P + 1)));
+  PCDB_TRY(stage_normals(ctx, B, P, w.nrm_curv.as<float>()));
+  PCDB_TRY(download(ctx, normals_out, w.in_nrm.p, sizeof(float) * 3 * P));
+  if (curvature_out) PCDB_TRY(download(ctx, curvature_out, w.nrm_curv.p, sizeof(float) * P));
+  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PCDB_OK;
+}
+
 int pcdb_compute_features(pcdb_ctx* ctx, const float* xyz, const float* normals, const uint32_t* rgb,
                           const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
                           float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity) {
   if (!ctx) return PCDB_E_INVALID;
   PCDB_CUDA(cudaSetDevice(ctx->device));
   PCDB_TRY(check_offsets(ctx, cloud_off, B, "cloud_off"));
-  if (!normals)
-    return ctx->fail(PCDB_E_UNSUPPORTED, "normals are required (normal estimation is a SURVEY 8f-1 'next' row, not built)");
   Workspace& w = ctx->ws;
   const int64_t P = cloud_off[B];
   const int D = ctx->prm.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   PCDB_TRY(upload(ctx, w.in_xyz, xyz, sizeof(float) * 3 * P));
-  PCDB_TRY(upload(ctx, w.in_nrm, normals, sizeof(float) * 3 * P));
+  if (normals) PCDB_TRY(upload(ctx, w.in_nrm, normals, sizeof(float) * 3 * P));
   if (rgb) PCDB_TRY(upload(ctx, w.in_rgb, rgb, sizeof(uint32_t) * P));
   PCDB_TRY(upload(ctx, w.cloud_off, cloud_off, sizeof(int64_t) * (B + 1)));
+  if (!normals) PCDB_TRY(stage_normals(ctx, B, P, nullptr));  // hasNormals == false (implicit_shape_model.cpp:852-858)
   int64_t F = 0, Q = 0;
   PCDB_TRY(features_pipeline(ctx, B, P, rgb != nullptr, &F, &Q));
   PCDB_TRY(download(ctx, feat_off_out, w.feat_off.p, sizeof(int64_t) * (B + 1)));
@@ -854,7 +874,7 @@ static void record_stage_times(pcdb_ctx* ctx, const float t[4]) {
 }
 
 // device-resident core of detect(): inputs already in ws.in_* / ws.cloud_off
-static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* M_out) {
+static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, bool has_normals, int64_t* M_out) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const pcdb_params& p = ctx->prm;
@@ -862,6 +882,8 @@ static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t*
   const int D = p.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   if (ctx->cb.D != D) return ctx->fail(PCDB_E_INVALID, "codebook dimension %d does not match Features.Type (%d)", ctx->cb.D, D);
   ctx->gemm_events_valid = false;
+  PCDB_CUDA(cudaEventRecord(ctx->ev[7], st));
+  if (!has_normals) PCDB_TRY(stage_normals(ctx, B, P, nullptr));  // "normals" bucket of the reference's timing table
   PCDB_CUDA(cudaEventRecord(ctx->ev[0], st));
   int64_t F = 0, Q = 0;
   PCDB_TRY(features_pipeline(ctx, B, P, has_rgb, &F, &Q));
@@ -892,25 +914,25 @@ int pcdb_classify_batch(pcdb_ctx* ctx, const float* xyz, const float* normals, c
   if (!ctx) return PCDB_E_INVALID;
   PCDB_CUDA(cudaSetDevice(ctx->device));
   PCDB_TRY(check_offsets(ctx, cloud_off, B, "cloud_off"));
-  if (!normals)
-    return ctx->fail(PCDB_E_UNSUPPORTED, "normals are required (normal estimation is a SURVEY 8f-1 'next' row, not built)");
   if (!label_out) return ctx->fail(PCDB_E_INVALID, "label_out is required");
   Workspace& w = ctx->ws;
   const int64_t P = cloud_off[B];
   PCDB_TRY(upload(ctx, w.in_xyz, xyz, sizeof(float) * 3 * P));
-  PCDB_TRY(upload(ctx, w.in_nrm, normals, sizeof(float) * 3 * P));
+  if (normals) PCDB_TRY(upload(ctx, w.in_nrm, normals, sizeof(float) * 3 * P));
   if (rgb) PCDB_TRY(upload(ctx, w.in_rgb, rgb, sizeof(uint32_t) * P));
   PCDB_TRY(upload(ctx, w.cloud_off, cloud_off, sizeof(int64_t) * (B + 1)));
   int64_t M = 0;
-  PCDB_TRY(classify_core(ctx, B, P, rgb != nullptr, &M));
+  PCDB_TRY(classify_core(ctx, B, P, rgb != nullptr, normals != nullptr, &M));
   PCDB_TRY(fetch_maxima(ctx, B, M, maxima_out, maxima_off_out, maxima_capacity, label_out));
   if (times_ms_out) {
     float t[4] = {0, 0, 0, 0};
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ctx->ev[i], ctx->ev[i + 1]);
-    times_ms_out[0] = t[0] + t[1] + t[2] + t[3];  // complete
+    float t_nrm = 0;
+    cudaEventElapsedTime(&t_nrm, ctx->ev[7], ctx->ev[0]);
+    times_ms_out[0] = t_nrm + t[0] + t[1] + t[2] + t[3];  // complete
     times_ms_out[1] = t[0];                       // features (keypoints included; split below is not tracked)
     times_ms_out[2] = 0;                          // keypoints
-    times_ms_out[3] = 0;                          // normals (given)
+    times_ms_out[3] = normals ? 0 : t_nrm;        // normals (0 when given)
     times_ms_out[4] = 0;                          // flann (index build: none, the codebook is resident)
     times_ms_out[5] = t[1] + t[2];                // voting = activation + vote casting
     times_ms_out[6] = t[3];                       // maxima
@@ -924,19 +946,19 @@ int pcdb_classify_batch_d(pcdb_ctx* ctx, const float* xyz_d, const float* normal
   if (!ctx) return PCDB_E_INVALID;
   PCDB_CUDA(cudaSetDevice(ctx->device));
   PCDB_TRY(check_offsets(ctx, cloud_off, B, "cloud_off"));
-  if (!normals_d || !xyz_d || !label_out_d) return ctx->fail(PCDB_E_INVALID, "xyz_d, normals_d and label_out_d are required");
+  if (!xyz_d || !label_out_d) return ctx->fail(PCDB_E_INVALID, "xyz_d and label_out_d are required");
   Workspace& w = ctx->ws;
   const int64_t P = cloud_off[B];
   // borrow the caller's device arrays for this call (no copy)
   DevBuf sx = w.in_xyz, sn = w.in_nrm, sr = w.in_rgb;
   w.in_xyz.p = const_cast<float*>(xyz_d);
-  w.in_nrm.p = const_cast<float*>(normals_d);
+  if (normals_d) w.in_nrm.p = const_cast<float*>(normals_d);  // else estimated into the workspace's own buffer
   w.in_rgb.p = const_cast<uint32_t*>(rgb_d);
   int rc = upload(ctx, w.cloud_off, cloud_off, sizeof(int64_t) * (B + 1));
   int64_t M = 0;
-  if (rc == PCDB_OK) rc = classify_core(ctx, B, P, rgb_d != nullptr, &M);
+  if (rc == PCDB_OK) rc = classify_core(ctx, B, P, rgb_d != nullptr, normals_d != nullptr, &M);
   w.in_xyz = sx;
-  w.in_nrm = sn;
+  if (normals_d) w.in_nrm = sn;
   w.in_rgb = sr;
   PCDB_TRY(rc);
   PCDB_CUDA(cudaMemcpyAsync(label_out_d, w.labels.p, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));

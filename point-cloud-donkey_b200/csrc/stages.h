@@ -9,6 +9,9 @@ int stage_cloud_setup(pcdb_ctx* ctx, int B, int64_t n_pts, const float4* extra_k
 int stage_voxel_keypoints(pcdb_ctx* ctx, int B, int64_t n_pts, float leaf, int64_t* Q_out);  // syncs
 int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color);
 
+// normals.cu: ws.in_xyz -> ws.in_nrm (and optionally the curvature) for clouds without normals; syncs
+int stage_normals(pcdb_ctx* ctx, int B, int64_t P, float* curv_out_d);
+
 // shot.cu
 size_t shot_smem_bytes(bool color);
 int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lrf, double r_shot, bool do_lrf,

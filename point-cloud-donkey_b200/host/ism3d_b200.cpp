@@ -3,6 +3,7 @@
 #include "ism3d_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <ctime>
@@ -186,6 +187,10 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   pcdb_params P;
   pcdb_default_params(&P);
   ParamReader top{oc["Parameters"], this, &warn};
+  P.normal_radius = (float)top.num("NormalRadius", 0.05);                       // implicit_shape_model.cpp:110
+  P.consistent_normals_method = (int)top.num("ConsistentNormalsMethod", 2);      // :112
+  if (P.consistent_normals_method < 0 || P.consistent_normals_method > 2)
+    throw BadParamException("ConsistentNormalsMethod must be 0, 1 or 2 (3 needs the optional VCG library)");
   const std::string dist = top.str("DistanceType", "Euclidean");
   if (dist == "Euclidean") P.distance_type = PCDB_DIST_EUCLIDEAN;
   else if (dist == "ChiSquared") P.distance_type = PCDB_DIST_CHISQUARED;
@@ -531,15 +536,17 @@ void ImplicitShapeModel::train() {
       std::string err;
       if (!io::load_pcd(it.second[j], cloud, err)) throw RuntimeException("could not load training model: " + err);
       if (cloud.size() == 0) throw RuntimeException("point cloud is empty: " + it.second[j]);
-      if (!cloud.has_normals)
-        throw RuntimeException("training cloud without normals: normal estimation is a 'next' row (SURVEY 8f-1): " + it.second[j]);
+      // implicit_shape_model.cpp:374-390: clouds without (usable) normals get them estimated
+      const bool has_normals = cloud.has_normals && !(cloud.normals[0] == 0 && cloud.normals[1] == 0 && cloud.normals[2] == 0) &&
+                               !std::isnan(cloud.normals[0]);
       Utils::BoundingBox bb = Utils::computeAABB(cloud);
       const int64_t off[2] = {0, (int64_t)cloud.size()};
       const int64_t cap = (int64_t)cloud.size();
       std::vector<float> x((size_t)cap * 3), l((size_t)cap * 9), d((size_t)cap * D);
       int64_t out_off[2];
-      check(pcdb_compute_features(m_ctx, cloud.xyz.data(), cloud.normals.data(), cloud.has_rgb ? cloud.rgb.data() : nullptr,
-                                  off, 1, x.data(), l.data(), d.data(), out_off, cap));
+      check(pcdb_compute_features(m_ctx, cloud.xyz.data(), has_normals ? cloud.normals.data() : nullptr,
+                                  cloud.has_rgb ? cloud.rgb.data() : nullptr, off, 1, x.data(), l.data(), d.data(), out_off,
+                                  cap));
       const int64_t nf = out_off[1];
       fxyz.insert(fxyz.end(), x.begin(), x.begin() + nf * 3);
       flrf.insert(flrf.end(), l.begin(), l.begin() + nf * 9);
@@ -770,8 +777,12 @@ bool ImplicitShapeModel::detectBatch(const std::vector<std::string>& filenames,
       if (c.size() == 0) { log("ERROR", "point cloud is empty"); return false; }
       // detect(): "first normal is zero/NaN => hasNormals=false" (implicit_shape_model.cpp:614-625)
       if (!c.has_normals || (c.normals[0] == 0 && c.normals[1] == 0 && c.normals[2] == 0) || std::isnan(c.normals[0])) {
-        log("ERROR", "cloud without normals: normal estimation is a 'next' row (SURVEY 8f-1): " + filenames[i]);
-        return false;
+        // a batch shares one normals array: estimate this cloud's normals now (the "normals" bucket of the timing table)
+        const int64_t o1[2] = {0, (int64_t)c.size()};
+        c.normals.assign(c.size() * 3, 0.f);
+        const auto t0 = std::chrono::steady_clock::now();
+        check(pcdb_compute_normals(m_ctx, c.xyz.data(), o1, 1, c.normals.data(), nullptr));
+        m_processing_times["normals"] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       }
       xyz.insert(xyz.end(), c.xyz.begin(), c.xyz.end());
       nrm.insert(nrm.end(), c.normals.begin(), c.normals.end());
@@ -847,8 +858,10 @@ std::tuple<std::vector<VotingMaximum>, std::map<std::string, double>> ImplicitSh
     log("WARN", "point cloud is empty");
     return std::make_tuple(std::vector<VotingMaximum>(), m_processing_times);
   }
-  if (!hasNormals || !points.has_normals)
-    throw RuntimeException("detect(): clouds without normals need the normal-estimation stage, a 'next' row (SURVEY 8f-1)");
+  // implicit_shape_model.cpp:614-625: a zero / NaN first normal means "no normals"
+  if (hasNormals && (!points.has_normals || (points.normals[0] == 0 && points.normals[1] == 0 && points.normals[2] == 0) ||
+                     std::isnan(points.normals[0])))
+    hasNormals = false;
   if (!m_codebook_uploaded) uploadCodebook();
   const int64_t off[2] = {0, (int64_t)points.size()};
   int32_t label;
@@ -856,8 +869,8 @@ std::tuple<std::vector<VotingMaximum>, std::map<std::string, double>> ImplicitSh
   std::vector<pcdb_maximum> mx((size_t)cap);
   int64_t moff[2];
   double t[7];
-  check(pcdb_classify_batch(m_ctx, points.xyz.data(), points.normals.data(), points.has_rgb ? points.rgb.data() : nullptr, off,
-                            1, &label, mx.data(), moff, cap, t));
+  check(pcdb_classify_batch(m_ctx, points.xyz.data(), hasNormals ? points.normals.data() : nullptr,
+                            points.has_rgb ? points.rgb.data() : nullptr, off, 1, &label, mx.data(), moff, cap, t));
   static const char* keys[7] = {"complete", "features", "keypoints", "normals", "flann", "voting", "maxima"};
   for (int i = 0; i < 7; ++i) m_processing_times[keys[i]] += t[i];
   return std::make_tuple(toMaxima(mx.data(), moff[1], nullptr, nullptr, nullptr), m_processing_times);

@@ -20,7 +20,7 @@ F, I64, I32, U32, D = C.c_float, C.c_int64, C.c_int32, C.c_uint32, C.c_double
 SYMBOLS = [
     "pcdb_abi_version", "pcdb_create", "pcdb_destroy", "pcdb_last_error", "pcdb_default_params", "pcdb_set_params",
     "pcdb_set_stream", "pcdb_set_codebook", "pcdb_voxel_keypoints", "pcdb_radius_neighbours", "pcdb_shot_lrf",
-    "pcdb_shot_describe", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
+    "pcdb_shot_describe", "pcdb_compute_normals", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
     "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
     "pcdb_get_stats", "pcdb_reset_stats",
 ]
@@ -136,6 +136,16 @@ class Context:
                                              ptr(out, F)))
         return out
 
+    def compute_normals(self, xyz, cloud_off):
+        """ImplicitShapeModel::computeNormals: (normals (P,3), curvature (P,)) with the context's NormalRadius /
+        ConsistentNormalsMethod."""
+        xyz, cloud_off = f32(xyz), i64(cloud_off)
+        nrm = np.empty((xyz.shape[0], 3), np.float32)
+        curv = np.empty(xyz.shape[0], np.float32)
+        self._check(lib().pcdb_compute_normals(self.h, ptr(xyz, F), ptr(cloud_off, I64), len(cloud_off) - 1,
+                                               ptr(nrm, F), ptr(curv, F)))
+        return nrm, curv
+
     def compute_features(self, xyz, normals, rgb, cloud_off):
         xyz, normals, rgb, cloud_off = f32(xyz), f32(normals), u32(rgb), i64(cloud_off)
         B = len(cloud_off) - 1
@@ -232,7 +242,8 @@ class Context:
     def classify_batch_device(self, xyz_ptr, normals_ptr, rgb_ptr, cloud_off, labels_ptr):
         """Device-resident inputs (raw device pointers, e.g. torch.Tensor.data_ptr()); labels stay on the device."""
         cloud_off = i64(cloud_off)
-        self._check(lib().pcdb_classify_batch_d(self.h, C.c_void_p(xyz_ptr), C.c_void_p(normals_ptr),
+        self._check(lib().pcdb_classify_batch_d(self.h, C.c_void_p(xyz_ptr),
+                                                C.c_void_p(normals_ptr) if normals_ptr else None,
                                                 C.c_void_p(rgb_ptr) if rgb_ptr else None, ptr(cloud_off, I64),
                                                 len(cloud_off) - 1, C.c_void_p(labels_ptr)))
 

@@ -7,6 +7,7 @@ FEATURE_SHOT, FEATURE_CSHOT = 0, 1
 DIST_EUCLIDEAN, DIST_CHISQUARED = 0, 1
 KERNEL_GAUSSIAN, KERNEL_UNIFORM = 0, 1
 SUPPRESS_AVERAGE, SUPPRESS_SUPPRESS = 0, 1
+MAXFILTER_NONE, MAXFILTER_SIMPLE, MAXFILTER_MERGE = 0, 1, 2
 KNN_AUTO, KNN_SCAN, KNN_GEMM = 0, 1, 2
 SHOT_DIM, CSHOT_DIM, MAX_K = 352, 1344, 16
 
@@ -40,6 +41,9 @@ class Params(C.Structure):
         ("best_k", C.c_int32),
         ("average_rotation", C.c_int32),
         ("single_object_mode", C.c_int32),
+        ("normal_radius", C.c_float),
+        ("consistent_normals_method", C.c_int32),
+        ("max_filter_type", C.c_int32),
     ]
 
     @property
@@ -73,6 +77,9 @@ def default_params(**kw):
     p.best_k = -1
     p.average_rotation = 0
     p.single_object_mode = 0
+    p.normal_radius = 0.05
+    p.consistent_normals_method = 2
+    p.max_filter_type = MAXFILTER_NONE
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)

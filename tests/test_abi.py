@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), "libpcdb200.so does not export %s" % name
     assert sorted(api.SYMBOLS) == declared, "pcdb200/api.py binds a different symbol set than the header declares"
     lib.pcdb_abi_version.restype = C.c_int
-    assert lib.pcdb_abi_version() == 1
+    assert lib.pcdb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -62,7 +62,7 @@ def test_header_compiles_as_c_and_cpp():
     with tempfile.TemporaryDirectory() as d:
         for ext, cc in ((".c", "/usr/bin/gcc"), (".cpp", "/usr/bin/g++")):
             f = os.path.join(d, "h" + ext)
-            open(f, "w").write('#include "pcdb200.h"\nint main(void){return PCDB_ABI_VERSION - 1;}\n')
+            open(f, "w").write('#include "pcdb200.h"\nint main(void){return PCDB_ABI_VERSION - 2;}\n')
             subprocess.check_call([cc, "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), f, "-o", f + ".out"])
 
 

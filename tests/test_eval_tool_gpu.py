@@ -62,3 +62,47 @@ def test_eval_tool_train_and_classify(tmp_path, orc):
     assert got == labels.tolist() == ref.tolist()
     assert "Accuracy:" in summary and "class id to class name mapping" in summary and "0: cat" in summary
     ctx.close()
+
+
+def test_eval_tool_on_clouds_without_normals(tmp_path):
+    """Raw x y z rgb PCD files: the front-end estimates the normals (NormalRadius / ConsistentNormalsMethod of the
+    config) in training and in classification, like the reference's hasNormals == false path; the labels must be the
+    ones the Python binding gives with normals=None."""
+    import json
+    from pcdb200 import api, train
+    tool = os.path.join(HOST, "eval_tool")
+    names = ["cat", "horse", "wolf"]
+    P = 1536
+    tr_cls = [c for c in range(3) for _ in range(2)]
+    te_cls = [0, 1, 2]
+    xyz, _, rgb, off = synth.make_clouds(tr_cls, [300 + i for i in range(len(tr_cls))], P)
+    xt, _, rt, ot = synth.make_clouds(te_cls, [800 + i for i in range(len(te_cls))], P)
+    cfg = json.load(open(os.path.join(ROOT, "config", "c2_synthetic.ism")))
+    cfg["ObjectConfig"]["Parameters"]["NormalRadius"] = 0.08
+    cfg["ObjectConfig"]["Parameters"]["ConsistentNormalsMethod"] = 2
+    cfg_path = str(tmp_path / "cfg.ism")
+    json.dump(cfg, open(cfg_path, "w"), indent=1)
+    for name, (x, r, o, cls) in {"train": (xyz, rgb, off, tr_cls), "test": (xt, rt, ot, te_cls)}.items():
+        with open(tmp_path / (name + ".txt"), "w") as f:
+            f.write("# %s\n" % name)  # the reference's list files open with a header line (data/qs_train_list.txt)
+            for i, c in enumerate(cls):
+                p = str(tmp_path / ("%s_%d.pcd" % (name, i)))
+                pcd.write_pcd(p, x[o[i]:o[i + 1]], None, r[o[i]:o[i + 1]], ascii=(i == 1))
+                f.write("%s %s\n" % (p, names[c]))
+    model = str(tmp_path / "model.ism")
+    r = subprocess.run([tool, "-t", cfg_path, "-f", str(tmp_path / "train.txt"), "-o", model], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    outdir = str(tmp_path / "out")
+    r = subprocess.run([tool, "-d", model, "-f", str(tmp_path / "test.txt"), "-o", outdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    summary = open(os.path.join(outdir, "summary.txt")).read()
+    got = [int(m) for m in re.findall(r"classified class: (-?\d+)", summary)]
+    prm = synth.workload_params("c2", normal_radius=0.08, consistent_normals_method=2)
+    ctx = api.Context(prm)
+    fx, fl, fd, foff = ctx.compute_features(xyz, None, rgb, off)
+    bb = np.stack([train.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    cb = train.train_codebook(ctx, prm, fx, fl, fd, foff, tr_cls, tr_cls, bb, len(names))
+    ctx.set_codebook(cb)
+    labels, _, _ = ctx.classify_batch(xt, None, rt, ot)
+    assert got == labels.tolist()
+    ctx.close()

@@ -121,6 +121,68 @@ def test_shot_lrf_tie_break_and_degenerate(ctx, orc):
     assert np.allclose(a[0], b[0], atol=1e-5)
 
 
+# ---- normals -------------------------------------------------------------------------------------------
+def _scene_with_stragglers():
+    """Two objects plus a few isolated points: the stragglers have < 5 neighbours (no SHOT frame) or < 3 (no normal)."""
+    xyz, nrm, _, off = synth.make_clouds([0, 2], [41, 42], 3000)
+    far = np.array([[9, 9, 9], [9.01, 9, 9], [9, 9.01, 9.01], [20, 20, 20], [np.nan, 0, 0]], np.float32)
+    xyz = np.concatenate([xyz[:3000], far[:3], xyz[3000:], far[3:]]).astype(np.float32)
+    return xyz, np.array([0, 3003, len(xyz)], np.int64)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_compute_normals_parity(api, orc, method):
+    xyz, off = _scene_with_stragglers()
+    prm = default_params(normal_radius=0.08, consistent_normals_method=method)
+    c = api.Context(prm)
+    a, ca = c.compute_normals(xyz, off)
+    b, cb_ = orc.compute_normals(prm, xyz, off)
+    c.close()
+    nan_a, nan_b = np.isnan(a).any(1), np.isnan(b).any(1)
+    assert np.array_equal(nan_a, nan_b) and nan_b.sum() >= 2  # the isolated point and the NaN input
+    ok = ~nan_b
+    assert np.allclose(np.linalg.norm(a[ok], axis=1), 1, atol=1e-4)
+    dots = (a[ok].astype(np.float64) * b[ok]).sum(1)
+    # PCA normals: the reference accumulates the moments in fp32 (this oracle too), the kernel in fp64, and both then
+    # run the closed-form float eigen-solve: the bar is the angle, 2e-3 rad for 99 % of the points; the SHOT-frame
+    # normals of method 2 are the fp64 LRF and agree to 1e-4
+    tol = 1e-4 if method == 2 else 2e-3
+    ang = np.abs(a[ok] - np.sign(dots)[:, None] * b[ok]).max(1)  # chord ~ angle (arccos is noise at 1e-4 in float)
+    assert (ang < tol).mean() > 0.99, "normal direction: %g of points off, worst %g rad" % ((ang >= tol).mean(), ang.max())
+    assert (np.sign(dots) > 0).mean() > 0.995  # orientation decisions (cos_theta ~ 0 can flip either way)
+    assert (np.abs(ca[ok] - cb_[ok]) < 5e-3).mean() > 0.99  # degenerate 3-point neighbourhoods are noise in both
+    if method == 2:
+        # the reference's repair loop rewrites points 0..n_invalid-1 of each cloud (normal_orientation.cpp:96-106):
+        # cloud 0 has three stragglers without a SHOT frame, so its first three normals are the raw PCA normals
+        prm0 = default_params(normal_radius=0.08, consistent_normals_method=0)
+        raw, _ = orc.compute_normals(prm0, xyz, off)
+        for i in range(3):
+            assert abs(abs(float(np.dot(a[i], raw[i]))) - 1) < 1e-4 and ca[i] == 0
+
+
+def test_classify_without_normals_matches_oracle(api, orc):
+    """hasNormals == false: normals estimated on the fly (default method 2), training included."""
+    prm = synth.workload_params("c2", normal_radius=0.08)
+    n_cls = 4
+    tr_cls = [c for c in range(n_cls) for _ in range(3)]
+    xyz, _, rgb, off = synth.make_clouds(tr_cls, [1000 + i for i in range(len(tr_cls))], 1536)
+    fx, fl, fd, foff = orc.compute_features(prm, xyz, None, rgb, off)
+    c = api.Context(prm)
+    gx, gl, gd, goff = c.compute_features(xyz, None, rgb, off)
+    assert np.array_equal(goff, foff)
+    assert np.abs(gd - fd).max() < 5e-3  # estimated normals differ at the 1e-4 level (see the normals test)
+    bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    cb = orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bb, n_cls)
+    c.set_codebook(cb)
+    te = [c_ for c_ in range(n_cls) for _ in range(2)]
+    xt, _, rt, ot = synth.make_clouds(te, [5000 + i for i in range(len(te))], 1536)
+    la, _, _ = c.classify_batch(xt, None, rt, ot)
+    lb, _, _ = orc.Model(prm, cb).classify_batch(xt, None, rt, ot)
+    assert np.array_equal(la, lb)
+    assert c.last_times["normals"] > 0
+    c.close()
+
+
 # ---- K4 / K5 ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ft", [FEATURE_SHOT, FEATURE_CSHOT])
 def test_shot_describe_parity(ctx, orc, ft):

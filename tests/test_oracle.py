@@ -396,3 +396,47 @@ def test_merge_topk(orc):
     for q in range(Q):
         c = sorted((float(d[s, q, j]), int(i[s, q, j])) for s in range(S) for j in range(k) if i[s, q, j] >= 0)[:k]
         assert [x[1] for x in c] == idx[q].tolist() and np.allclose([x[0] for x in c], dist[q])
+
+
+# ---- normals ---------------------------------------------------------------------------------------------
+def test_pca_normals_known_answers(orc):
+    """computePointNormalMod: a noisy plane gives +-z, curvature ~ 0; every point agrees with numpy.linalg.eigh of the
+    same neighbourhood; method 0 orients towards the origin, method 1 away from the centroid."""
+    rng = np.random.default_rng(3)
+    pts = np.zeros((1500, 3), np.float32)
+    pts[:, :2] = rng.uniform(-1, 1, (1500, 2))
+    pts[:, 2] = 2.0 + rng.normal(0, 1e-4, 1500)
+    off = np.array([0, 1500], np.int64)
+    prm = default_params(normal_radius=0.2, consistent_normals_method=0)
+    n, cv = orc.compute_normals(prm, pts, off)
+    assert np.isfinite(n).all() and (np.abs(n[:, 2]) > 0.9999).all() and (n[:, 2] < 0).all()  # towards the origin
+    assert (cv < 2e-3).all()  # float moment sums at z = 2: cancellation noise, as in the reference
+    x, _, _, o = synth.make_clouds([1], [17], 3000)
+    n0, cv0 = orc.compute_normals(prm, x, o)
+    for i in (0, 100, 2000):
+        nb = x[((x - x[i]) ** 2).sum(1) < np.float32(0.2 ** 2)].astype(np.float64)
+        w, V = np.linalg.eigh(np.cov(nb.T, bias=True))
+        assert abs(abs(np.dot(n0[i], V[:, 0])) - 1) < 1e-4 and abs(cv0[i] - w[0] / w.sum()) < 1e-3
+        assert np.dot(n0[i], -x[i]) >= 0
+    prm1 = default_params(normal_radius=0.2, consistent_normals_method=1)
+    n1, _ = orc.compute_normals(prm1, x, o)
+    assert (((x - x.mean(0)) * n1).sum(1) >= 0).all()  # pointing away from the centroid
+
+
+def test_shot_frame_normals_and_repair_loop(orc):
+    """Method 2: normal = inverted z axis of the SHOT frame at NormalRadius; the reference's repair loop rewrites the
+    FIRST n_invalid points (normal_orientation.cpp:96-106), kept as written."""
+    x, _, _, o = synth.make_clouds([1], [17], 2000)
+    far = np.array([[9, 9, 9], [9.01, 9, 9], [9, 9.01, 9.01]], np.float32)  # 3 points: PCA defined, no SHOT frame
+    xyz = np.concatenate([x, far]).astype(np.float32)
+    off = np.array([0, len(xyz)], np.int64)
+    prm = default_params(normal_radius=0.1, consistent_normals_method=2)
+    n2, cv2 = orc.compute_normals(prm, xyz, off)
+    kp = xyz.copy()
+    lrf = orc.shot_lrf(xyz, off, kp, [0, len(kp)], float(np.float32(0.1)))
+    valid = np.isfinite(lrf[:, 0])
+    assert (~valid).sum() == 3
+    body = np.arange(3, 2000)
+    assert np.array_equal(n2[body], -lrf[body, 6:9])
+    raw, _ = orc.compute_normals(default_params(normal_radius=0.1, consistent_normals_method=0), xyz, off)
+    assert np.allclose(np.abs((n2[:3] * raw[:3]).sum(1)), 1, atol=1e-6) and (cv2[:3] == 0).all()
