@@ -125,6 +125,26 @@ def cpu_time_clouds(model, x, n, c, o, lo, hi):
     return time.perf_counter() - t, labels
 
 
+def cpu_approx_baseline(model, batch, ctx=None, n_clouds=96):
+    """The reference's DEFAULT activation is approximate (4 randomized kd-trees, 128 checks): time the oracle port with
+    its FLANN-like forest on a bounded sample.  A cost stand-in: its neighbour sets are random-seed dependent and are
+    not used for parity; agreement with the exact labels is reported."""
+    x, n, c, o, truth = batch
+    n_clouds = min(n_clouds, len(o) - 1)
+    build_ms = model.set_approximate(4, 128)
+    t, labels = cpu_time_clouds(model, x, n, c, o, 0, n_clouds)
+    out = {"value": n_clouds / t, "unit": "clouds/s", "kind": "port, FLANN-like kd-forest (4 trees, 128 checks)",
+           "sample": "%d clouds of the timed batch, %.1f s" % (n_clouds, t), "index_build_s": build_ms / 1e3,
+           "stage_ms_per_cloud": {k: round(v / n_clouds, 3) for k, v in model.last_times.items()},
+           "label_accuracy_vs_truth": float((labels == truth[:n_clouds]).mean())}
+    if ctx is not None:
+        e = int(o[n_clouds])
+        g = ctx.classify_batch(x[:e], n[:e], c[:e], o[:n_clouds + 1], want_maxima=False)[0]
+        out["label_agreement_with_exact"] = float((labels == g).mean())
+    model.set_approximate(0)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,7 +217,10 @@ def main():
                                            % (len(times), per_step)},
                 "e2e": {"value": val, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
-                "note": "oracle port of the reference CPU path (the reference needs PCL/FLANN and cannot be built here); "
+                "approximate_mode": cpu_approx_baseline(model, test_batch(wl, 96, 0, 1)),
+                "note": "FLANNExactMatch=true on both arms (the only mode whose labels can be compared); the reference's "
+                        "default approximate search is timed beside it in approximate_mode. "
+                        "oracle port of the reference CPU path (the reference needs PCL/FLANN and cannot be built here); "
                         "the codebook is built by the untimed set-up on the GPU"}
         print(json.dumps(line), flush=True)
         return 0
@@ -312,6 +335,7 @@ def main():
             cpu_base = {"value": cnt / tt, "unit": "clouds/s", "cores": orc.num_threads(), "kind": "port",
                         "sample": "%d clouds of the timed batch, exact (FLANNExactMatch) activation, %.1f s"
                                   % (cnt, tt), "stage_ms_per_cloud": {k: round(v / cnt, 2) for k, v in model.last_times.items()}}
+            cpu_base["approximate_mode"] = cpu_approx_baseline(model, batches[0], ctx)
 
     if rank == 0:
         fm = np.mean(np.array(stage_ms), axis=0) if stage_ms else np.zeros(4)

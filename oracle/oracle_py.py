@@ -262,6 +262,14 @@ class Model:
         _check(lib().orc_get_maximum_votes(ptr(mi, I64), ptr(mw, F), I64(mi.shape[0]), C.byref(n)))
         return mx[: int(moff[-1])].copy(), moff, mi[: n.value].copy(), mw[: n.value].copy()
 
+    def set_approximate(self, trees=4, checks=128, seed=1):
+        """FLANN-like randomized kd-forest for the activation (the reference's default: KDTreeIndexParams(4),
+        SearchParams(128)).  COST STAND-IN ONLY: neighbour sets depend on random draws and are never used for parity.
+        trees=0 switches back to the exact search.  Returns the index build time in ms (the "flann" bucket)."""
+        f = lib().orc_model_set_approximate
+        f.restype = C.c_double
+        return f(self.h, int(trees), int(checks), C.c_uint32(seed))
+
     def classify_batch(self, xyz, normals, rgb, cloud_off, want_maxima=True):
         xyz, normals, rgb, cloud_off = f32(xyz), f32(normals), u32(rgb), i64(cloud_off)
         B = len(cloud_off) - 1

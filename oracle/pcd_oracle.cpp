@@ -31,6 +31,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <random>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -955,6 +956,197 @@ inline void quat_rotate_inv(const Quat& q, const float* p, float* out) { /* q* p
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Approximate activation: FLANN's randomized kd-forest (KDTreeIndexParams(FLANNNumKDTrees = 4),  */
+/* SearchParams(checks = 128); utils/flann_helper.cpp:59-65, activation_strategy_knn.h:66-70).   */
+/* FLANN 1.9.1 is not in the reference tree: this restates the published algorithm               */
+/* (flann/algorithms/kdtree_index.h: meanSplit on a 100-point sample, cut dimension drawn from   */
+/* the 5 highest-variance dimensions, best-bin-first search over all trees with one shared heap). */
+/* It is the HONEST COST STAND-IN for what the reference executes by default; its neighbour sets */
+/* depend on the random draws and are never used for parity.             */
+/* ------------------------------------------------------------------------------------------- */
+struct KdForest {
+  struct Node {
+    int divfeat = -1; /* -1: leaf */
+    float divval = 0.f;
+    int child1 = -1, child2 = -1; /* leaf: child1 = point index */
+  };
+  int D = 0;
+  const float* data = nullptr;
+  std::vector<std::vector<Node>> trees;
+  std::vector<int> roots;
+  int checks = 128;
+
+  static constexpr int SAMPLE_MEAN = 100, RAND_DIM = 5;
+
+  int divide(std::vector<Node>& nodes, int* ind, int count, std::mt19937& rng) {
+    int id = int(nodes.size());
+    nodes.emplace_back();
+    if (count == 1) {
+      nodes[id].child1 = ind[0];
+      return id;
+    }
+    /* meanSplit */
+    std::vector<double> mean(D, 0.0), var(D, 0.0);
+    int cnt = std::min(int(SAMPLE_MEAN) + 1, count);
+    for (int j = 0; j < cnt; ++j) {
+      const float* v = data + size_t(ind[j]) * D;
+      for (int k = 0; k < D; ++k) mean[k] += v[k];
+    }
+    for (int k = 0; k < D; ++k) mean[k] /= cnt;
+    for (int j = 0; j < cnt; ++j) {
+      const float* v = data + size_t(ind[j]) * D;
+      for (int k = 0; k < D; ++k) {
+        double d = v[k] - mean[k];
+        var[k] += d * d;
+      }
+    }
+    /* selectDivision: one of the RAND_DIM dimensions of highest variance */
+    int topind[RAND_DIM];
+    int num = 0;
+    for (int i = 0; i < D; ++i) {
+      if (num < RAND_DIM || var[i] > var[topind[num - 1]]) {
+        if (num < RAND_DIM) topind[num++] = i;
+        else topind[num - 1] = i;
+        int j = num - 1;
+        while (j > 0 && var[topind[j]] > var[topind[j - 1]]) {
+          std::swap(topind[j], topind[j - 1]);
+          --j;
+        }
+      }
+    }
+    int cutfeat = topind[std::uniform_int_distribution<int>(0, num - 1)(rng)];
+    float cutval = float(mean[cutfeat]);
+    /* planeSplit */
+    int left = 0, right = count - 1;
+    for (;;) {
+      while (left <= right && data[size_t(ind[left]) * D + cutfeat] < cutval) ++left;
+      while (left <= right && data[size_t(ind[right]) * D + cutfeat] >= cutval) --right;
+      if (left > right) break;
+      std::swap(ind[left], ind[right]);
+      ++left;
+      --right;
+    }
+    int lim1 = left;
+    right = count - 1;
+    for (;;) {
+      while (left <= right && data[size_t(ind[left]) * D + cutfeat] <= cutval) ++left;
+      while (left <= right && data[size_t(ind[right]) * D + cutfeat] > cutval) --right;
+      if (left > right) break;
+      std::swap(ind[left], ind[right]);
+      ++left;
+      --right;
+    }
+    int lim2 = left;
+    int index;
+    if (lim1 > count / 2) index = lim1;
+    else if (lim2 < count / 2) index = lim2;
+    else index = count / 2;
+    if (lim1 == count || lim2 == 0) index = count / 2;
+    nodes[id].divfeat = cutfeat;
+    nodes[id].divval = cutval;
+    int c1 = divide(nodes, ind, index, rng);
+    int c2 = divide(nodes, ind + index, count - index, rng);
+    nodes[id].child1 = c1;
+    nodes[id].child2 = c2;
+    return id;
+  }
+
+  void build(const float* words, int64_t N, int dim, int n_trees, unsigned seed) {
+    data = words;
+    D = dim;
+    trees.assign(n_trees, {});
+    roots.assign(n_trees, -1);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < n_trees; ++t) {
+      std::mt19937 rng(seed + 7919u * unsigned(t));
+      std::vector<int> ind(N);
+      for (int64_t i = 0; i < N; ++i) ind[i] = int(i);
+      std::shuffle(ind.begin(), ind.end(), rng);
+      trees[t].reserve(size_t(2 * N));
+      roots[t] = divide(trees[t], ind.data(), int(N), rng);
+    }
+  }
+
+  struct Branch {
+    float mind;
+    int tree, node;
+    bool operator<(const Branch& o) const { return mind > o.mind; } /* min-heap */
+  };
+
+  /* L2 functor with FLANN's early exit on worst_dist (dist.h: checked every 4 elements) */
+  static float l2_bounded(const float* a, const float* b, int n, float worst) {
+    float result = 0.f;
+    int i = 0;
+    for (; i + 3 < n; i += 4) {
+      float d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
+      result += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      if (worst > 0 && result > worst) return result;
+    }
+    for (; i < n; ++i) {
+      float d = a[i] - b[i];
+      result += d * d;
+    }
+    return result;
+  }
+
+  void search_level(const float* q, int t, int node, float mind, int& check_count, std::vector<Branch>& heap,
+                    std::vector<unsigned char>& checked, std::vector<int>& touched, Cand* best, int kk,
+                    int& found) const {
+    for (;;) {
+      const Node& nd = trees[t][node];
+      if (nd.divfeat < 0) {
+        const int idx = nd.child1;
+        if (checked[idx] || (check_count >= checks && found >= kk)) return;
+        checked[idx] = 1;
+        touched.push_back(idx);
+        ++check_count;
+        const float worst = found >= kk ? best[kk - 1].d : -1.f;
+        const float d = l2_bounded(data + size_t(idx) * D, q, D, worst);
+        Cand c{d, idx};
+        if (found < kk || cand_less(c, best[kk - 1])) {
+          int pos = std::min(found, kk - 1);
+          best[pos] = c;
+          if (found < kk) ++found;
+          while (pos > 0 && cand_less(best[pos], best[pos - 1])) {
+            std::swap(best[pos], best[pos - 1]);
+            --pos;
+          }
+        }
+        return;
+      }
+      if (found >= kk && best[kk - 1].d < mind) return; /* result_set.worstDist() < mindist */
+      const float diff = q[nd.divfeat] - nd.divval;
+      const int best_child = diff < 0 ? nd.child1 : nd.child2;
+      const int other = diff < 0 ? nd.child2 : nd.child1;
+      const float new_d = mind + diff * diff;
+      if (found < kk || new_d < best[kk - 1].d) {
+        heap.push_back({new_d, t, other});
+        std::push_heap(heap.begin(), heap.end());
+      }
+      node = best_child;
+    }
+  }
+
+  void knn(const float* q, int kk, Cand* best, int& found, std::vector<unsigned char>& checked,
+           std::vector<int>& touched) const {
+    found = 0;
+    int check_count = 0;
+    std::vector<Branch> heap;
+    heap.reserve(512);
+    touched.clear();
+    for (int t = 0; t < int(trees.size()); ++t)
+      search_level(q, t, roots[t], 0.f, check_count, heap, checked, touched, best, kk, found);
+    while (!heap.empty() && (check_count < checks || found < kk)) {
+      std::pop_heap(heap.begin(), heap.end());
+      Branch b = heap.back();
+      heap.pop_back();
+      search_level(q, b.tree, b.node, b.mind, check_count, heap, checked, touched, best, kk, found);
+    }
+    for (int idx : touched) checked[idx] = 0; /* the visited marks are reset through the list of touched leaves */
+  }
+};
+
+/* ------------------------------------------------------------------------------------------- */
 /* model held by the oracle                                                                     */
 /* ------------------------------------------------------------------------------------------- */
 struct Model {
@@ -968,6 +1160,8 @@ struct Model {
   std::vector<float> kp_train, codeword_weight;
   std::vector<int32_t> codeword_ids;
   std::vector<float> sigma2;
+  std::shared_ptr<KdForest> forest; /* set: activation runs FLANN-style approximate search (cost stand-in only) */
+  double forest_build_ms = 0;
 };
 
 /* A.7  CodewordDistribution::castVotes / castVote (codebook/codeword_distribution.cpp:73-167) */
@@ -1480,7 +1674,13 @@ void activate_block(const Model& m, const float* queries, int64_t Q, int k, int 
     int kk = use_ratio ? k + 1 : k;
     Cand best[PCDB_MAX_K + 1];
     int found = 0;
-    knn_one(qv, m.words.data(), m.N, m.D, kk, dist_type, best, found);
+    if (m.forest && dist_type == PCDB_DIST_EUCLIDEAN) {
+      static thread_local std::vector<unsigned char> checked;
+      static thread_local std::vector<int> touched;
+      if ((int64_t)checked.size() != m.N) checked.assign(m.N, 0);
+      m.forest->knn(qv, kk, best, found, checked, touched);
+    } else
+      knn_one(qv, m.words.data(), m.N, m.D, kk, dist_type, best, found);
     int use = std::min(found, k);
     if (use_ratio && k == 1 && found >= 2) {
       if (best[0].d / best[1].d > ratio_thr) use = 0; /* :75-85 */
@@ -1738,6 +1938,21 @@ void* orc_model_create(const pcdb_params* prm, const float* words, int64_t N, in
     m->codeword_weight.assign(N, 1.0f);
   m->sigma2.assign(class_sigma2, class_sigma2 + n_classes);
   return m;
+}
+/* trees > 0: build the FLANN-like forest and use it for activation (approximate; cost stand-in); trees == 0: exact */
+double orc_model_set_approximate(void* model, int32_t trees, int32_t checks, uint32_t seed) {
+  Model* m = static_cast<Model*>(model);
+  if (trees <= 0) {
+    m->forest.reset();
+    return 0.0;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  auto f = std::make_shared<KdForest>();
+  f->checks = checks;
+  f->build(m->words.data(), m->N, m->D, trees, seed);
+  m->forest = f;
+  m->forest_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return m->forest_build_ms;
 }
 void orc_model_set_params(void* model, const pcdb_params* prm) { static_cast<Model*>(model)->prm = *prm; }
 void orc_model_destroy(void* model) { delete static_cast<Model*>(model); }

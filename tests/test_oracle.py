@@ -440,3 +440,28 @@ def test_shot_frame_normals_and_repair_loop(orc):
     assert np.array_equal(n2[body], -lrf[body, 6:9])
     raw, _ = orc.compute_normals(default_params(normal_radius=0.1, consistent_normals_method=0), xyz, off)
     assert np.allclose(np.abs((n2[:3] * raw[:3]).sum(1)), 1, atol=1e-6) and (cv2[:3] == 0).all()
+
+
+# ---- the approximate-mode cost stand-in ------------------------------------------------------------
+def test_kd_forest_is_a_search_over_the_same_rows(orc):
+    """FLANN-like randomized kd-forest: with unlimited checks it must return the exact neighbours; with 128 checks its
+    distances can only be >= the exact ones and most queries still find the true neighbour on clustered data."""
+    rng = np.random.default_rng(5)
+    centres = rng.random((40, 64), dtype=np.float32)
+    W = (centres[rng.integers(0, 40, 4000)] + 0.05 * rng.standard_normal((4000, 64))).astype(np.float32)
+    Q = (centres[rng.integers(0, 40, 200)] + 0.05 * rng.standard_normal((200, 64))).astype(np.float32)
+    N = W.shape[0]
+    cb = Codebook(W, np.arange(N + 1), np.zeros((N, 3)), np.ones(N), np.zeros(N), np.zeros(N),
+                  np.tile(np.array([1, 0, 0, 0, 1, 1, 1], np.float32), (N, 1)), np.ones(N), np.zeros((N, 3)),
+                  np.arange(N), np.ones(2))
+    m = orc.Model(default_params(), cb)
+    ie, de, _ = m.knn(Q, k=2, dist_type=DIST_EUCLIDEAN)
+    assert m.set_approximate(4, 10 ** 9) >= 0
+    ia, da, _ = m.knn(Q, k=2, dist_type=DIST_EUCLIDEAN)
+    assert np.array_equal(ia, ie) and np.allclose(da, de, rtol=1e-6)
+    m.set_approximate(4, 128)
+    ib, db, _ = m.knn(Q, k=2, dist_type=DIST_EUCLIDEAN)
+    assert (db >= de * (1 - 1e-6)).all() and (ib[:, 0] == ie[:, 0]).mean() > 0.5
+    m.set_approximate(0)
+    ic, _, _ = m.knn(Q, k=2, dist_type=DIST_EUCLIDEAN)
+    assert np.array_equal(ic, ie)
