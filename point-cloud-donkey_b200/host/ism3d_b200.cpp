@@ -534,7 +534,7 @@ void ImplicitShapeModel::train() {
     for (size_t j = 0; j < it.second.size(); ++j) {
       io::Cloud cloud;
       std::string err;
-      if (!io::load_pcd(it.second[j], cloud, err)) throw RuntimeException("could not load training model: " + err);
+      if (!io::load_cloud(it.second[j], cloud, err)) throw RuntimeException("could not load training model: " + err);
       if (cloud.size() == 0) throw RuntimeException("point cloud is empty: " + it.second[j]);
       // implicit_shape_model.cpp:374-390: clouds without (usable) normals get them estimated
       const bool has_normals = cloud.has_normals && !(cloud.normals[0] == 0 && cloud.normals[1] == 0 && cloud.normals[2] == 0) &&
@@ -773,7 +773,7 @@ bool ImplicitShapeModel::detectBatch(const std::vector<std::string>& filenames,
     for (size_t i = b0; i < b1; ++i) {
       io::Cloud c;
       std::string err;
-      if (!io::load_pcd(filenames[i], c, err)) { log("ERROR", err); return false; }
+      if (!io::load_cloud(filenames[i], c, err)) { log("ERROR", err); return false; }
       if (c.size() == 0) { log("ERROR", "point cloud is empty"); return false; }
       // detect(): "first normal is zero/NaN => hasNormals=false" (implicit_shape_model.cpp:614-625)
       if (!c.has_normals || (c.normals[0] == 0 && c.normals[1] == 0 && c.normals[2] == 0) || std::isnan(c.normals[0])) {

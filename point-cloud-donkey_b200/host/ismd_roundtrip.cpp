@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
   if (cmd == "pcd" && argc > 2) {
     io::Cloud c;
     std::string err;
-    if (!io::load_pcd(argv[2], c, err)) return fail(err.c_str());
+    if (!io::load_cloud(argv[2], c, err)) return fail(err.c_str());
     double sx = 0, sn = 0;
     unsigned long long sc = 0;
     for (float v : c.xyz) sx += v;

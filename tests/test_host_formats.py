@@ -53,3 +53,74 @@ def test_pcd_reader(tmp_path, ascii_mode):
     assert abs(float(f["sum_xyz"]) - float(xyz.astype(np.float64).sum())) < 1e-3
     assert abs(float(f["sum_n"]) - float(nrm.astype(np.float64).sum())) < 1e-3
     assert int(f["sum_rgb"]) == int(rgb.astype(np.uint64).sum())
+
+
+def _summary(path):
+    out = subprocess.check_output([TOOL, "pcd", path]).decode()
+    return dict(kv.split("=") for kv in out.split())
+
+
+def test_pcd_binary_compressed_reader(tmp_path):
+    """DATA binary_compressed (LZF, structure-of-arrays payload): literal runs and back references, incl. the long
+    overlapping ones a constant column produces."""
+    xyz, nrm, rgb, off = synth.make_clouds([2], [6], 700)
+    rgb[:300] = rgb[0]  # long runs -> extended-length back references
+    p = str(tmp_path / "c.pcd")
+    pcd.write_pcd_compressed(p, xyz, nrm, rgb)
+    assert os.path.getsize(p) < 700 * 32  # it did compress
+    f = _summary(p)
+    assert int(f["points"]) == 700 and f["normals"] == "1" and f["rgb"] == "1"
+    assert abs(float(f["sum_xyz"]) - float(xyz.astype(np.float64).sum())) < 1e-3
+    assert abs(float(f["sum_n"]) - float(nrm.astype(np.float64).sum())) < 1e-3
+    assert int(f["sum_rgb"]) == int(rgb.astype(np.uint64).sum())
+    # a corrupt stream is an error, not garbage
+    raw = bytearray(open(p, "rb").read())
+    raw[-40:] = b"\xff" * 40
+    open(p, "wb").write(raw)
+    assert subprocess.run([TOOL, "pcd", p], capture_output=True).returncode != 0
+
+
+def test_lzf_roundtrip_matches_python_reference():
+    rng = np.random.default_rng(0)
+    data = bytes(rng.integers(0, 4, 5000, dtype=np.uint8)) + b"\x00" * 1000 + bytes(rng.integers(0, 256, 300, dtype=np.uint8))
+    comp = pcd.lzf_compress(data)
+    # independent decoder of the liblzf stream format
+    out = bytearray()
+    i = 0
+    while i < len(comp):
+        c = comp[i]
+        i += 1
+        if c < 32:
+            out += comp[i:i + c + 1]
+            i += c + 1
+        else:
+            ln = c >> 5
+            if ln == 7:
+                ln += comp[i]
+                i += 1
+            dist = ((c & 31) << 8) + comp[i] + 1
+            i += 1
+            for _ in range(ln + 2):
+                out.append(out[-dist])
+    assert bytes(out) == data and len(comp) < len(data)
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+@pytest.mark.parametrize("with_normals", [True, False])
+def test_ply_reader(tmp_path, fmt, with_normals):
+    xyz, nrm, rgb, off = synth.make_clouds([3], [7], 250)
+    p = str(tmp_path / "c.ply")
+    pcd.write_ply(p, xyz, nrm if with_normals else None, rgb, fmt=fmt, with_faces=True)
+    f = _summary(p)
+    assert int(f["points"]) == 250 and f["normals"] == ("1" if with_normals else "0") and f["rgb"] == "1"
+    assert abs(float(f["sum_xyz"]) - float(xyz.astype(np.float64).sum())) < 1e-3
+    if with_normals:
+        assert abs(float(f["sum_n"]) - float(nrm.astype(np.float64).sum())) < 1e-3
+    assert int(f["sum_rgb"]) == int(rgb.astype(np.uint64).sum())
+
+
+def test_unknown_extension_is_rejected(tmp_path):
+    p = str(tmp_path / "c.xyz")
+    open(p, "w").write("0 0 0\n")
+    r = subprocess.run([TOOL, "pcd", p], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unknown extension" in (r.stdout + r.stderr)
