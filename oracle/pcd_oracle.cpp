@@ -1542,7 +1542,30 @@ void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv,
       all.push_back(std::move(t));
     }
   }
-  /* (cross-class filterMaxima, voting.cpp:265-268: MaxFilterType "None" on this path) */
+  /* cross-class filterMaxima (voting.cpp:265-268) */
+  if (!P.single_object_mode && P.max_filter_type == PCDB_MAXFILTER_SIMPLE) {
+    /* MaximaHandler::suppressNeighborMaxima2 (maxima_handler.cpp:227-268) with radius = Voting.Bandwidth
+     * (voting_mean_shift.cpp:48): repeatedly keep the heaviest pending maximum (std::max_element: the first of equal
+     * ones) and drop every maximum closer than the radius, whatever its class */
+    std::vector<float> work(all.size());
+    for (size_t i = 0; i < all.size(); ++i) work[i] = all[i].m.weight;
+    std::vector<Tmp> kept_max;
+    for (;;) {
+      int best = -1;
+      for (size_t i = 0; i < all.size(); ++i)
+        if (best < 0 || work[best] < work[i]) best = int(i);
+      if (best < 0 || work[best] == -1.f) break;
+      kept_max.push_back(all[best]);
+      work[best] = -1.f;
+      const float* c = all[best].m.position;
+      for (size_t i = 0; i < all.size(); ++i) {
+        const float* q = all[i].m.position;
+        float dx = c[0] - q[0], dy = c[1] - q[1], dz = c[2] - q[2];
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) < P.bandwidth) work[i] = -1.f;
+      }
+    }
+    all = std::move(kept_max);
+  }
   std::stable_sort(all.begin(), all.end(), [](const Tmp& a, const Tmp& b) { return a.m.weight > b.m.weight; });
   float sum = 0, sum_inst = 0; /* normalizeWeights :441-462 */
   for (const Tmp& t : all) {

@@ -20,6 +20,7 @@ struct MsP {
   float h, r2, hh, bin, thr;
   int max_iter, kernel, suppression, min_votes, best_k, average_rotation, n_classes;
   float min_threshold;
+  int cross_class_filter;  // PCDB_MAXFILTER_* applied per cloud when !single_object_mode
 };
 
 __device__ __forceinline__ float ms_profile(int kernel, float u) {
@@ -561,7 +562,7 @@ __global__ void k_max_reduce(const int* __restrict__ M_ptr, const float4* __rest
 
 // ---- per-cloud sort / normalise / threshold / best-K / label (voting.cpp:272-323), one warp per cloud ----------
 __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const unsigned* __restrict__ seg_key,
-                                 const int* __restrict__ max_off, const pcdb_maximum* __restrict__ raw, MsP P,
+                                 const int* __restrict__ max_off, pcdb_maximum* raw, MsP P, int* flag,
                                  pcdb_maximum* sorted, int* kept, int* first, int* label) {
   const int b = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -581,6 +582,29 @@ __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const 
   }
   int g1 = lo;
   const int m0 = max_off[g0], m1 = max_off[g1];
+  if (P.cross_class_filter == PCDB_MAXFILTER_SIMPLE) {
+    // MaximaHandler::suppressNeighborMaxima2 (maxima_handler.cpp:227-268), radius = Voting.Bandwidth: keep the heaviest
+    // pending maximum (the first of equal ones), drop every maximum of any class closer than the radius, repeat.  The
+    // list is short and the loop order dependent: one lane.  Dropped maxima get n_votes = 0 and fall out below.
+    if (lane == 0) {
+      for (int i = m0; i < m1; ++i) flag[i] = (raw[i].n_votes >= P.min_votes && raw[i].n_votes > 0) ? 0 : 2;
+      for (;;) {
+        int best = -1;
+        for (int i = m0; i < m1; ++i)
+          if (flag[i] == 0 && (best < 0 || raw[best].weight < raw[i].weight)) best = i;
+        if (best < 0) break;
+        flag[best] = 1;
+        const float cx = raw[best].position[0], cy = raw[best].position[1], cz = raw[best].position[2];
+        for (int i = m0; i < m1; ++i)
+          if (flag[i] == 0 &&
+              norm3_rn(cx, cy, cz, raw[i].position[0], raw[i].position[1], raw[i].position[2]) < P.h)
+            flag[i] = 2;
+      }
+      for (int i = m0; i < m1; ++i)
+        if (flag[i] == 2) raw[i].n_votes = 0;
+    }
+    __syncwarp();
+  }
   // stable rank by weight (descending) among maxima that pass MinVotesThreshold
   int n_ok = 0;
   for (int i = m0 + lane; i < m1; i += 32) {
@@ -665,6 +689,9 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   P.average_rotation = p.average_rotation;
   P.n_classes = C;
   P.min_threshold = p.min_threshold;
+  P.cross_class_filter = p.single_object_mode ? PCDB_MAXFILTER_NONE : p.max_filter_type;
+  if (P.cross_class_filter == PCDB_MAXFILTER_MERGE)
+    return ctx->fail(PCDB_E_UNSUPPORTED, "Voting.MaxFilterType \"Merge\" is not built (SURVEY 8f-4); use None or Simple");
   if (!(P.bin > 0.f)) return ctx->fail(PCDB_E_INVALID, "Voting.Bandwidth must be positive");
 
   const size_t n = (size_t)V + 2;
@@ -707,6 +734,7 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   PCDB_CUDA(w.mem_off.ensure(sizeof(int) * n));
   PCDB_CUDA(w.max_raw.ensure(sizeof(pcdb_maximum) * n));
   PCDB_CUDA(w.max_sorted.ensure(sizeof(pcdb_maximum) * n));
+  PCDB_CUDA(w.max_flag.ensure(sizeof(int) * n));
 
   const unsigned gV = cdiv(V, 256), gV1 = cdiv(V + 1, 256);
   const pcdb_vote* votes = w.votes.as<pcdb_vote>();
@@ -796,7 +824,7 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   }
   k_cloud_finalize<<<cdiv((int64_t)B * 32, 128), 128, 0, st>>>(B, nseg_ptr, w.seg2_key.as<unsigned>(),
                                                                w.max_off.as<int>(), w.max_raw.as<pcdb_maximum>(), P,
-                                                               w.max_sorted.as<pcdb_maximum>(), w.max_kept.as<int>(),
+                                                               w.max_flag.as<int>(), w.max_sorted.as<pcdb_maximum>(), w.max_kept.as<int>(),
                                                                w.max_first.as<int>(), w.labels.as<int>());
   PCDB_LAUNCH_CHECK();
   *M_out = hM;

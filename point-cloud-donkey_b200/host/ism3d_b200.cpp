@@ -268,7 +268,9 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   if (P.single_object_mode && mtype != "None" && mtype != "Default")
     throw BadParamException("SingleObjectMaxType \"" + mtype + "\" is a 'next' row (SURVEY 8f)");
   const std::string ftr = vr.str("MaxFilterType", "None");
-  if (!P.single_object_mode && ftr != "None") throw BadParamException("MaxFilterType \"" + ftr + "\" is a 'next' row (SURVEY 8f-4)");
+  if (ftr == "None") P.max_filter_type = PCDB_MAXFILTER_NONE;
+  else if (ftr == "Simple") P.max_filter_type = PCDB_MAXFILTER_SIMPLE;
+  else if (!P.single_object_mode) throw BadParamException("MaxFilterType \"" + ftr + "\" is not built (SURVEY 8f-4); use None or Simple");
   if (vr.boolean("UseGlobalFeatures", false)) throw BadParamException("UseGlobalFeatures=true is outside the built hot path");
   if (vo["Parameters"].isMember("RansacVoteFiltering") && vr.boolean("RansacVoteFiltering", false))
     throw BadParamException("RansacVoteFiltering=true is outside the built hot path");

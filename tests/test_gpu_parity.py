@@ -539,6 +539,33 @@ def test_classify_batch_through_gemm_activation(api, orc):
     c.close()
 
 
+def test_scene_cross_class_filter_simple(api, orc):
+    """Voting.MaxFilterType = "Simple" (MaximaHandler::suppressNeighborMaxima2): cross-class non-maximum suppression
+    within the bandwidth leaves one maximum per object; list identical to the oracle's."""
+    from pcdb200.structs import MAXFILTER_SIMPLE
+    base = synth.workload_params("c2", single_object_mode=0, knn_k=2, min_votes_threshold=3)
+    filt = synth.workload_params("c2", single_object_mode=0, knn_k=2, min_votes_threshold=3, max_filter_type=MAXFILTER_SIMPLE)
+    cb = _train_world(orc, base, 4, 3, 1536)
+    classes = [0, 1, 2, 3, 1, 2]
+    x, n, col, truth = synth.make_scene(classes, 77, 1536)
+    off = np.array([0, len(x)], np.int64)
+    c = api.Context(filt, cb)
+    la, mxa, offa = c.classify_batch(x, n, col, off)
+    lb, mxb, offb = orc.Model(filt, cb).classify_batch(x, n, col, off)
+    _, mx0, off0 = orc.Model(base, cb).classify_batch(x, n, col, off)
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb)
+    assert len(classes) <= offa[1] < off0[1]  # the filter removed the overlapping minor-class maxima
+    assert np.array_equal(mxa["class_id"], mxb["class_id"]) and np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    assert np.allclose(mxa["weight"], mxb["weight"], rtol=2e-3, atol=1e-6)
+    assert np.allclose(mxa["position"], mxb["position"], atol=3e-3)
+    pos = mxa["position"].astype(np.float64)
+    d = np.linalg.norm(pos[:, None] - pos[None], axis=2) + np.eye(len(pos)) * 1e9
+    assert d.min() >= filt.bandwidth - 3e-3  # no two survivors closer than the radius
+    with pytest.raises(api.PcdbError):
+        api.Context(synth.workload_params("c2", single_object_mode=0, max_filter_type=2), cb).classify_batch(x, n, col, off)
+    c.close()
+
+
 @pytest.mark.parametrize("k", [1, 2])
 def test_scene_multi_object_maxima_parity(api, orc, k):
     """C5 stand-in: one cluttered scene, SingleObjectMode=false: the full ranked maxima list (class, instance, member
