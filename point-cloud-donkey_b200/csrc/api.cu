@@ -485,6 +485,7 @@ void pcdb_destroy(pcdb_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->ws.release();
   ctx->cb.release();
+  if (ctx->gemm_state && ctx->gemm_state_free) ctx->gemm_state_free(ctx->gemm_state);
   if (ctx->lab_lut_d) cudaFree(ctx->lab_lut_d);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

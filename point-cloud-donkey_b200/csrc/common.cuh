@@ -119,6 +119,8 @@ struct pcdb_ctx {
   pcdb_stats stats;
   bool gemm_events_valid = false;  // ev[5], ev[6] bracket the last tcgen05 activation kernel
   float grid_inv_cell = 0.f;  // 1 / search-grid cell edge of the current batch
+  void* gemm_state = nullptr;            // knn_gemm.cu's per-context buffers / tensor map (opaque here)
+  void (*gemm_state_free)(void*) = nullptr;
   float* lab_lut_d = nullptr;  // 256 + 4000 floats, built on the host with powf (features_cshot.cpp:52-71)
   // host mirrors of the last batch (for pcdb_get_votes / pcdb_get_maximum_votes)
   int64_t last_V = 0, last_M = 0, last_members = 0;

@@ -571,14 +571,20 @@ struct GemmState {
   CUtensorMap map_b;
   DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
   float cmax_h = 0, cerr_max = 0, cmax2 = 0;
+  int max_clusters[2] = {0, 0};  // co-resident CTA pairs of the streaming / resident-query kernel on this device
+  ~GemmState() {
+    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
+                     &fb_list};
+    for (DevBuf* b : all) b->release();
+  }
 };
-// one per context, keyed by pointer (contexts are few and long-lived)
-std::vector<std::pair<pcdb_ctx*, GemmState*>> g_states;
+// owned by the context (freed by pcdb_destroy through gemm_state_free)
 GemmState* state_of(pcdb_ctx* ctx) {
-  for (auto& p : g_states)
-    if (p.first == ctx) return p.second;
-  g_states.push_back({ctx, new GemmState()});
-  return g_states.back().second;
+  if (!ctx->gemm_state) {
+    ctx->gemm_state = new GemmState();
+    ctx->gemm_state_free = [](void* p) { delete static_cast<GemmState*>(p); };
+  }
+  return static_cast<GemmState*>(ctx->gemm_state);
 }
 
 template <bool A_RES, int KT>
@@ -587,9 +593,9 @@ int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_
                       (size_t)(A_RES ? 7 : 6) * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
   // co-resident CTA pairs: GPCs with an odd number of usable SMs leave one SM without a partner, and a pair that
   // cannot be resident from the start would run after the others and double the sweep time
-  static int max_clusters = 0;
+  PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int& max_clusters = state_of(ctx)->max_clusters[A_RES ? 1 : 0];  // same footprint for every KT
   if (max_clusters == 0) {
-    PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
     cfg.blockDim = dim3(THREADS);
