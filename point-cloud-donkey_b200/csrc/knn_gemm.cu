@@ -16,13 +16,27 @@
 // CTA fetching HALF of every codebook tile (128 rows).  Per SM that is 256 flop per streamed byte: a single-CTA
 // 128-row tile needs 64 B/clk/SM from L2 at full tensor rate, i.e. 9.5 KB/clk chip-wide against a measured L2 cap of
 // about 6.3 KB/clk (the first version of this kernel sat exactly on that cap, profiles/r01_gemm_c3_1cta.txt); the pair
-// needs half.  For D=1344 the query tile does not fit and both operands stream.  All pairs sweep the codebook in the
-// same order, so codebook tiles are shared through the 126 MB L2.
+// needs half.  For D=1344 the query tile does not fit and both operands stream.
+//
+// Sweep order: the codebook is cut into slices of <= 40 MB of fp16 rows and the work units (slice, query-tile pair) are
+// handed out SLICE-MAJOR, so all 74 pairs stream the same L2-resident slice at any time and the codebook is read from
+// HBM about once per launch (a query-major sweep of the 0.75 GB C3 codebook let the pairs drift apart: L2 hit rate
+// 53 %, 480 GB of DRAM reads per launch, and on a power-capped part those reads cost clock).  The candidate filter
+// survives the slicing because the running k-th-best bound of every query is carried from slice to slice in global
+// memory (atomic min; a stale value is still an upper bound), and the per-query candidate lists are shared by all
+// slices (atomic append).
 //
 // Pair protocol (leader = even CTA of the cluster): both CTAs issue their TMA loads with .cta_group::2 so the bytes
 // are counted on the LEADER's "full" barrier; the leader's elected thread issues every MMA; tcgen05.commit
 // ...multicast::cluster arrives on the "empty"/"tmem_full" barriers of BOTH CTAs; the epilogue warps of both CTAs
 // release an accumulator by arriving on the leader's "tmem_empty" barrier.
+//
+// The |c|^2 term rides in the GEMM: operand rows are AUGMENTED by one K step of 16 columns, queries with
+// [.., 1, 1, 0 x 14], codewords with [-2 ch, hi, lo, 0 x 14] where hi + lo is an fp16 split of |c|^2 (relative error
+// 2^-22).  The accumulator is then |c|^2 - 2 qh.ch directly and the epilogue is tcgen05.ld + a min tree: no FFMA, no
+// |c|^2 staging, no barrier between epilogue warps.  (On a power-capped B200 the epilogue's instructions cost
+// throughput, not just issue slots: D=1344, where the same epilogue is amortised over 3.8x more MMAs, runs at
+// 1.74 PFLOP/s against 1.16 for D=352 before this change.)
 //
 // Error margin (DESIGN.md "activation"): with qh = fp16(q), ch = fp16(c),
 //   |q.c - fl(qh.ch)| <= |q-qh| |c| + |qh| |c-ch| + |q-qh| |c-ch| + D 2^-22 |qh| |ch|
@@ -43,7 +57,8 @@ constexpr int A_BOX_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_BOX_BYTES = BN_HALF * BK * 2;  // 16 KB per CTA
 constexpr int MAX_STAGES = 7;
 constexpr unsigned kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
-constexpr int KB_RES_MAX = 6;             // resident K-blocks (D <= 384)
+constexpr int KB_RES_MAX = 6;             // resident K-blocks (D + 16 <= 384)
+constexpr int K_AUG = 16;                 // extra K columns carrying the |c|^2 term (one UMMA_K step)
 constexpr int CAND_CAP = 64;              // candidates per (query, codebook split)
 constexpr unsigned TMEM_COLS = 512;
 
@@ -161,7 +176,6 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, unsigned* r) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO in [16,30) (unused for swizzled K-major, set to 1), SBO = 1024 B (8 rows x 128 B) in [32,46), version 1 in
@@ -180,6 +194,12 @@ __device__ __forceinline__ unsigned long long desc64(unsigned lo, unsigned hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+// atomic min on a float that may be negative (+inf initialised): non-negative values order like signed ints,
+// negative ones inversely like unsigned ints
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
 __device__ __forceinline__ bool elect_one() {  // the same lane every time for a full warp
   unsigned pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -191,18 +211,16 @@ constexpr unsigned kIdesc = (1u << 4) | ((unsigned)(BN >> 3) << 17) | ((unsigned
 
 struct GemmArgs {
   long long Q, N;
-  int D;
+  int D;                 // augmented operand row length (descriptor dimension + K_AUG)
   int n_mpairs, n_ntiles, tiles_per_split, n_splits;  // n_mpairs: 256-query tile pairs
-  const float* cnorm;    // |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
-  int* cand_idx;         // [Q][2 S][CAND_CAP]   (2 column halves per codebook split)
+  int* cand_idx;         // [Q][2][CAND_CAP]: one list per (query, column half), shared by all codebook slices
   float* cand_apx;
-  int* cand_cnt;         // [2 S][Q]
-  float* cand_thr;       // [2 S][Q]
+  int* cand_cnt;         // [2][Q], appended with atomics (zeroed before the launch)
+  float* bound;          // [Q] running upper bound on the k-th best approximate distance (+inf before the launch)
 };
 
 struct __align__(16) Barriers {
-  float cn[2][BN];  // |c|^2 of the tile in each accumulator buffer, staged by the epilogue warps
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   unsigned tmem_base;
 };
@@ -346,7 +364,6 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // ===================================================== epilogue: TMEM -> registers -> running candidate filter
     const int grp = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which 128 columns of the 256-wide accumulator this warp filters
-    const int epi_tid = (warp - 4) * 32 + lane;
     int acc = 0;
     unsigned acc_phase = 0;
     for (int unit = pair_id; unit < n_units; unit += n_pairs) {
@@ -358,58 +375,45 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       float best[KT];
 #pragma unroll
       for (int i = 0; i < KT; ++i) best[i] = __int_as_float(0x7f800000);
-      float thr = __int_as_float(0x7f800000);
-      int cnt = 0;
-      const int slice = split * 2 + half;
-      const size_t cbase = active ? ((size_t)row * (2 * g.n_splits) + slice) * CAND_CAP : 0;
-      // software-prefetched |c|^2: each of the 256 epilogue threads owns one column of the tile
-      float cn_next = __ldg(g.cnorm + (size_t)t0 * BN + epi_tid);
+      // bound carried over from the slices already swept for this query (any stale value is still an upper bound)
+      const float gb = active ? __ldcg(g.bound + row) : __int_as_float(0x7f800000);
+      float thr = gb + margin;
+      int* cnt_p = g.cand_cnt + (size_t)half * g.Q + (active ? row : 0);
+      const size_t cbase = active ? ((size_t)row * 2 + half) * CAND_CAP : 0;
       for (int t = t0; t < t1; ++t) {
-        // publish this tile's |c|^2; the barrier also orders it after every thread's reads of tile t-2
-        bars->cn[acc][epi_tid] = cn_next;
-        if (t + 1 < t1) cn_next = __ldg(g.cnorm + (size_t)(t + 1) * BN + epi_tid);
-        epi_bar_sync();
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const int col0 = half * (BN / 2);
         const unsigned taddr = tmem_base + ((unsigned)(grp * 32) << 16) + (unsigned)(acc * BN + col0);
-        const float* cn_s = bars->cn[acc] + col0;
         unsigned ra[32], rb[32];
         tc_ld_32x32b_x32(taddr, ra);
         // Branch-free common path: 32 distances, one min-tree, ONE compare per 32 columns; the per-column scan only runs
         // when some column of the chunk can still be among the k best (rare after the first tiles of a sweep).
 #define PCDB_FILTER_CHUNK(REG, C)                                                                  \
   {                                                                                                \
-    float dv[32];                                                                                  \
-    _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4) {                                             \
-      const float4 cn = *reinterpret_cast<const float4*>(cn_s + (C) * 32 + j4 * 4);                \
-      dv[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 0]), cn.x);                         \
-      dv[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 1]), cn.y);                         \
-      dv[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 2]), cn.z);                         \
-      dv[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 3]), cn.w);                         \
-    }                                                                                              \
     float m16[16];                                                                                 \
-    _Pragma("unroll") for (int i = 0; i < 16; ++i) m16[i] = fminf(dv[i], dv[i + 16]);              \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                 \
+      m16[i] = fminf(__uint_as_float(REG[i]), __uint_as_float(REG[i + 16]));                       \
     _Pragma("unroll") for (int i = 0; i < 8; ++i) m16[i] = fminf(m16[i], m16[i + 8]);              \
     _Pragma("unroll") for (int i = 0; i < 4; ++i) m16[i] = fminf(m16[i], m16[i + 4]);              \
     const float mn = fminf(fminf(m16[0], m16[1]), fminf(m16[2], m16[3]));                          \
     if (mn <= thr) {                                                                               \
       const int n_base = t * BN + col0 + (C) * 32;                                                 \
       _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                             \
-        const float d = dv[e];                                                                     \
+        const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c straight from the accumulator */ \
         if (d <= thr && active && n_base + e < g.N) {                                              \
-          if (cnt < CAND_CAP) {                                                                    \
-            g.cand_idx[cbase + cnt] = n_base + e;                                                  \
-            g.cand_apx[cbase + cnt] = d;                                                           \
+          const int pos = atomicAdd(cnt_p, 1);                                                     \
+          if (pos < CAND_CAP) {                                                                    \
+            g.cand_idx[cbase + pos] = n_base + e;                                                  \
+            g.cand_apx[cbase + pos] = d;                                                           \
           }                                                                                        \
-          ++cnt;                                                                                   \
           float x = d;                                                                             \
           _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                         \
             float lo = fminf(best[i], x);                                                          \
             x = fmaxf(best[i], x);                                                                 \
             best[i] = lo;                                                                          \
           }                                                                                        \
-          thr = best[KT - 1] + margin;                                                             \
+          thr = fminf(best[KT - 1], gb) + margin;                                                  \
         }                                                                                          \
       }                                                                                            \
     }                                                                                              \
@@ -432,10 +436,7 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           acc_phase ^= 1;
         }
       }
-      if (active) {
-        g.cand_cnt[(size_t)slice * g.Q + row] = cnt;
-        g.cand_thr[(size_t)slice * g.Q + row] = thr;
-      }
+      if (active && best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
     }
   }
   tc_fence_before();
@@ -447,18 +448,22 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 }
 
 // ---- codebook / query preparation ------------------------------------------------------------------------------
-// one warp per row: fp16 copy, |row|^2 (double accumulate), |row|, |row - fp16(row)|
+// One warp per row: the fp16 operand row of the augmented GEMM (pitch D + K_AUG), |row|^2 (double accumulate),
+// |fp16(row)|, |row - fp16(row)|.  CODEBOOK rows are stored as [-2 fp16(c), hi, lo, 0 x 14] with hi + lo = |c|^2 split
+// into two halves; query rows as [fp16(q), 1, 1, 0 x 14]: the accumulator of the GEMM is |c|^2 - 2 qh.ch.
+template <bool CODEBOOK>
 __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, __half* xh, float* norm2,
                             float* norm, float* err) {
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n) return;
+  const int Dh = D + K_AUG;
   double s2 = 0, e2 = 0, h2 = 0;
   for (int j = lane; j < D; j += 32) {
     float v = x[r * D + j];
     __half h = __float2half_rn(v);
-    xh[r * D + j] = h;
     float hv = __half2float(h);
+    xh[r * Dh + j] = CODEBOOK ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
     s2 += (double)v * v;
     h2 += (double)hv * hv;
     double dd = (double)v - (double)hv;
@@ -467,6 +472,18 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, __h
   s2 = warp_sum(s2);
   e2 = warp_sum(e2);
   h2 = warp_sum(h2);
+  if (lane < K_AUG) {
+    __half a = __float2half_rn(0.f);
+    if (CODEBOOK) {
+      const float cn = (float)s2;
+      const __half hi = __float2half_rn(cn);
+      if (lane == 0) a = hi;
+      if (lane == 1) a = __float2half_rn(cn - __half2float(hi));
+    } else if (lane < 2) {
+      a = __float2half_rn(1.0f);
+    }
+    xh[r * Dh + D + lane] = a;
+  }
   if (lane == 0) {
     if (norm2) norm2[r] = (float)s2;
     norm[r] = (float)sqrt(h2) * 1.0000002f;   // |fp16(row)|, rounded up
@@ -493,17 +510,34 @@ __global__ void k_max2(const float* __restrict__ a, const float* __restrict__ b,
   }
 }
 
-// margin[q] = 2 * eps_d(q); eps_d = 2 * eps_dot + cnorm rounding
+// margin[q] = 2 * eps_d(q); eps_d bounds |accumulator - (|c|^2 - 2 q.c)|
 __global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restrict__ qerr, long long Q, int D,
                          float cmax_h, float cerr_max, float cmax2, float* margin) {
   long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= Q) return;
   // |q.c - fl(qh.ch)| <= |q-qh||c| + |qh||c-ch| + accumulation error; |c| <= |ch| + |c-ch|
+  const double p22 = 2.384185791015625e-07 /* 2^-22 */;
   double cmax = (double)cmax_h + (double)cerr_max;
-  double eps_dot = (double)qerr[q] * cmax + (double)qnorm_h[q] * (double)cerr_max +
-                   (double)D * 2.384185791015625e-07 /* 2^-22 */ * (double)qnorm_h[q] * (double)cmax_h;
-  double eps_d = 2.0 * eps_dot + 2.0 * 5.9604644775390625e-08 /* 2^-24 */ * ((double)cmax2 + 2.0);
+  double eps_dot = (double)qerr[q] * cmax + (double)qnorm_h[q] * (double)cerr_max;  // operand rounding to fp16
+  // fp32 accumulation of D + 2 products whose magnitudes sum to at most 2 |qh||ch| + |c|^2; the fp16 hi/lo split of
+  // |c|^2 (relative 2^-22, subnormal floor 6e-8) and its own fp32 rounding
+  double eps_acc = (double)(D + 2) * p22 * (2.0 * (double)qnorm_h[q] * (double)cmax_h + (double)cmax2);
+  double eps_cn = p22 * (double)cmax2 + 1.2e-7;
+  double eps_d = 2.0 * eps_dot + eps_acc + eps_cn;
   margin[q] = (float)(2.0 * eps_d * 1.0001);
+}
+
+__global__ void k_fill_f32(float* a, long long n, float v) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+// final pruning threshold of the re-rank: carried bound + margin, written for both column halves
+__global__ void k_final_thr(const float* __restrict__ bound, const float* __restrict__ margin, long long Q, float* thr) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float t = bound[q] + margin[q];
+  thr[q] = t;
+  thr[Q + q] = t;
 }
 
 // queries whose candidate list overflowed in some split -> exact-scan fallback list
@@ -569,11 +603,11 @@ int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, in
 
 struct GemmState {
   CUtensorMap map_b;
-  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, bound, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
   float cmax_h = 0, cerr_max = 0, cmax2 = 0;
   int max_clusters[2] = {0, 0};  // co-resident CTA pairs of the streaming / resident-query kernel on this device
   ~GemmState() {
-    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
+    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &bound, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
                      &fb_list};
     for (DevBuf* b : all) b->release();
   }
@@ -638,14 +672,15 @@ int gemm_prepare_codebook(pcdb_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   cb.gemm_ready = false;
   if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
+  const int Dh = cb.D + K_AUG;
   GemmState* gs = state_of(ctx);
   const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
-  PCDB_CUDA(cb.words_h.ensure(sizeof(__half) * (size_t)cb.N * cb.D + 256));
+  PCDB_CUDA(cb.words_h.ensure(sizeof(__half) * (size_t)cb.N * Dh + 256));
   PCDB_CUDA(cb.cnorm.ensure(sizeof(float) * (n_pad + 4)));
   PCDB_CUDA(gs->cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(gs->cerr.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(ctx->ws.scalars.ensure(256));
-  k_prep_rows<<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, cb.words_h.as<__half>(),
+  k_prep_rows<true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, cb.words_h.as<__half>(),
                                                     cb.cnorm.as<float>(), gs->cnorm_h.as<float>(),
                                                     gs->cerr.as<float>());
   PCDB_LAUNCH_CHECK();
@@ -666,7 +701,7 @@ int gemm_prepare_codebook(pcdb_ctx* ctx) {
   gs->cerr_max = h[1];
   gs->cmax2 = h[2];
   if (!std::isfinite(h[0]) || !std::isfinite(h[2])) return PCDB_OK;  // non-finite codewords: scan path only
-  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, cb.D, BN_HALF));
+  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, Dh, BN_HALF));
   cb.gemm_ready = true;
   return PCDB_OK;
 }
@@ -683,34 +718,37 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   const int K = use_ratio ? k + 1 : k;
   const int D = cb.D;
   // query side: fp16 copy + norms + margins
-  PCDB_CUDA(w.feat_h.ensure(sizeof(__half) * (size_t)Q * D + 256));
+  const int Dh = D + K_AUG;
+  PCDB_CUDA(w.feat_h.ensure(sizeof(__half) * (size_t)Q * Dh + 256));
   PCDB_CUDA(gs->qnorm_h.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->qerr.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->margin.ensure(sizeof(float) * (Q + 1)));
-  k_prep_rows<<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, w.feat_h.as<__half>(), nullptr,
+  k_prep_rows<false><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, w.feat_h.as<__half>(), nullptr,
                                                  gs->qnorm_h.as<float>(), gs->qerr.as<float>());
   PCDB_LAUNCH_CHECK();
   k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, gs->cmax_h,
                                          gs->cerr_max, gs->cmax2, gs->margin.as<float>());
   PCDB_LAUNCH_CHECK();
   CUtensorMap map_a;
-  PCDB_TRY(make_map(ctx, &map_a, w.feat_h.p, Q, D, BM));
+  PCDB_TRY(make_map(ctx, &map_a, w.feat_h.p, Q, Dh, BM));
   GemmArgs g;
   g.Q = Q;
   g.N = cb.N;
-  g.D = D;
+  g.D = Dh;
   g.n_mpairs = (int)cdiv(Q, 2 * BM);
   g.n_ntiles = (int)cdiv(cb.N, BN);
-  // split the codebook sweep when there are fewer 256-query tile pairs than CTA pairs
+  // codebook slices: small enough to stay L2-resident while every query-tile pair passes over them (40 MB of fp16
+  // rows), and at least as many as it takes to give every CTA pair a unit when there are few queries
   const int max_pairs = std::max(1, ctx->sm_count / 2);
-  int S = 1;
-  if (g.n_mpairs < max_pairs) S = std::min(g.n_ntiles, std::max(1, max_pairs / g.n_mpairs));
+  const int64_t tile_bytes = (int64_t)BN * Dh * (int64_t)sizeof(__half);
+  int S = (int)cdiv((int64_t)g.n_ntiles * tile_bytes, 40ll << 20);
+  if (g.n_mpairs < max_pairs) S = std::max(S, max_pairs / g.n_mpairs);
+  S = std::max(1, std::min(S, g.n_ntiles));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
   g.n_splits = S;
-  g.cnorm = cb.cnorm.as<float>();
   g.margin = gs->margin.as<float>();
-  const int S2 = 2 * S;  // two column halves per split
+  const int S2 = 2;  // candidate lists: one per column half, shared by all slices
   const size_t nc = (size_t)Q * S2 * CAND_CAP;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
   PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
@@ -721,9 +759,13 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.cand_idx = w.cand_idx.as<int>();
   g.cand_apx = w.cand_apx.as<float>();
   g.cand_cnt = w.cand_cnt.as<int>();
-  g.cand_thr = w.cand_thr.as<float>();
+  PCDB_CUDA(gs->bound.ensure(sizeof(float) * (Q + 1)));
+  g.bound = gs->bound.as<float>();
+  PCDB_CUDA(cudaMemsetAsync(w.cand_cnt.p, 0, sizeof(int) * (size_t)Q * S2, st));
+  k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, Q, INFINITY);
+  PCDB_LAUNCH_CHECK();
   const int grid = 2 * std::min(g.n_mpairs * S, max_pairs);  // CTA pairs (cluster of 2)
-  const bool a_res = (D + BK - 1) / BK <= KB_RES_MAX;
+  const bool a_res = (Dh + BK - 1) / BK <= KB_RES_MAX;
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
   PCDB_CUDA(cudaEventRecord(e0, st));
   if (a_res)
@@ -732,6 +774,8 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
     PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, gs->map_b, g, grid)));
   PCDB_CUDA(cudaEventRecord(e1, st));
   ctx->gemm_events_valid = true;
+  k_final_thr<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, g.margin, Q, w.cand_thr.as<float>());
+  PCDB_LAUNCH_CHECK();
   PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S2, CAND_CAP, use_ratio, ratio_thr));
   // overflow fallback: exact scan of the affected queries (still on the GPU)
   PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
