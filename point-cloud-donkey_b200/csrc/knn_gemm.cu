@@ -18,7 +18,7 @@
 // about 6.3 KB/clk (the first version of this kernel sat exactly on that cap, profiles/r01_gemm_c3_1cta.txt); the pair
 // needs half.  For D=1344 the query tile does not fit and both operands stream.
 //
-// Sweep order: the codebook is cut into slices of <= 40 MB of fp16 rows and the work units (slice, query-tile pair) are
+// Sweep order: the codebook is cut into slices of <= 20 MB of fp16 rows and the work units (slice, query-tile pair) are
 // handed out SLICE-MAJOR, so all 74 pairs stream the same L2-resident slice at any time and the codebook is read from
 // HBM about once per launch (a query-major sweep of the 0.75 GB C3 codebook let the pairs drift apart: L2 hit rate
 // 53 %, 480 GB of DRAM reads per launch, and on a power-capped part those reads cost clock).  The candidate filter
@@ -42,6 +42,8 @@
 //   |q.c - fl(qh.ch)| <= |q-qh| |c| + |qh| |c-ch| + |q-qh| |c-ch| + D 2^-22 |qh| |ch|
 // per-query norms are computed in the query-prep kernel, codebook maxima at upload time.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "stages.h"
@@ -737,11 +739,16 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.D = Dh;
   g.n_mpairs = (int)cdiv(Q, 2 * BM);
   g.n_ntiles = (int)cdiv(cb.N, BN);
-  // codebook slices: small enough to stay L2-resident while every query-tile pair passes over them (40 MB of fp16
+  // codebook slices: small enough to stay L2-resident while every query-tile pair passes over them (20 MB of fp16
   // rows), and at least as many as it takes to give every CTA pair a unit when there are few queries
   const int max_pairs = std::max(1, ctx->sm_count / 2);
   const int64_t tile_bytes = (int64_t)BN * Dh * (int64_t)sizeof(__half);
-  int S = (int)cdiv((int64_t)g.n_ntiles * tile_bytes, 40ll << 20);
+  static const int64_t slice_mb = [] {  // tuning knob for experiments; the default is what profiles/ was measured with
+    const char* e = getenv("PCDB_GEMM_SLICE_MB");
+    const long v = e ? atol(e) : 0;
+    return (int64_t)(v > 0 ? v : 20);
+  }();
+  int S = (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20);
   if (g.n_mpairs < max_pairs) S = std::max(S, max_pairs / g.n_mpairs);
   S = std::max(1, std::min(S, g.n_ntiles));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
