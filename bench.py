@@ -366,7 +366,11 @@ def main():
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tflops"] if pk["tflops"] else None, "traffic": traffic,
                          "traffic_unit": "DRAM bytes per launch (ncu, profiles/gemm_traffic.json)",
-                         "peak_source": pk["src"], "flop_per_launch": flop_per_launch, "ms_per_launch": avg_gemm_ms,
+                         "peak_source": pk["src"], "peak_burst": pk["tflops_burst"],
+                         "frac_of_burst_peak": achieved / pk["tflops_burst"] if pk["tflops_burst"] else None,
+                         "flop_note": "algorithmic 2*Q*N*D with D = the descriptor length; the kernel issues (D+16)/D of "
+                                      "that (|c|^2 rides in one extra K step)",
+                         "flop_per_launch": flop_per_launch, "ms_per_launch": avg_gemm_ms,
                          "share_of_step": avg_gemm_ms / (ms_total / args.steps) if ms_total else None},
             "cpu_baseline": cpu_base,
             "roofline_stages": stage_roofs,
