@@ -178,6 +178,7 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(unsigned taddr, unsigned* r) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
 // LBO in [16,30) (unused for swizzled K-major, set to 1), SBO = 1024 B (8 rows x 128 B) in [32,46), version 1 in
@@ -215,14 +216,17 @@ struct GemmArgs {
   long long Q, N;
   int D;                 // augmented operand row length (descriptor dimension + K_AUG)
   int n_mpairs, n_ntiles, tiles_per_split, n_splits;  // n_mpairs: 256-query tile pairs
+  const float* cnorm;    // streaming-query variant only: |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
   int* cand_idx;         // [Q][2][CAND_CAP]: one list per (query, column half), shared by all codebook slices
   float* cand_apx;
   int* cand_cnt;         // [2][Q], appended with atomics (zeroed before the launch)
   float* bound;          // [Q] running upper bound on the k-th best approximate distance (+inf before the launch)
+  int2* stage;           // [CTAs][EPI_THREADS][CAND_CAP] private staging lists of the epilogue threads
 };
 
 struct __align__(16) Barriers {
+  float cn[2][BN];  // streaming-query variant only: |c|^2 of the tile in each accumulator buffer
   unsigned long long full[MAX_STAGES], empty[MAX_STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   unsigned tmem_base;
 };
@@ -380,19 +384,44 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // bound carried over from the slices already swept for this query (any stale value is still an upper bound)
       const float gb = active ? __ldcg(g.bound + row) : __int_as_float(0x7f800000);
       float thr = gb + margin;
-      int* cnt_p = g.cand_cnt + (size_t)half * g.Q + (active ? row : 0);
-      const size_t cbase = active ? ((size_t)row * 2 + half) * CAND_CAP : 0;
+      // Candidates of this unit are staged in a list private to this thread (plain stores, local counter) and moved
+      // to the query's shared list at the end of the unit with ONE atomic reservation: a returning global atomic per
+      // append put a ~1 us round trip into the filter loop (C4: 1724 -> 1412 TFLOP/s).
+      int cnt = 0;
+      int2* stage = g.stage + ((size_t)blockIdx.x * EPI_THREADS + (size_t)((warp - 4) * 32 + lane)) * CAND_CAP;
+      // Streaming-query variant (D = 1344): the operands are not augmented (a 17th partial K block would cost a full
+      // 64 KB stage per tile pair on a kernel that already sits on the L2->SM limit), so |c|^2 is added here from a
+      // shared-memory staged tile, one column per epilogue thread, software-prefetched.
+      const int epi_tid = (warp - 4) * 32 + lane;
+      float cn_next = 0.f;
+      if (!A_RES) cn_next = __ldg(g.cnorm + (size_t)t0 * BN + epi_tid);
       for (int t = t0; t < t1; ++t) {
+        if (!A_RES) {
+          // publish this tile's |c|^2; the barrier also orders it after every thread's reads of tile t-2
+          bars->cn[acc][epi_tid] = cn_next;
+          if (t + 1 < t1) cn_next = __ldg(g.cnorm + (size_t)(t + 1) * BN + epi_tid);
+          epi_bar_sync();
+        }
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const int col0 = half * (BN / 2);
         const unsigned taddr = tmem_base + ((unsigned)(grp * 32) << 16) + (unsigned)(acc * BN + col0);
+        const float* cn_s = bars->cn[acc] + col0;
         unsigned ra[32], rb[32];
         tc_ld_32x32b_x32(taddr, ra);
         // Branch-free common path: 32 distances, one min-tree, ONE compare per 32 columns; the per-column scan only runs
         // when some column of the chunk can still be among the k best (rare after the first tiles of a sweep).
 #define PCDB_FILTER_CHUNK(REG, C)                                                                  \
   {                                                                                                \
+    if (!A_RES) {                                                                                  \
+      _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4) {                                           \
+        const float4 cn = *reinterpret_cast<const float4*>(cn_s + (C) * 32 + j4 * 4);              \
+        REG[j4 * 4 + 0] = __float_as_uint(fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 0]), cn.x));     \
+        REG[j4 * 4 + 1] = __float_as_uint(fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 1]), cn.y));     \
+        REG[j4 * 4 + 2] = __float_as_uint(fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 2]), cn.z));     \
+        REG[j4 * 4 + 3] = __float_as_uint(fmaf(-2.f, __uint_as_float(REG[j4 * 4 + 3]), cn.w));     \
+      }                                                                                            \
+    }                                                                                              \
     float m16[16];                                                                                 \
     _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                 \
       m16[i] = fminf(__uint_as_float(REG[i]), __uint_as_float(REG[i + 16]));                       \
@@ -402,13 +431,10 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     if (mn <= thr) {                                                                               \
       const int n_base = t * BN + col0 + (C) * 32;                                                 \
       _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                             \
-        const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c straight from the accumulator */ \
+        const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c */                               \
         if (d <= thr && active && n_base + e < g.N) {                                              \
-          const int pos = atomicAdd(cnt_p, 1);                                                     \
-          if (pos < CAND_CAP) {                                                                    \
-            g.cand_idx[cbase + pos] = n_base + e;                                                  \
-            g.cand_apx[cbase + pos] = d;                                                           \
-          }                                                                                        \
+          if (cnt < CAND_CAP) stage[cnt] = make_int2(n_base + e, __float_as_int(d));               \
+          ++cnt;                                                                                   \
           float x = d;                                                                             \
           _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                         \
             float lo = fminf(best[i], x);                                                          \
@@ -438,7 +464,17 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           acc_phase ^= 1;
         }
       }
-      if (active && best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
+      if (active && cnt > 0) {
+        if (best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
+        // a count above CAND_CAP (here or in the shared list) marks the query for the exact-scan fallback
+        const int base = atomicAdd(g.cand_cnt + (size_t)half * g.Q + row, cnt);
+        const size_t cbase = ((size_t)row * 2 + half) * CAND_CAP;
+        for (int i = 0; i < min(cnt, CAND_CAP) && base + i < CAND_CAP; ++i) {
+          const int2 c = stage[i];
+          g.cand_idx[cbase + base + i] = c.x;
+          g.cand_apx[cbase + base + i] = __int_as_float(c.y);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -454,18 +490,18 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 // |fp16(row)|, |row - fp16(row)|.  CODEBOOK rows are stored as [-2 fp16(c), hi, lo, 0 x 14] with hi + lo = |c|^2 split
 // into two halves; query rows as [fp16(q), 1, 1, 0 x 14]: the accumulator of the GEMM is |c|^2 - 2 qh.ch.
 template <bool CODEBOOK>
-__global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, __half* xh, float* norm2,
+__global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int aug, __half* xh, float* norm2,
                             float* norm, float* err) {
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n) return;
-  const int Dh = D + K_AUG;
+  const int Dh = D + (aug ? K_AUG : 0);  // aug == 0: plain fp16 copy (streaming-query variant)
   double s2 = 0, e2 = 0, h2 = 0;
   for (int j = lane; j < D; j += 32) {
     float v = x[r * D + j];
     __half h = __float2half_rn(v);
     float hv = __half2float(h);
-    xh[r * Dh + j] = CODEBOOK ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
+    xh[r * Dh + j] = (CODEBOOK && aug) ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
     s2 += (double)v * v;
     h2 += (double)hv * hv;
     double dd = (double)v - (double)hv;
@@ -474,7 +510,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, __h
   s2 = warp_sum(s2);
   e2 = warp_sum(e2);
   h2 = warp_sum(h2);
-  if (lane < K_AUG) {
+  if (aug && lane < K_AUG) {
     __half a = __float2half_rn(0.f);
     if (CODEBOOK) {
       const float cn = (float)s2;
@@ -513,7 +549,7 @@ __global__ void k_max2(const float* __restrict__ a, const float* __restrict__ b,
 }
 
 // margin[q] = 2 * eps_d(q); eps_d bounds |accumulator - (|c|^2 - 2 q.c)|
-__global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restrict__ qerr, long long Q, int D,
+__global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restrict__ qerr, long long Q, int D, int aug,
                          float cmax_h, float cerr_max, float cmax2, float* margin) {
   long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= Q) return;
@@ -526,6 +562,9 @@ __global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restr
   double eps_acc = (double)(D + 2) * p22 * (2.0 * (double)qnorm_h[q] * (double)cmax_h + (double)cmax2);
   double eps_cn = p22 * (double)cmax2 + 1.2e-7;
   double eps_d = 2.0 * eps_dot + eps_acc + eps_cn;
+  if (!aug)  // epilogue-side |c|^2: fp32 dot accumulation + one fmaf with a correctly rounded |c|^2
+    eps_d = 2.0 * (eps_dot + (double)D * p22 * (double)qnorm_h[q] * (double)cmax_h) +
+            2.0 * 5.9604644775390625e-08 /* 2^-24 */ * ((double)cmax2 + 2.0);
   margin[q] = (float)(2.0 * eps_d * 1.0001);
 }
 
@@ -605,11 +644,11 @@ int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, in
 
 struct GemmState {
   CUtensorMap map_b;
-  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, bound, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, bound, stage, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
   float cmax_h = 0, cerr_max = 0, cmax2 = 0;
   int max_clusters[2] = {0, 0};  // co-resident CTA pairs of the streaming / resident-query kernel on this device
   ~GemmState() {
-    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &bound, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
+    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &bound, &stage, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
                      &fb_list};
     for (DevBuf* b : all) b->release();
   }
@@ -674,7 +713,8 @@ int gemm_prepare_codebook(pcdb_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   cb.gemm_ready = false;
   if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
-  const int Dh = cb.D + K_AUG;
+  const int aug = (cb.D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;  // resident-query variant <=> augmented operands
+  const int Dh = cb.D + (aug ? K_AUG : 0);
   GemmState* gs = state_of(ctx);
   const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
   PCDB_CUDA(cb.words_h.ensure(sizeof(__half) * (size_t)cb.N * Dh + 256));
@@ -682,7 +722,7 @@ int gemm_prepare_codebook(pcdb_ctx* ctx) {
   PCDB_CUDA(gs->cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(gs->cerr.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(ctx->ws.scalars.ensure(256));
-  k_prep_rows<true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, cb.words_h.as<__half>(),
+  k_prep_rows<true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, aug, cb.words_h.as<__half>(),
                                                     cb.cnorm.as<float>(), gs->cnorm_h.as<float>(),
                                                     gs->cerr.as<float>());
   PCDB_LAUNCH_CHECK();
@@ -720,15 +760,16 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   const int K = use_ratio ? k + 1 : k;
   const int D = cb.D;
   // query side: fp16 copy + norms + margins
-  const int Dh = D + K_AUG;
+  const int aug = (D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;
+  const int Dh = D + (aug ? K_AUG : 0);
   PCDB_CUDA(w.feat_h.ensure(sizeof(__half) * (size_t)Q * Dh + 256));
   PCDB_CUDA(gs->qnorm_h.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->qerr.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->margin.ensure(sizeof(float) * (Q + 1)));
-  k_prep_rows<false><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, w.feat_h.as<__half>(), nullptr,
+  k_prep_rows<false><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, aug, w.feat_h.as<__half>(), nullptr,
                                                  gs->qnorm_h.as<float>(), gs->qerr.as<float>());
   PCDB_LAUNCH_CHECK();
-  k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, gs->cmax_h,
+  k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, aug, gs->cmax_h,
                                          gs->cerr_max, gs->cmax2, gs->margin.as<float>());
   PCDB_LAUNCH_CHECK();
   CUtensorMap map_a;
@@ -748,13 +789,17 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
     const long v = e ? atol(e) : 0;
     return (int64_t)(v > 0 ? v : 20);
   }();
-  int S = (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20);
+  const bool a_res = aug != 0;
+  // (the streaming-query variant for D = 1344 re-reads its query tile with every codebook tile and sits on the L2->SM
+  // limit either way; it keeps the query-major sweep, whose L2 hit rate measured 99 %)
+  int S = a_res ? (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20) : 1;
   if (g.n_mpairs < max_pairs) S = std::max(S, max_pairs / g.n_mpairs);
   S = std::max(1, std::min(S, g.n_ntiles));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
   g.n_splits = S;
   g.margin = gs->margin.as<float>();
+  g.cnorm = cb.cnorm.as<float>();
   const int S2 = 2;  // candidate lists: one per column half, shared by all slices
   const size_t nc = (size_t)Q * S2 * CAND_CAP;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
@@ -768,11 +813,12 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.cand_cnt = w.cand_cnt.as<int>();
   PCDB_CUDA(gs->bound.ensure(sizeof(float) * (Q + 1)));
   g.bound = gs->bound.as<float>();
+  PCDB_CUDA(gs->stage.ensure(sizeof(int2) * (size_t)ctx->sm_count * EPI_THREADS * CAND_CAP));
+  g.stage = gs->stage.as<int2>();
   PCDB_CUDA(cudaMemsetAsync(w.cand_cnt.p, 0, sizeof(int) * (size_t)Q * S2, st));
   k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, Q, INFINITY);
   PCDB_LAUNCH_CHECK();
   const int grid = 2 * std::min(g.n_mpairs * S, max_pairs);  // CTA pairs (cluster of 2)
-  const bool a_res = (Dh + BK - 1) / BK <= KB_RES_MAX;
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
   PCDB_CUDA(cudaEventRecord(e0, st));
   if (a_res)
