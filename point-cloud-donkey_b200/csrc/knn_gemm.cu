@@ -218,7 +218,8 @@ struct GemmArgs {
   int n_mpairs, n_ntiles, tiles_per_split, n_splits;  // n_mpairs: 256-query tile pairs
   const float* cnorm;    // streaming-query variant only: |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
-  int* cand_idx;         // [Q][2][CAND_CAP]: one list per (query, column half), shared by all codebook slices
+  int cand_cap;          // capacity of one shared list: CAND_CAP x (slices of one query tile that can be in flight at once)
+  int* cand_idx;         // [Q][2][cand_cap]: one list per (query, column half), shared by all codebook slices
   float* cand_apx;
   int* cand_cnt;         // [2][Q], appended with atomics (zeroed before the launch)
   float* bound;          // [Q] running upper bound on the k-th best approximate distance (+inf before the launch)
@@ -466,10 +467,11 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }
       if (active && cnt > 0) {
         if (best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
-        // a count above CAND_CAP (here or in the shared list) marks the query for the exact-scan fallback
-        const int base = atomicAdd(g.cand_cnt + (size_t)half * g.Q + row, cnt);
-        const size_t cbase = ((size_t)row * 2 + half) * CAND_CAP;
-        for (int i = 0; i < min(cnt, CAND_CAP) && base + i < CAND_CAP; ++i) {
+        // a staging list that overflowed, or a shared list above its capacity, marks the query for the exact-scan
+        // fallback (the count is pushed past any capacity)
+        const int base = atomicAdd(g.cand_cnt + (size_t)half * g.Q + row, cnt > CAND_CAP ? (1 << 24) : cnt);
+        const size_t cbase = ((size_t)row * 2 + half) * g.cand_cap;
+        for (int i = 0; i < min(cnt, CAND_CAP) && base + i < g.cand_cap; ++i) {
           const int2 c = stage[i];
           g.cand_idx[cbase + base + i] = c.x;
           g.cand_apx[cbase + base + i] = __int_as_float(c.y);
@@ -801,7 +803,11 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   g.margin = gs->margin.as<float>();
   g.cnorm = cb.cnorm.as<float>();
   const int S2 = 2;  // candidate lists: one per column half, shared by all slices
-  const size_t nc = (size_t)Q * S2 * CAND_CAP;
+  // Slices of one query tile run one after the other when there are more tile pairs than CTA pairs; with few queries
+  // they run side by side, each starting from an empty bound and contributing its own descending staircase
+  const int in_flight = std::min(S, (int)cdiv(max_pairs, g.n_mpairs));
+  g.cand_cap = CAND_CAP * std::max(1, in_flight);
+  const size_t nc = (size_t)Q * S2 * g.cand_cap;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
   PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
   PCDB_CUDA(w.cand_cnt.ensure(sizeof(int) * ((size_t)Q * S2 + 1)));
@@ -829,11 +835,11 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   ctx->gemm_events_valid = true;
   k_final_thr<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, g.margin, Q, w.cand_thr.as<float>());
   PCDB_LAUNCH_CHECK();
-  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S2, CAND_CAP, use_ratio, ratio_thr));
+  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S2, g.cand_cap, use_ratio, ratio_thr));
   // overflow fallback: exact scan of the affected queries (still on the GPU)
   PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
   PCDB_CUDA(gs->fb_pos.ensure(sizeof(int) * (Q + 2)));
-  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, CAND_CAP, gs->fb_flag.as<int>());
+  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, g.cand_cap, gs->fb_flag.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
   int n_fb = 0;

@@ -287,7 +287,7 @@ def test_knn_small_codebook_and_ratio(api, orc):
 
 
 # ---- K6: tcgen05 GEMM + exact re-rank -------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,Qn,k", [(20000, 700, 1), (9000, 130, 4), (70000, 2000, 1)])
+@pytest.mark.parametrize("N,Qn,k", [(20000, 700, 1), (9000, 130, 4), (70000, 2000, 1), (150000, 5000, 2)])
 def test_knn_gemm_matches_exact_scan(api, orc, N, Qn, k):
     rng = np.random.default_rng(N + k)
     W = _shot_like(rng, N, 352)
@@ -308,6 +308,26 @@ def test_knn_gemm_matches_exact_scan(api, orc, N, Qn, k):
     o = orc.Model(prm, cb).knn(Q[sub], k=k, dist_type=DIST_EUCLIDEAN)
     assert np.array_equal(a[0][sub], o[0]) and np.array_equal(a[1][sub].view(np.uint32), o[1].view(np.uint32))
     assert st["knn_candidates"] > 0
+    c.close()
+
+
+def test_knn_gemm_candidate_overflow_falls_back_to_the_scan(api):
+    """Hundreds of identical codewords tie within the error margin: the candidate lists overflow and those queries
+    must take the exact-scan fallback on the GPU (ties -> lower row), the rest stays on the tensor-core path."""
+    rng = np.random.default_rng(7)
+    W = _shot_like(rng, 30000, 352)
+    v = _shot_like(rng, 1, 352)[0]
+    dup = np.arange(5700, 6100)  # contiguous, inside a sweep unit: more than 64 candidates inside one work unit of the sweep
+    W[dup] = v
+    Q = _shot_like(rng, 600, 352)
+    Q[:40] = v + 1e-4 * rng.random((40, 352), dtype=np.float32)
+    c = api.Context(default_params(knn_k=3), _dummy_codebook(W))
+    a = c.knn(Q, k=3, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
+    st = c.stats()
+    b = c.knn(Q, k=3, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
+    assert 40 <= st["knn_fallback_queries"] < 600
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[0][:40], np.tile(np.sort(dup)[:3], (40, 1)))
     c.close()
 
 
