@@ -71,3 +71,38 @@ def sharded_cast_votes(ctx, row_lo, row_hi, feat_xyz, feat_lrf, feat_off, idx, d
         out_off.append(out_off[-1] + sum(int(offs[r][b + 1] - offs[r][b]) for r in range(len(per_rank))))
     votes_all = np.concatenate(out) if out else np.zeros(0, VOTE_DTYPE)
     return votes_all, np.asarray(out_off, np.int64)
+
+
+def sharded_scene_votes(ctx, prm, xyz, normals, rgb, device="cpu"):
+    """One large scene on several GPUs: the cloud and the codebook are replicated, the
+    KEYPOINTS are sharded contiguously over the ranks.  Every rank computes the voxel-grid keypoints of the whole scene
+    (cheap, identical everywhere), the reference frames / descriptors / activation / votes of its own keypoint slice, and
+    the votes are all-gathered in rank order — which is keypoint order, so every rank ends up with exactly the vote list
+    a single GPU produces.  Returns (votes, vote_off) for one cloud; feed them to ctx.find_maxima."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    finite = np.isfinite(xyz).all(1)                       # removeNaNFromPointCloud (implicit_shape_model.cpp:611)
+    pts = xyz[finite]
+    col = (np.zeros(len(xyz), np.uint32) if rgb is None else np.asarray(rgb, np.uint32))[finite]
+    nrm = np.ascontiguousarray(normals, np.float32)[finite]
+    kp, kr, _ = ctx.voxel_keypoints(pts, col, [0, len(pts)], prm.leaf_size)
+    cuts = shard_bounds(len(kp), world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    surf = np.isfinite(nrm).all(1)                         # filterNormals (:1040-1068)
+    sx, sn, sc = pts[surf], nrm[surf], col[surf]
+    soff = [0, len(sx)]
+    kx, kc = kp[lo:hi], kr[lo:hi]
+    lrf = ctx.shot_lrf(sx, soff, kx, [0, len(kx)], prm.lrf_radius)
+    ok = np.isfinite(lrf[:, 0]) & np.isfinite(lrf[:, 3]) & np.isfinite(lrf[:, 6])      # features.cpp:64-76
+    kx, kc, lrf = kx[ok], kc[ok], lrf[ok]
+    desc = ctx.shot_describe(prm.feature_type, sx, sn, sc, soff, kx, kc, lrf, [0, len(kx)], prm.feature_radius)
+    ok = ~np.isnan(desc).any(1)                            # removeNaNFeatures (:1276-1308)
+    kx, lrf, desc = kx[ok], lrf[ok], desc[ok]
+    if len(kx):
+        idx, dst, cnt = ctx.knn(desc, k=prm.knn_k, dist_type=prm.distance_type)
+        votes, _ = ctx.cast_votes(kx, lrf, [0, len(kx)], idx, dst, cnt)
+    else:
+        votes = np.zeros(0, VOTE_DTYPE)
+    parts = _all_gather_var(votes.view(np.uint8).reshape(-1), device)
+    allv = np.concatenate([p.view(VOTE_DTYPE) for p in parts]) if parts else np.zeros(0, VOTE_DTYPE)
+    return allv, np.array([0, len(allv)], np.int64)

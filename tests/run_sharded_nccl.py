@@ -6,7 +6,8 @@ Every rank uploads its row shard of a CSHOT-1344 codebook (row_base = first glob
 query batch; the exchange step is one all-gather of the per-shard top-k lists followed by pcdb_merge_topk on the
 device, then the owners cast the votes and all ranks receive them.  Checked on every rank against the unsharded
 codebook on the same GPU: identical rows, bit-identical distances, the same vote multiset, the same labels; on rank 0
-also against the oracle.  (The world-size-2 gloo twin of this script is tests/test_sharding_cpu.py.)
+also against the oracle.  A second section shards the KEYPOINTS of one cluttered scene over the ranks (C5) and checks
+that the all-gathered votes and the maxima equal the single-GPU fused path bit for bit.  (The world-size-2 gloo twin of this script is tests/test_sharding_cpu.py.)
 """
 import argparse
 import json
@@ -87,11 +88,33 @@ def main():
         oidx, odst, ocnt = m.knn(td[:64], k=2)
         ok_oracle = bool(np.array_equal(idx[:64], oidx) and np.array_equal(cnt[:64], ocnt))
 
-    flags = torch.tensor([int(ok_knn), int(ok_votes), int(ok_labels)], device=dev)
+    # C5: one scene, keypoints sharded over the ranks, votes all-gathered; must equal the single-GPU fused path
+    sprm = synth.workload_params("c4", knn_k=1, single_object_mode=0, min_votes_threshold=3)
+    full.set_params(sprm)
+    sx_, sn_, sc_, truth = synth.make_scene([0, 1, 2, 3, 4, 5], 21, P, scale=wl["scale"], plane_points=30000,
+                                            clutter_points=5000)
+    soff_ = np.array([0, len(sx_)], np.int64)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    sv, svoff = sharded.sharded_scene_votes(full, sprm, sx_, sn_, sc_, device=dev)
+    smx, smoff, _, _ = full.find_maxima(sv, svoff)
+    torch.cuda.synchronize()
+    dt_scene = time.perf_counter() - t1
+    _, rmx2, rmoff2 = full.classify_batch(sx_, sn_, sc_, soff_)
+    rv2, rvoff2 = full.get_votes(1, len(sv) + 16)
+    ok_scene = bool(np.array_equal(svoff, rvoff2) and sv.tobytes() == rv2.tobytes() and len(sv) > 0
+                    and np.array_equal(smoff, rmoff2) and np.array_equal(smx["class_id"], rmx2["class_id"])
+                    and np.array_equal(smx["weight"].view(np.uint32), rmx2["weight"].view(np.uint32)))
+    full.set_params(prm)
+
+    flags = torch.tensor([int(ok_knn), int(ok_votes), int(ok_labels), int(ok_scene)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     res = {"world": world, "codewords": int(cb.N), "D": int(cb.D), "queries": int(td.shape[0]), "k": 2,
            "knn_identical": bool(flags[0].item()), "votes_identical": bool(flags[1].item()),
            "labels_identical": bool(flags[2].item()), "knn_vs_oracle_first64": ok_oracle,
+           "scene_keypoint_sharding_identical_to_one_gpu": bool(flags[3].item()), "scene_points": int(len(sx_)),
+           "scene_votes": int(len(sv)), "scene_maxima": int(smoff[1]), "scene_seconds_rank0": dt_scene,
            "labels": labels.tolist(), "truth": te, "sharded_path_seconds_rank0": dt}
     if rank == 0:
         print(json.dumps(res), flush=True)
@@ -102,7 +125,8 @@ def main():
     dist.destroy_process_group()
     shard.close()
     full.close()
-    ok = res["knn_identical"] and res["votes_identical"] and res["labels_identical"] and ok_oracle in (None, True)
+    ok = (res["knn_identical"] and res["votes_identical"] and res["labels_identical"] and ok_oracle in (None, True)
+          and res["scene_keypoint_sharding_identical_to_one_gpu"])
     return 0 if ok else 1
 
 

@@ -26,6 +26,19 @@ class OracleShardCtx:
     def merge_topk(self, i, d):
         return self.orc.merge_topk(i, d)
 
+    # stage entry points used by the keypoint-sharded scene path
+    def voxel_keypoints(self, xyz, rgb, off, leaf):
+        return self.orc.voxel_keypoints(xyz, rgb, off, leaf)
+
+    def shot_lrf(self, sx, soff, kx, koff, radius):
+        return self.orc.shot_lrf(sx, soff, kx, koff, radius)
+
+    def shot_describe(self, ft, sx, sn, sc, soff, kx, kc, lrf, koff, radius):
+        return self.orc.shot_describe(ft, sx, sn, sc, soff, kx, kc, lrf, koff, radius)
+
+    def find_maxima(self, votes, voff):
+        return self.m.find_maxima(votes, voff)
+
     def cast_votes(self, fx, fl, foff, idx, dst, cnt):
         # the oracle has no mask support: cast per (feature, j) for owned rows only
         local = np.where(idx >= 0, idx - self.lo, -1).astype(np.int32)
@@ -87,6 +100,16 @@ def _worker(rank, world, port, q):
         lab, _, _ = full.classify_batch(xt[ot[lo]:ot[hi]], nt[ot[lo]:ot[hi]], rt[ot[lo]:ot[hi]], ot[lo:hi + 1] - ot[lo],
                                         want_maxima=False) if hi > lo else (np.zeros(0, np.int32), None, None)
         ok = ok and np.array_equal(lab, lab_all[lo:hi])
+        # one scene, keypoints sharded over the ranks (C5): the gathered votes are the single-rank votes, bit for bit
+        sprm = synth.workload_params("c2", knn_k=2, single_object_mode=0, min_votes_threshold=3)
+        sx_, sn_, sc_, _ = synth.make_scene([0, 1, 2], 5, 900, plane_points=1500, clutter_points=300)
+        sx_[7] = np.nan
+        whole = OracleShardCtx(orc, sprm, cb, 0, cb.N)
+        sv, svoff = sharded.sharded_scene_votes(whole, sprm, sx_, sn_, sc_)
+        fx1, fl1, fd1, fo1 = orc.compute_features(sprm, sx_, sn_, sc_, [0, len(sx_)])
+        i1, d1, c1 = orc.Model(sprm, cb).knn(fd1, k=2)
+        rv, rvo = orc.Model(sprm, cb).cast_votes(fx1, fl1, fo1, i1, d1, c1)
+        ok = ok and np.array_equal(svoff, rvo) and sv.tobytes() == rv.tobytes() and len(sv) > 0
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
