@@ -5,6 +5,11 @@ lab_golden.npz    RGB -> normalised CIELab + colour distance computed by the REF
                   third_party/pcl_color_conversion/color_conversion.cpp (compiled into oracle/_ref by oracle/Makefile).
 flann_golden.npz  squared-L2 exact nearest neighbours + distances computed by a real FLANN build
                   (cv2.flann_Index, linear index = exhaustive search with FLANN's own distance functors).
+path_golden.npz   REGRESSION fixture of the whole path, produced by the oracle itself (not a pin against the reference:
+                  nothing in the reference produces vectors here): keypoints, LRFs, descriptors, activation, votes,
+                  maxima and labels of a small seeded world (pcdb200.synth).  It freezes today's oracle, so that a later
+                  edit of the oracle or of a kernel that moves any stage shows up against a committed file, on the CPU
+                  (tests/test_oracle.py) and on the GPU (tests/test_gpu_parity.py).
 """
 import ctypes as C
 import os
@@ -67,6 +72,37 @@ def make_flann():
     print("flann_golden written")
 
 
+def path_world():
+    """Inputs of path_golden.npz, regenerated from seeds by the tests (only the outputs are stored)."""
+    sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
+    from pcdb200 import synth
+    prm = synth.workload_params("c2", knn_k=2, single_object_mode=0, min_votes_threshold=2)
+    tr_cls = [c for c in range(3) for _ in range(2)]
+    train = synth.make_clouds(tr_cls, [31 + i for i in range(len(tr_cls))], 1200)
+    te_cls = [0, 1, 2]
+    test = synth.make_clouds(te_cls, [77 + i for i in range(len(te_cls))], 1200)
+    return prm, tr_cls, train, te_cls, test
+
+
+def make_path():
+    prm, tr_cls, (xyz, nrm, rgb, off), te_cls, (xt, nt, rt, ot) = path_world()
+    fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
+    bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    cb = orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bb, 3)
+    m = orc.Model(prm, cb)
+    tx, tl, td, toff = orc.compute_features(prm, xt, nt, rt, ot)
+    idx, dist, cnt = m.knn(td, k=2)
+    votes, voff = m.cast_votes(tx, tl, toff, idx, dist, cnt)
+    labels, mx, moff = m.classify_batch(xt, nt, rt, ot)
+    np.savez_compressed(os.path.join(HERE, "path_golden.npz"), train_feat_off=foff, codebook_words=cb.words,
+                        codebook_sigma2=cb.sigma2, feat_xyz=tx, feat_lrf=tl, feat_desc=td, feat_off=toff, knn_idx=idx,
+                        knn_dist=dist, knn_cnt=cnt, vote_off=voff, votes=votes.view(np.uint8).reshape(-1, 80),
+                        labels=labels, maxima=mx.view(np.uint8).reshape(len(mx), -1), maxima_off=moff)
+    print("path_golden: %d test features, %d votes, %d maxima, labels %s" % (len(tx), len(votes), len(mx), labels))
+
+
 if __name__ == "__main__":
-    make_lab()
-    make_flann()
+    if os.path.isdir("/root/reference"):
+        make_lab()
+        make_flann()
+    make_path()

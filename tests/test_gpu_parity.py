@@ -648,6 +648,49 @@ def test_scene_multi_object_maxima_parity(api, orc, k):
     c.close()
 
 
+def test_path_against_committed_golden_fixture(api):
+    """tests/golden/path_golden.npz (frozen oracle outputs of a seeded world): the CUDA path, fed the same seeds, must
+    land on the committed vectors — keypoints / activation rows bit-exact, descriptors and vote positions within 1e-4,
+    maxima list and labels identical.  No oracle call here: the fixture is the reference."""
+    import importlib.util
+    import os
+    here = os.path.dirname(__file__)
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    prm, tr_cls, (xyz, nrm, rgb, off), te_cls, (xt, nt, rt, ot) = mod.path_world()
+    G = np.load(os.path.join(here, "golden", "path_golden.npz"))
+    from pcdb200 import train
+    c = api.Context(prm)
+    fx, fl, fd, foff = c.compute_features(xyz, nrm, rgb, off)
+    assert np.array_equal(foff, G["train_feat_off"])
+    bb = np.stack([train.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    cb = train.train_codebook(c, prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bb, 3)
+    assert np.abs(cb.words - G["codebook_words"]).max() < DESC_TOL
+    assert np.allclose(cb.sigma2, G["codebook_sigma2"], rtol=1e-3)
+    # from here on use the fixture's codebook so that every later stage is compared on identical inputs
+    cb.words[:] = G["codebook_words"]
+    cb.sigma2[:] = G["codebook_sigma2"]
+    c.set_codebook(cb)
+    tx, tl, td, toff = c.compute_features(xt, nt, rt, ot)
+    assert np.array_equal(toff, G["feat_off"]) and tx.tobytes() == G["feat_xyz"].tobytes()  # keypoints bit-exact
+    assert np.abs(td - G["feat_desc"]).max() < DESC_TOL
+    idx, dist, cnt = c.knn(G["feat_desc"], k=2)
+    assert np.array_equal(idx, G["knn_idx"]) and dist.tobytes() == G["knn_dist"].tobytes()
+    votes, voff = c.cast_votes(G["feat_xyz"], G["feat_lrf"], G["feat_off"], idx, dist, cnt)
+    gv = G["votes"].view(VOTE_DTYPE).reshape(-1)
+    assert np.array_equal(voff, G["vote_off"]) and np.array_equal(votes["class_id"], gv["class_id"])
+    assert np.abs(votes["position"] - gv["position"]).max() < 1e-4
+    labels, mx, moff = c.classify_batch(xt, nt, rt, ot)
+    from pcdb200.structs import MAXIMUM_DTYPE
+    gm = G["maxima"].view(MAXIMUM_DTYPE).reshape(-1)
+    assert labels.tolist() == G["labels"].tolist() and np.array_equal(moff, G["maxima_off"])
+    assert np.array_equal(mx["class_id"], gm["class_id"]) and np.array_equal(mx["n_votes"], gm["n_votes"])
+    assert np.allclose(mx["weight"], gm["weight"], rtol=2e-3, atol=1e-6)
+    assert np.allclose(mx["position"], gm["position"], atol=3e-3)
+    c.close()
+
+
 def test_classify_batch_device_entry(api, small_world):
     import torch
     w = small_world

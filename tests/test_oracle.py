@@ -465,3 +465,35 @@ def test_kd_forest_is_a_search_over_the_same_rows(orc):
     m.set_approximate(0)
     ic, _, _ = m.knn(Q, k=2, dist_type=DIST_EUCLIDEAN)
     assert np.array_equal(ic, ie)
+
+
+# ---- committed whole-path fixture (tests/golden/path_golden.npz) ---------------------------------------------------------
+def _path_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden",
+                                                                              "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.path_world(), np.load(os.path.join(os.path.dirname(__file__), "golden", "path_golden.npz"))
+
+
+def test_oracle_reproduces_the_committed_path_fixture(orc):
+    """The oracle is deterministic and has not drifted: every stage output of the seeded world equals the committed
+    file bit for bit (features, codebook, activation, votes, maxima, labels)."""
+    (prm, tr_cls, (xyz, nrm, rgb, off), te_cls, (xt, nt, rt, ot)), G = _path_golden()
+    fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
+    assert np.array_equal(foff, G["train_feat_off"])
+    bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(len(tr_cls))])
+    cb = orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bb, 3)
+    assert cb.words.tobytes() == G["codebook_words"].tobytes() and cb.sigma2.tobytes() == G["codebook_sigma2"].tobytes()
+    m = orc.Model(prm, cb)
+    tx, tl, td, toff = orc.compute_features(prm, xt, nt, rt, ot)
+    assert np.array_equal(toff, G["feat_off"]) and tx.tobytes() == G["feat_xyz"].tobytes()
+    assert tl.tobytes() == G["feat_lrf"].tobytes() and td.tobytes() == G["feat_desc"].tobytes()
+    idx, dist, cnt = m.knn(td, k=2)
+    assert np.array_equal(idx, G["knn_idx"]) and dist.tobytes() == G["knn_dist"].tobytes()
+    votes, voff = m.cast_votes(tx, tl, toff, idx, dist, cnt)
+    assert np.array_equal(voff, G["vote_off"]) and votes.tobytes() == G["votes"].tobytes()
+    labels, mx, moff = m.classify_batch(xt, nt, rt, ot)
+    assert labels.tolist() == G["labels"].tolist() == te_cls
+    assert np.array_equal(moff, G["maxima_off"]) and mx.tobytes() == G["maxima"].tobytes()
