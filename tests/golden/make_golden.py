@@ -5,6 +5,9 @@ lab_golden.npz    RGB -> normalised CIELab + colour distance computed by the REF
                   third_party/pcl_color_conversion/color_conversion.cpp (compiled into oracle/_ref by oracle/Makefile).
 flann_golden.npz  squared-L2 exact nearest neighbours + distances computed by a real FLANN build
                   (cv2.flann_Index, linear index = exhaustive search with FLANN's own distance functors).
+lzf_golden.npz    a binary_compressed PCD payload compressed by the REFERENCE's vendored liblzf 3.6
+                  (third_party/liblzf-3.6/lzf_c.c, compiled into oracle/_ref/libref_lzf.so): pins the LZF decoder of
+                  host/io_formats.h against the real encoder.
 path_golden.npz   REGRESSION fixture of the whole path, produced by the oracle itself (not a pin against the reference:
                   nothing in the reference produces vectors here): keypoints, LRFs, descriptors, activation, votes,
                   maxima and labels of a small seeded world (pcdb200.synth).  It freezes today's oracle, so that a later
@@ -72,6 +75,27 @@ def make_flann():
     print("flann_golden written")
 
 
+def make_lzf():
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_lzf.so")
+    assert os.path.exists(so), "oracle/_ref/libref_lzf.so missing: run make -C oracle with /root/reference mounted"
+    lz = C.CDLL(so)
+    lz.lzf_compress.restype = C.c_uint
+    lz.lzf_compress.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+    sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
+    from pcdb200 import synth
+    xyz, nrm, rgb, _ = synth.make_clouds([4], [123], 3000)
+    rgb[:800] = rgb[0]
+    n = len(xyz)
+    cols = [xyz[:, 0], xyz[:, 1], xyz[:, 2], rgb.astype(np.uint32), nrm[:, 0], nrm[:, 1], nrm[:, 2], np.zeros(n, np.float32)]
+    raw = b"".join(np.ascontiguousarray(c).tobytes() for c in cols)   # PCD binary_compressed: structure of arrays
+    out = C.create_string_buffer(len(raw) * 2)
+    m = lz.lzf_compress(raw, len(raw), out, len(raw) * 2)
+    assert 0 < m < len(raw)
+    np.savez_compressed(os.path.join(HERE, "lzf_golden.npz"), raw=np.frombuffer(raw, np.uint8),
+                        compressed=np.frombuffer(out.raw[:m], np.uint8), points=np.int64(n))
+    print("lzf_golden: %d -> %d bytes by the reference's liblzf" % (len(raw), m))
+
+
 def path_world():
     """Inputs of path_golden.npz, regenerated from seeds by the tests (only the outputs are stored)."""
     sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
@@ -105,4 +129,5 @@ if __name__ == "__main__":
     if os.path.isdir("/root/reference"):
         make_lab()
         make_flann()
+        make_lzf()
     make_path()

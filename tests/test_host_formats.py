@@ -124,3 +124,34 @@ def test_unknown_extension_is_rejected(tmp_path):
     open(p, "w").write("0 0 0\n")
     r = subprocess.run([TOOL, "pcd", p], capture_output=True, text=True)
     assert r.returncode != 0 and "Unknown extension" in (r.stdout + r.stderr)
+
+
+def test_lzf_reader_against_the_references_own_encoder(tmp_path):
+    """tests/golden/lzf_golden.npz holds a PCD payload compressed by the reference's vendored liblzf 3.6 (compiled from
+    /root/reference into oracle/_ref by oracle/Makefile; generator tests/golden/make_golden.py).  The host reader must
+    decode it to the original column data; when oracle/_ref/libref_lzf.so is present, the reference's decoder must
+    also accept what this repository's test compressor writes."""
+    import ctypes as C
+    G = np.load(os.path.join(ROOT, "tests", "golden", "lzf_golden.npz"))
+    raw, comp, n = G["raw"].tobytes(), G["compressed"].tobytes(), int(G["points"])
+    head = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgb normal_x normal_y normal_z curvature\n"
+            "SIZE 4 4 4 4 4 4 4 4\nTYPE F F F U F F F F\nCOUNT 1 1 1 1 1 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+            "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary_compressed\n" % (n, n))
+    p = str(tmp_path / "ref.pcd")
+    with open(p, "wb") as f:
+        f.write(head.encode() + np.array([len(comp), len(raw)], np.uint32).tobytes() + comp)
+    f_ = _summary(p)
+    cols = np.frombuffer(raw, np.float32).reshape(8, n)
+    rgb = np.frombuffer(raw, np.uint32).reshape(8, n)[3]
+    assert int(f_["points"]) == n and f_["normals"] == "1"
+    assert abs(float(f_["sum_xyz"]) - float(cols[:3].astype(np.float64).sum())) < 1e-3
+    assert abs(float(f_["sum_n"]) - float(cols[4:7].astype(np.float64).sum())) < 1e-3
+    assert int(f_["sum_rgb"]) == int(rgb.astype(np.uint64).sum())
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_lzf.so")
+    if os.path.exists(so):
+        lz = C.CDLL(so)
+        lz.lzf_decompress.restype = C.c_uint
+        lz.lzf_decompress.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
+        mine = pcd.lzf_compress(raw[:20000])
+        out = C.create_string_buffer(20000)
+        assert lz.lzf_decompress(mine, len(mine), out, 20000) == 20000 and out.raw == raw[:20000]
