@@ -5,14 +5,14 @@
 // DistanceType "Euclidean":  d(q,c) = |q|^2 + |c|^2 - 2 q.c.  The q.c term is an fp16 x fp16 -> fp32 GEMM issued with
 // tcgen05.mma (cta_group::2: a CTA pair on one TPC computes a 256 x 256 tile, M=256, N=256, K=16) from TMA-staged,
 // 128B-swizzled shared-memory tiles with the accumulator double-buffered in TMEM.  The M x N score matrix is never
-// written: eight epilogue warps per CTA read each accumulator tile back with tcgen05.ld, add |c|^2 and keep, per query
-// row, every column whose approximate distance is within a RIGOROUS error margin of the running k-th best.  Those
+// written: eight epilogue warps per CTA read each accumulator tile back with tcgen05.ld and keep, per query row, every
+// column whose approximate distance is within a RIGOROUS error margin of the running k-th best.  Those
 // candidates are re-ranked with the exact FLANN fp32 arithmetic (knn_scan.cu:k_rerank), so the neighbour set equals
 // the exact scan's.
 //
 // Tiling: each CTA of a pair owns 128 queries whose fp16 descriptors stay RESIDENT in its shared memory for the whole
-// sweep (D=352: 6 K-blocks of 64, the last one half used — the TMA zero-fills columns >= D, and only 2 of its 4 MMAs
-// are issued, so no flop is wasted on padding) while 256-codeword tiles stream through a 7-stage mbarrier ring, each
+// sweep (D=352 + 16 augmented columns: 6 K-blocks of 64, the last one partly used — the TMA zero-fills the columns
+// beyond the row, and only 3 of its 4 MMAs are issued) while 256-codeword tiles stream through a 7-stage mbarrier ring, each
 // CTA fetching HALF of every codebook tile (128 rows).  Per SM that is 256 flop per streamed byte: a single-CTA
 // 128-row tile needs 64 B/clk/SM from L2 at full tensor rate, i.e. 9.5 KB/clk chip-wide against a measured L2 cap of
 // about 6.3 KB/clk (the first version of this kernel sat exactly on that cap, profiles/r01_gemm_c3_1cta.txt); the pair
@@ -24,7 +24,7 @@
 // 53 %, 480 GB of DRAM reads per launch, and on a power-capped part those reads cost clock).  The candidate filter
 // survives the slicing because the running k-th-best bound of every query is carried from slice to slice in global
 // memory (atomic min; a stale value is still an upper bound), and the per-query candidate lists are shared by all
-// slices (atomic append).
+// slices (a work unit stages its candidates privately and appends them with one atomic reservation).
 //
 // Pair protocol (leader = even CTA of the cluster): both CTAs issue their TMA loads with .cta_group::2 so the bytes
 // are counted on the LEADER's "full" barrier; the leader's elected thread issues every MMA; tcgen05.commit
@@ -35,8 +35,9 @@
 // [.., 1, 1, 0 x 14], codewords with [-2 ch, hi, lo, 0 x 14] where hi + lo is an fp16 split of |c|^2 (relative error
 // 2^-22).  The accumulator is then |c|^2 - 2 qh.ch directly and the epilogue is tcgen05.ld + a min tree: no FFMA, no
 // |c|^2 staging, no barrier between epilogue warps.  (On a power-capped B200 the epilogue's instructions cost
-// throughput, not just issue slots: D=1344, where the same epilogue is amortised over 3.8x more MMAs, runs at
-// 1.74 PFLOP/s against 1.16 for D=352 before this change.)
+// throughput, not just issue slots.)  The streaming-query variant (D=1344) is not augmented: a 22nd, mostly empty
+// K block would cost a full 64 KB stage per tile pair on a kernel that sits on the L2->SM limit; it adds |c|^2 in the
+// epilogue from a shared-memory staged tile and keeps the query-major sweep.
 //
 // Error margin (DESIGN.md "activation"): with qh = fp16(q), ch = fp16(c),
 //   |q.c - fl(qh.ch)| <= |q-qh| |c| + |qh| |c-ch| + |q-qh| |c-ch| + D 2^-22 |qh| |ch|
