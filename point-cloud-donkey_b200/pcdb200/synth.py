@@ -7,7 +7,7 @@ Host-side numpy only: this is input generation, not part of the measured path.
 """
 import numpy as np
 
-from .structs import (DIST_CHISQUARED, DIST_EUCLIDEAN, FEATURE_CSHOT, FEATURE_SHOT, default_params)
+from .structs import (MAXFILTER_SIMPLE, DIST_CHISQUARED, DIST_EUCLIDEAN, FEATURE_CSHOT, FEATURE_SHOT, default_params)
 
 
 def _rand_rot(rng):
@@ -186,6 +186,11 @@ WORKLOADS = {
     # C4: Washington-shaped CSHOT (default_config_kinect.ism radii at object scale 0.2 m)
     "c4": dict(n_classes=51, P=8192, scale=0.2, train_per_class=None, n_test=512, cshot=True,
                radius=0.05, lrf_radius=0.05, leaf=0.02, bandwidth=0.045, dist=DIST_EUCLIDEAN, n_words=1_000_000),
+    # C5: cluttered-scene localisation: one ~300k-point scene per step (25 objects of 8192 points on a table plane plus
+    # clutter), about 2.5e4 keypoints in one cloud, multi-class maxima (SingleObjectMode=false, cross-class filter)
+    "c5": dict(n_classes=10, P=8192, scale=1.0, train_per_class=None, n_test=8, cshot=False,
+               radius=0.40, lrf_radius=0.30, leaf=0.08, bandwidth=0.30, dist=DIST_EUCLIDEAN, n_words=200_000,
+               scene_objects=25, plane_points=80_000, clutter_points=15_000),
 }
 
 
@@ -196,6 +201,10 @@ def workload_params(name, **over):
         feature_radius=w["radius"], lrf_radius=w["lrf_radius"], leaf_size=w["leaf"], bandwidth=w["bandwidth"],
         distance_type=w["dist"], knn_k=1, average_rotation=1, single_object_mode=1,
     )
+    if "scene_objects" in w:
+        p.single_object_mode = 0
+        p.min_votes_threshold = 5
+        p.max_filter_type = MAXFILTER_SIMPLE
     for k, v in over.items():
         setattr(p, k, v)
     return p
