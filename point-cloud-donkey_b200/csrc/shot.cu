@@ -9,6 +9,8 @@
 //
 // Work item = one occupied search-grid cell of keypoints.  The 27 surrounding cells (9 contiguous runs of the
 // cell-sorted surface) are staged once into shared memory as float4 (xyz|rgb), float4 (normal|index) [+ float4 Lab]
+// (dense scenes whose 27 cells hold more than kChunk points skip the staging: each warp filters the runs once from
+// L2 into a global list of in-radius points and the passes read those points by index)
 // and every keypoint of the cell is processed by one warp from that staged copy: pass A weighted covariance (fp64,
 // warp-shuffle reduction), 3x3 symmetric eigen-solve, pass B sign disambiguation, pass C quadrilinear soft histogram
 // accumulated in 32-bit fixed point in shared memory (native integer atomics => bit-reproducible across runs).
@@ -50,6 +52,8 @@ struct ShotArgs {
   int* work_counter;
   unsigned long long* nbr_counts;
   const float* lab_lut;
+  unsigned* glist;   // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of in-radius points
+  long long gcap;    // entries per warp (>= the largest 27-cell population of the batch)
 };
 
 // cyclic Jacobi, ascending eigenvalues; V columns are eigenvectors (the reference: Eigen::SelfAdjointEigenSolver)
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   const int n_items = *a.n_items_ptr;
   unsigned* hist = s_hist + (size_t)warp * D;
   unsigned short* list = s_list + (size_t)warp * kChunk;
+  unsigned* glist = a.glist ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
 
   while (true) {
     __syncthreads();
@@ -212,8 +217,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
     const int T = s_pref[9];
     const float fix_scale = exp2f(floorf(log2f(4294967296.0f / (4.0f * (float)T + 4.0f))));
     const float fix_inv = 1.0f / fix_scale;
-    const int n_chunks = (T + kChunk - 1) / kChunk;
-    const bool multi = n_chunks > 1;
+    const bool multi = T > kChunk;  // dense neighbourhood: no staging, per-warp global lists (see below)
 
     auto stage = [&](int chunk) {
       const int base = chunk * kChunk;
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
     };
     if (!multi && T > 0) stage(0);
     __syncthreads();
+    const float r2_max = fmaxf(a.do_lrf ? a.r2_lrf : 0.f, a.do_desc ? a.r2_shot : 0.f);
 
     for (int round = k0; round < k1; round += kWarps) {
       const bool have = round + warp < k1;
@@ -261,25 +266,43 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         __syncwarp();
         return n;
       };
+      // Dense neighbourhood: one sweep over the nine runs (coalesced float4 reads, served by L2) keeps the indices of
+      // the points inside the larger of the two radii; the passes below then touch only those (typically < 10 % of the
+      // 27-cell population) and apply their own radius inline.  No block-wide barrier in this mode.
+      int n_g = 0;
+      if (multi && have) {
+        for (int r = 0; r < 9; ++r) {
+          const long long rb = s_rbeg[r];
+          const int rl = s_rlen[r];
+          for (int e0 = 0; e0 < rl; e0 += 32) {
+            const int e = e0 + lane;
+            bool in = false;
+            if (e < rl) {
+              const float4 p = a.surfS[rb + e];
+              in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2_max;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) glist[n_g + __popc(m & ((1u << lane) - 1u))] = (unsigned)(rb + e);
+            n_g += __popc(m);
+          }
+        }
+        __syncwarp();
+      }
+      auto pt_at = [&](int i) -> float4 { return multi ? a.surfS[glist[i]] : s_pts[list[i]]; };
+      auto nrm_at = [&](int i) -> float4 { return multi ? a.snrmS[glist[i]] : s_nrm[list[i]]; };
       float rf[9];
       bool lrf_ok = have;
       // ---------------------------------------------------------------- LRF
       if (a.do_lrf) {
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, sw = 0;
         int valid = 0, nall = 0, n_lrf = 0;
-        for (int c = 0; c < max(n_chunks, 1); ++c) {
-          if (multi) {
-            __syncthreads();
-            stage(c);
-            __syncthreads();
-          }
-          const int cnt = min(kChunk, T - c * kChunk);
-          n_lrf = compact(cnt, a.r2_lrf);
+        {
+          n_lrf = multi ? n_g : compact(T, a.r2_lrf);
           if (have)
             for (int i = lane; i < n_lrf; i += 32) {
-              float4 p = s_pts[list[i]];
+              float4 p = pt_at(i);
               float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-              {
+              if (!multi || d2 < a.r2_lrf) {
                 ++nall;
                 if (!(p.x == kx && p.y == ky && p.z == kz)) {
                   double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
@@ -315,17 +338,11 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         }
         // pass B: sign disambiguation
         int plusX = 0, plusZ = 0;
-        for (int c = 0; c < max(n_chunks, 1); ++c) {
-          if (multi) {
-            __syncthreads();
-            stage(c);
-            __syncthreads();
-          }
-          const int cnt = min(kChunk, T - c * kChunk);
-          if (multi) n_lrf = compact(cnt, a.r2_lrf);  // single chunk: pass A's list is still valid
-          if (lrf_ok)
+        {
+          if (lrf_ok)  // the list of pass A is still valid
             for (int i = lane; i < n_lrf; i += 32) {
-              float4 p = s_pts[list[i]];
+              float4 p = pt_at(i);
+              if (multi && !(sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < a.r2_lrf)) continue;
               if (!(p.x == kx && p.y == ky && p.z == kz)) {
                 double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
                        vz = (double)__fsub_rn(p.z, kz);
@@ -342,14 +359,8 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             // Tie (about 2% of real keypoints): the reference looks at the 5 neighbours around the median of the
             // (d^2, index)-sorted valid list (shot_na_lrf.hpp:141-153).  Rank selection by bisection on the 63-bit
             // key (d^2 bits << 32 | index): 63 counting passes over the staged points + 5 successive-minimum passes.
-            auto scan = [&](auto&& f) {
-              if (!multi) {  // the LRF-radius list of passes A/B
-                for (int i = lane; i < n_lrf; i += 32) f(s_pts[list[i]], __float_as_int(s_nrm[list[i]].w));
-              } else {
-                for (int r = 0; r < 9; ++r)
-                  for (int e = lane; e < s_rlen[r]; e += 32)
-                    f(a.surfS[s_rbeg[r] + e], __float_as_int(a.snrmS[s_rbeg[r] + e].w));
-              }
+            auto scan = [&](auto&& f) {  // the list of passes A/B (key_of applies the LRF radius itself)
+              for (int i = lane; i < n_lrf; i += 32) f(pt_at(i), __float_as_int(nrm_at(i).w));
             };
             const unsigned long long kInvalid = ~0ull;
             auto key_of = [&](const float4& p, int idx) -> unsigned long long {
@@ -434,21 +445,14 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
       const float inv_r12f = (float)(1.0 / (a.r_shot / 2));
       const float inv_90f = (float)(1.0 / PST_RAD_90), inv_45f = (float)(1.0 / PST_RAD_45);
       int nshot = 0;
-      for (int c = 0; c < max(n_chunks, 1); ++c) {
-        if (multi) {
-          __syncthreads();
-          stage(c);
-          __syncthreads();
-        }
-        const int cnt = min(kChunk, T - c * kChunk);
-        if (!frame_ok) continue;  // warp-uniform
-        const int n_in = compact(cnt, a.r2_shot);
+      if (frame_ok) {  // warp-uniform
+        const int n_in = multi ? n_g : compact(T, a.r2_shot);
         for (int i = lane; i < n_in; i += 32) {
-          const int e = list[i];
-          float4 p = s_pts[e];
+          float4 p = pt_at(i);
           float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+          if (multi && !(d2 < a.r2_shot)) continue;
           ++nshot;
-          float4 nr = s_nrm[e];
+          float4 nr = nrm_at(i);
           if (!finite3(nr.x, nr.y, nr.z)) continue;
           double cosineDesc = (double)dot3_rn(nr.x, nr.y, nr.z, rf[6], rf[7], rf[8]);
           cosineDesc = fmin(1.0, fmax(-1.0, cosineDesc));
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           int stepC = 0, volC = 0;
           float wC = 0.f;
           if (COLOR) {
-            float4 lb = s_lab[e];
+            float4 lb = multi ? a.slabS[glist[i]] : s_lab[list[i]];
             float cdist = __fdiv_rn(
                 __fadd_rn(fabsf(__fsub_rn(LRef, lb.x)),
                           __fdiv_rn(__fadd_rn(fabsf(__fsub_rn(aRef, lb.y)), fabsf(__fsub_rn(bRef, lb.z))), 2.0f)),
@@ -592,6 +596,27 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   }
 }
 
+// population of the 27-cell neighbourhood of every work item; its maximum sizes the per-warp lists of the dense mode
+__global__ void k_item_population(const unsigned long long* __restrict__ kp_keys, const int* __restrict__ item_start,
+                                  const int* __restrict__ n_items_ptr, const unsigned long long* __restrict__ skeys,
+                                  const long long* __restrict__ surf_off, unsigned long long* max_pop) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= *n_items_ptr) return;
+  const unsigned long long key = kp_keys[item_start[item]];
+  const unsigned cloud = (unsigned)(key >> 48);
+  const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
+  const long long lo = surf_off[cloud], hi = surf_off[cloud + 1];
+  long long T = 0;
+  for (int j = 0; j < 9; ++j) {
+    const int y = cy + j % 3 - 1, z = cz + j / 3 - 1;
+    if (y < 0 || y > 65535 || z < 0 || z > 65535) continue;
+    const long long beg = lower_bound_u64(skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
+    const long long end = lower_bound_u64(skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
+    T += end - beg;
+  }
+  atomicMax(max_pop, (unsigned long long)T);
+}
+
 }  // namespace
 
 size_t shot_smem_bytes(bool color) {
@@ -654,6 +679,24 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   // persistent grid: a multiple of the SM count, bounded by the number of keypoints
   int per_sm = color ? 1 : 2;
   int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, Q);
+  // dense scenes: size the per-warp in-radius lists from the largest 27-cell population of this batch (one sync)
+  unsigned long long* max_pop = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 48);
+  k_item_population<<<cdiv(Q, 256), 256, 0, st>>>(a.kp_keys, a.item_start, a.n_items_ptr, a.skeys, a.surf_off, max_pop);
+  PCDB_LAUNCH_CHECK();
+  unsigned long long h_pop = 0;
+  PCDB_CUDA(cudaMemcpyAsync(&h_pop, max_pop, sizeof(h_pop), cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  a.glist = nullptr;
+  a.gcap = 0;
+  if (h_pop > (unsigned long long)kChunk) {
+    a.gcap = (long long)((h_pop + 31) & ~31ull);
+    const size_t bytes = sizeof(unsigned) * (size_t)a.gcap * (size_t)grid * kWarps;
+    if (bytes > (16ull << 30))
+      return ctx->fail(PCDB_E_INVALID, "a 27-cell neighbourhood holds %llu points: radius too large for this cloud density",
+                       h_pop);
+    PCDB_CUDA(w.shot_glist.ensure(bytes));
+    a.glist = w.shot_glist.as<unsigned>();
+  }
   if (color) {
     PCDB_CUDA(cudaFuncSetAttribute(k_shot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_shot<true><<<grid, kThreads, smem, st>>>(a);
