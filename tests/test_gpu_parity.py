@@ -488,6 +488,38 @@ def test_classify_batch_labels_identical(api, orc, small_world):
     c.close()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_classify_batch_random_parameter_sets(api, orc, small_world, seed):
+    """End-to-end label / maxima parity under randomly drawn option combinations (activation K and ratio test, the four
+    vote-weight flags, kernel, suppression mode, thresholds, BestK, single-object mode, distance functor)."""
+    from pcdb200.structs import KERNEL_GAUSSIAN, KERNEL_UNIFORM, SUPPRESS_AVERAGE, SUPPRESS_SUPPRESS
+    w = small_world
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.choice([1, 2, 3]))
+    prm = synth.workload_params(
+        "c2", knn_k=k, use_distance_ratio=int(k == 1 and rng.random() < 0.5),
+        distance_ratio_threshold=float(rng.choice([0.8, 0.95])),
+        use_class_weight=int(rng.random() < 0.5), use_vote_weight=int(rng.random() < 0.5),
+        use_matching_weight=int(rng.random() < 0.5), use_codeword_weight=int(rng.random() < 0.5),
+        ms_kernel=int(rng.choice([KERNEL_GAUSSIAN, KERNEL_UNIFORM])),
+        maxima_suppression=int(rng.choice([SUPPRESS_AVERAGE, SUPPRESS_SUPPRESS])),
+        min_threshold=float(rng.choice([0.0, 0.05, -0.3])), min_votes_threshold=int(rng.choice([1, 3])),
+        best_k=int(rng.choice([-1, 2])), single_object_mode=int(rng.random() < 0.5),
+        average_rotation=int(rng.random() < 0.5), bandwidth=float(rng.choice([0.2, 0.3, 0.45])),
+        distance_type=int(rng.choice([DIST_EUCLIDEAN, DIST_CHISQUARED])))
+    xt, nt, rt, ot, _ = w["test"]
+    c = api.Context(prm, w["cb"])
+    m = orc.Model(prm, w["cb"])
+    la, mxa, offa = c.classify_batch(xt, nt, rt, ot)
+    lb, mxb, offb = m.classify_batch(xt, nt, rt, ot)
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb)
+    assert np.array_equal(mxa["class_id"], mxb["class_id"]) and np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    assert np.allclose(mxa["weight"], mxb["weight"], rtol=2e-3, atol=1e-6)
+    assert np.allclose(mxa["position"], mxb["position"], atol=3e-3)
+    assert c.stats()["n_votes"] == m.last_counts["votes"]
+    c.close()
+
+
 def test_classify_batch_chi2_quickstart_shape(api, orc):
     """C1 stand-in: qs_input_config.ism radii at mm-like scale, ChiSquared distance (as shipped)."""
     wl = synth.WORKLOADS["c1"]
