@@ -324,6 +324,16 @@ def main():
     h2d = int(b0[0].nbytes + b0[1].nbytes + b0[2].nbytes + b0[3].nbytes)
     d2h = int(4 * args.batch)
 
+    # latency of the interactive use (training_gui / detect() on one cloud): host buffers in, label out, one cloud
+    b0 = batches[0]
+    one = (b0[0][: b0[3][1]], b0[1][: b0[3][1]], b0[2][: b0[3][1]], b0[3][:2])
+    lat = []
+    for i in range(12):
+        t0 = time.perf_counter()
+        ctx.classify_batch(one[0], one[1], one[2], one[3], want_maxima=False)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    single_ms = float(np.median(lat[2:]))
+
     # correctness spot check against the oracle (outside the timed region) ---------------------------------------------
     parity = None
     acc = float((host_labels == batches[(args.steps - 1) % n_distinct][4]).mean())
@@ -405,6 +415,7 @@ def main():
             "counts_per_step": {k: st[k] / args.steps for k in ("n_points", "n_keypoints", "n_features",
                                                                   "n_neighbours_lrf", "n_neighbours_shot", "n_votes",
                                                                   "knn_candidates", "knn_fallback_queries")},
+            "single_cloud_latency_ms": single_ms,
             "label_parity_vs_oracle": parity, "label_accuracy_vs_truth": acc,
         }
         print(json.dumps(line), flush=True)
