@@ -198,6 +198,7 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   m_bb_type = top.str("BoundingBoxType", "MVBB");
   m_instance_labels_primary = top.boolean("InstanceLabelsPrimary", true);
   m_distance_detection_thresh = (float)top.num("DistanceThresholdDetection", 0.05);
+  m_distance_thresh_type = top.str("DistanceThresholdType", "Fixed");
   if (top.boolean("SingleObjectMode", false))
     throw RuntimeException("The parameter for \"single object mode\" must be set inside the \"Voting\" section of the config file. You are using the \"Parameters\" section.");
   if (!top.boolean("FLANNExactMatch", false))
@@ -277,6 +278,17 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   for (const std::string& w : warn) log("WARN", w);
   m_params = P;
   check(pcdb_set_params(m_ctx, &m_params));
+}
+
+std::map<unsigned, float> ImplicitShapeModel::getDetectionThreshold() const {
+  std::map<unsigned, float> out;
+  for (const auto& it : m_voting.m_dimensions_map) {
+    float v = m_distance_detection_thresh;
+    if (m_distance_thresh_type == "ObjectRadius") v *= it.second.first;
+    if (m_distance_thresh_type == "BoundingBoxMedian") v *= it.second.second;
+    out.insert({it.first, v});
+  }
+  return out;
 }
 
 // ---- .ism / .ismd ----------------------------------------------------------------------------------------------------

@@ -117,7 +117,9 @@ class ImplicitShapeModel {
   const std::map<unsigned, unsigned>& getInstanceClassMap() const { return m_instance_to_class_map; }
   bool isInstancePrimaryLabel() const { return m_instance_labels_primary; }
   bool isUsingGlobalFeatures() const { return false; }
-  float getDetectionThreshold() const { return m_distance_detection_thresh; }
+  // size hint per class for detection (implicit_shape_model.h:215-247): DistanceThresholdDetection, scaled by the class's
+  // average object radius ("ObjectRadius") or median bounding-box dimension ("BoundingBoxMedian") learned in training
+  std::map<unsigned, float> getDetectionThreshold() const;
   const Codebook* getCodebook() const { return &m_codebook; }
   const Voting* getVoting() const { return &m_voting; }
   const pcdb_params& params() const { return m_params; }
@@ -142,6 +144,7 @@ class ImplicitShapeModel {
   bool m_logging = true;
   bool m_instance_labels_primary = true;
   float m_distance_detection_thresh = 0.05f;
+  std::string m_distance_thresh_type = "Fixed";
   std::string m_bb_type = "MVBB", m_output_file_name, m_input_config_file;
   std::map<unsigned, std::string> m_class_labels, m_instance_labels;
   std::map<unsigned, unsigned> m_instance_to_class_map;
