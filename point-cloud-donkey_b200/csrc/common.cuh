@@ -94,7 +94,7 @@ struct Codebook_d {
   X(mpos) X(mseg) X(mem_cnt) X(mem_off) X(mem_idx) X(mem_w) \
   X(max_raw) X(max_sorted) X(max_kept) X(max_first) X(labels) X(nbr_cnt) \
   X(nbr_off) X(nbr_key) X(nbr_key2) X(merge_a) X(merge_b) X(nrm_pca) \
-  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist)
+  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len)
 struct Workspace {
 #define X(n) DevBuf n;
   PCDB_WS_FIELDS(X)

@@ -52,6 +52,8 @@ struct ShotArgs {
   int* work_counter;
   unsigned long long* nbr_counts;
   const float* lab_lut;
+  const long long* item_beg;  // [items][9] first sorted-surface index of each of the nine cell runs of an item
+  const int* item_len;        // [items][9] run lengths (precomputed by k_item_ranges: no serial searches in k_shot)
   unsigned* glist;   // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of in-radius points
   long long gcap;    // entries per warp (>= the largest 27-cell population of the batch)
 };
@@ -190,19 +192,9 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
     const int item = s_item;
     if (item >= n_items) break;
     const int k0 = a.item_start[item], k1 = a.item_start[item + 1];
-    const unsigned long long key = a.kp_keys[k0];
-    const unsigned cloud = (unsigned)(key >> 48);
-    const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
     if (threadIdx.x < 9) {
-      int y = cy + (int)(threadIdx.x % 3) - 1, z = cz + (int)(threadIdx.x / 3) - 1;
-      long long beg = 0, end = 0;
-      if (y >= 0 && y <= 65535 && z >= 0 && z <= 65535) {
-        long long lo = a.surf_off[cloud], hi = a.surf_off[cloud + 1];
-        beg = lower_bound_u64(a.skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
-        end = lower_bound_u64(a.skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
-      }
-      s_rbeg[threadIdx.x] = beg;
-      s_rlen[threadIdx.x] = (int)(end - beg);
+      s_rbeg[threadIdx.x] = a.item_beg[(size_t)item * 9 + threadIdx.x];
+      s_rlen[threadIdx.x] = a.item_len[(size_t)item * 9 + threadIdx.x];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -596,24 +588,36 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   }
 }
 
-// population of the 27-cell neighbourhood of every work item; its maximum sizes the per-warp lists of the dense mode
-__global__ void k_item_population(const unsigned long long* __restrict__ kp_keys, const int* __restrict__ item_start,
-                                  const int* __restrict__ n_items_ptr, const unsigned long long* __restrict__ skeys,
-                                  const long long* __restrict__ surf_off, unsigned long long* max_pop) {
+// The nine cell runs (three x-neighbours are contiguous in the cell-sorted surface) of every work item, one thread
+// per (item, run): 18 binary searches that used to sit, serially, at the head of every item inside k_shot.  The
+// largest 27-cell population sizes the per-warp lists of the dense mode.
+__global__ void k_item_ranges(const unsigned long long* __restrict__ kp_keys, const int* __restrict__ item_start,
+                              const int* __restrict__ n_items_ptr, const unsigned long long* __restrict__ skeys,
+                              const long long* __restrict__ surf_off, long long* item_beg, int* item_len) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int item = (int)(t / 9), j = (int)(t % 9);
+  const bool live = item < *n_items_ptr;
+  long long beg = 0, end = 0;
+  if (live) {
+    const unsigned long long key = kp_keys[item_start[item]];
+    const unsigned cloud = (unsigned)(key >> 48);
+    const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
+    const int y = cy + j % 3 - 1, z = cz + j / 3 - 1;
+    if (y >= 0 && y <= 65535 && z >= 0 && z <= 65535) {
+      const long long lo = surf_off[cloud], hi = surf_off[cloud + 1];
+      beg = lower_bound_u64(skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
+      end = lower_bound_u64(skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
+    }
+    item_beg[t] = beg;
+    item_len[t] = (int)(end - beg);
+  }
+}
+__global__ void k_item_population(const int* __restrict__ item_len, const int* __restrict__ n_items_ptr,
+                                  unsigned long long* max_pop) {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= *n_items_ptr) return;
-  const unsigned long long key = kp_keys[item_start[item]];
-  const unsigned cloud = (unsigned)(key >> 48);
-  const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
-  const long long lo = surf_off[cloud], hi = surf_off[cloud + 1];
   long long T = 0;
-  for (int j = 0; j < 9; ++j) {
-    const int y = cy + j % 3 - 1, z = cz + j / 3 - 1;
-    if (y < 0 || y > 65535 || z < 0 || z > 65535) continue;
-    const long long beg = lower_bound_u64(skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
-    const long long end = lower_bound_u64(skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
-    T += end - beg;
-  }
+  for (int j = 0; j < 9; ++j) T += item_len[(size_t)item * 9 + j];
   atomicMax(max_pop, (unsigned long long)T);
 }
 
@@ -681,8 +685,15 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, Q);
   // dense scenes: size the per-warp in-radius lists from the largest 27-cell population of this batch (one sync)
   unsigned long long* max_pop = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 48);
-  k_item_population<<<cdiv(Q, 256), 256, 0, st>>>(a.kp_keys, a.item_start, a.n_items_ptr, a.skeys, a.surf_off, max_pop);
+  PCDB_CUDA(w.item_beg.ensure(sizeof(long long) * 9 * (size_t)(Q + 1)));
+  PCDB_CUDA(w.item_len.ensure(sizeof(int) * 9 * (size_t)(Q + 1)));
+  k_item_ranges<<<cdiv(Q * 9, 256), 256, 0, st>>>(a.kp_keys, a.item_start, a.n_items_ptr, a.skeys, a.surf_off,
+                                                  w.item_beg.as<long long>(), w.item_len.as<int>());
   PCDB_LAUNCH_CHECK();
+  k_item_population<<<cdiv(Q, 256), 256, 0, st>>>(w.item_len.as<int>(), a.n_items_ptr, max_pop);
+  PCDB_LAUNCH_CHECK();
+  a.item_beg = w.item_beg.as<long long>();
+  a.item_len = w.item_len.as<int>();
   unsigned long long h_pop = 0;
   PCDB_CUDA(cudaMemcpyAsync(&h_pop, max_pop, sizeof(h_pop), cudaMemcpyDeviceToHost, st));
   PCDB_CUDA(cudaStreamSynchronize(st));
