@@ -162,6 +162,10 @@ struct pcdb_ctx {
       return ctx->fail(PCDB_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
   } while (0)
 
+// points the descriptor kernel stages in shared memory for one work item (shot.cu); clouds whose whole surface fits
+// are one work item (prep.cu groups their keypoints by cloud instead of by search-grid cell)
+constexpr int PCDB_SHOT_CHUNK = 2048;
+
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // ---- device helpers -------------------------------------------------------------------------------------

@@ -221,6 +221,23 @@ __global__ void k_heads_u64(const unsigned long long* __restrict__ keys, long lo
   head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
+// Work items of the descriptor kernel: the keypoints of one search-grid cell — or of one whole cloud when the cloud's
+// surface fits the kernel's shared-memory stage (small objects: a cell holds 2-3 keypoints, a cloud a few hundred; one
+// staging then serves them all and every warp of the CTA has a keypoint in every round).
+__global__ void k_item_heads(const unsigned long long* __restrict__ keys, long long n,
+                             const long long* __restrict__ surf_off, int* head) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int h = 1;
+  if (i > 0) {
+    const unsigned long long a = keys[i], b = keys[i - 1];
+    const unsigned cloud = (unsigned)(a >> 48);
+    const bool whole = surf_off[cloud + 1] - surf_off[cloud] <= PCDB_SHOT_CHUNK;
+    h = whole ? ((a >> 48) != (b >> 48)) : (a != b);
+  }
+  head[i] = h;
+}
+
 // seg_start[id] = i for every head; seg_start[total] = n
 __global__ void k_seg_starts(const int* __restrict__ head, const int* __restrict__ seg_id, long long n,
                              int* seg_start) {
@@ -448,7 +465,8 @@ int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color) {
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.kkeys.as<unsigned long long>(), w.kkeys2.as<unsigned long long>(),
                                    w.kvals.as<int>(), w.kvals2.as<int>(), Q, 48 + ceil_log2(B + 1)));
-  k_heads_u64<<<cdiv(Q, 256), 256, 0, st>>>(w.kkeys2.as<unsigned long long>(), Q, w.item_head.as<int>());
+  k_item_heads<<<cdiv(Q, 256), 256, 0, st>>>(w.kkeys2.as<unsigned long long>(), Q, w.surf_off.as<long long>(),
+                                             w.item_head.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_CUDA(cudaMemsetAsync(w.item_head.as<int>() + Q, 0, sizeof(int), st));
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.item_head.as<int>(), w.item_id.as<int>(), Q + 1));

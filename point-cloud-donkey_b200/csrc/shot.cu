@@ -24,7 +24,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 2048;               // staged points per chunk
+constexpr int kChunk = PCDB_SHOT_CHUNK;     // staged points per work item
 
 constexpr double PST_RAD_45 = 0.78539816339744830961566084581988;
 constexpr double PST_RAD_90 = 1.5707963267948966192313216916398;
@@ -603,8 +603,10 @@ __global__ void k_item_ranges(const unsigned long long* __restrict__ kp_keys, co
     const unsigned cloud = (unsigned)(key >> 48);
     const int cz = (int)((key >> 32) & 0xffff), cy = (int)((key >> 16) & 0xffff), cx = (int)(key & 0xffff);
     const int y = cy + j % 3 - 1, z = cz + j / 3 - 1;
-    if (y >= 0 && y <= 65535 && z >= 0 && z <= 65535) {
-      const long long lo = surf_off[cloud], hi = surf_off[cloud + 1];
+    const long long lo = surf_off[cloud], hi = surf_off[cloud + 1];
+    if (hi - lo <= kChunk) {  // whole-cloud item (prep.cu:k_item_heads): one run, the cloud itself
+      if (j == 0) { beg = lo; end = hi; }
+    } else if (y >= 0 && y <= 65535 && z >= 0 && z <= 65535) {
       beg = lower_bound_u64(skeys, lo, hi, grid_key(cloud, max(cx - 1, 0), y, z));
       end = lower_bound_u64(skeys, beg, hi, grid_key(cloud, min(cx + 1, 65535), y, z) + 1ull);
     }
