@@ -219,13 +219,14 @@ int pcdb_get_votes(pcdb_ctx* ctx, pcdb_vote* votes_out, int64_t* vote_off_out, i
 /* ---- fused batch path (the throughput entry) -------------------------- */
 /* ImplicitShapeModel::detect (implicit_shape_model.cpp:583-712) for B clouds at once, label pick of
  * eval_tool (src/eval_tool/eval_classification.cpp:412-417) included.  Host buffers in, host buffers out.
+ * normals == NULL: the reference's hasNormals == false path, normals are estimated (see pcdb_compute_normals).
  * label_out[b] = class of the best maximum or -1.  maxima_out/maxima_off_out may be NULL.
  * times_ms_out[7]: complete, features, keypoints, normals, flann, voting, maxima (implicit_shape_model.cpp:160). */
 int pcdb_classify_batch(pcdb_ctx* ctx, const float* xyz, const float* normals, const uint32_t* rgb,
                         const int64_t* cloud_off, int32_t B, int32_t* label_out, pcdb_maximum* maxima_out,
                         int64_t* maxima_off_out, int64_t maxima_capacity, double* times_ms_out);
-/* Same, inputs already resident in device memory (xyz P x 3, normals P x 3, rgb P or NULL, cloud_off on HOST),
- * labels written to device memory. */
+/* Same, inputs already resident in device memory (xyz P x 3, normals P x 3 or NULL = estimate them, rgb P or NULL,
+ * cloud_off on HOST), labels written to device memory. */
 int pcdb_classify_batch_d(pcdb_ctx* ctx, const float* xyz_d, const float* normals_d, const uint32_t* rgb_d,
                           const int64_t* cloud_off, int32_t B, int32_t* label_out_d);
 
