@@ -233,7 +233,16 @@ __global__ void k_item_heads(const unsigned long long* __restrict__ keys, long l
     const unsigned long long a = keys[i], b = keys[i - 1];
     const unsigned cloud = (unsigned)(a >> 48);
     const bool whole = surf_off[cloud + 1] - surf_off[cloud] <= PCDB_SHOT_CHUNK;
-    h = whole ? ((a >> 48) != (b >> 48)) : (a != b);
+    if (!whole) {
+      h = a != b;
+    } else if ((a >> 48) != (b >> 48)) {
+      h = 1;
+    } else {
+      // a cloud's keypoints are cut into items of 64 (8 rounds of the 8 warps): fine enough to balance the persistent
+      // CTAs at the end of the launch, coarse enough to amortise the staging of the cloud
+      const long long first = lower_bound_u64(keys, 0, n, (unsigned long long)cloud << 48);
+      h = ((i - first) % 64) == 0;
+    }
   }
   head[i] = h;
 }
