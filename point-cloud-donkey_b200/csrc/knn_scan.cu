@@ -50,6 +50,30 @@ __device__ __forceinline__ float accum4(float acc, const float4 q, const float4 
   }
 }
 
+// Chi-squared tile pass: the same terms in the same order as the exact functor, but with the fast reciprocal-multiply
+// division (__fdividef, <= 2 ulp) instead of the IEEE one (which costs ~10 instructions per dimension).  The result is
+// only used to decide which pairs deserve the exact evaluation, see k_knn_scan.
+__device__ __forceinline__ float accum4_chi2_fast(float acc, const float4 q, const float4 c) {
+  const float qa[4] = {q.x, q.y, q.z, q.w}, ca[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float s = __fadd_rn(ca[e], qa[e]);
+    const float diff = __fsub_rn(ca[e], qa[e]);
+    const float t = __fdividef(__fmul_rn(diff, diff), s);
+    acc = __fadd_rn(acc, s > 0.f ? t : 0.f);
+  }
+  return acc;
+}
+
+// the exact functor over one pair of rows in FLANN order (one thread; used for the few pairs that pass the filter)
+template <int DIST>
+__device__ float exact_pair(const float* __restrict__ q, const float* __restrict__ c, int D) {
+  float acc = 0.f;
+  for (int j = 0; j < D; j += 4)
+    acc = accum4<DIST>(acc, *reinterpret_cast<const float4*>(q + j), __ldg(reinterpret_cast<const float4*>(c + j)));
+  return acc;
+}
+
 // grid = (q tiles, splits).  Each CTA scans codeword rows [split*rows_per_split, ...) for its 64 queries and writes
 // its K best per query to part_* [split][q][K].
 template <int DIST>
@@ -66,6 +90,9 @@ __global__ void __launch_bounds__(256) k_knn_scan(const float* __restrict__ quer
   const long long n_begin = (long long)blockIdx.y * rows_per_split;
   const long long n_end = min(N, n_begin + rows_per_split);
   if (threadIdx.x < TQ) sCnt[threadIdx.x] = 0;
+  // |approx - exact| <= rho * exact with rho = (D + 16) 2^-23: 2.5 ulp per term (fast vs IEEE division) plus the
+  // propagation of those differences through D sequential fp32 additions of non-negative terms
+  const float chi2_slack = 1.0f + 2.0f * (float)(D + 16) * 1.1920929e-07f;
   __syncthreads();
   for (long long n0 = n_begin; n0 < n_end; n0 += TC) {
     float acc[4][4];
@@ -97,7 +124,9 @@ __global__ void __launch_bounds__(256) k_knn_scan(const float* __restrict__ quer
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = accum4<DIST>(acc[i][j], qv[i], cv[j]);
+          for (int j = 0; j < 4; ++j)
+            acc[i][j] = DIST == PCDB_DIST_CHISQUARED ? accum4_chi2_fast(acc[i][j], qv[i], cv[j])
+                                                     : accum4<DIST>(acc[i][j], qv[i], cv[j]);
       }
       __syncthreads();
     }
@@ -114,6 +143,13 @@ __global__ void __launch_bounds__(256) k_knn_scan(const float* __restrict__ quer
       for (int c = 0; c < lim; ++c) {
         float d = sDist[q][c];
         int idx = (int)(n0 + c);
+        if (DIST == PCDB_DIST_CHISQUARED) {
+          // d is the fast approximation (relative error <= rho, see above): a pair that cannot reach the running
+          // k-th best even at the favourable end of that interval is dropped, the others get the exact functor, so
+          // the list holds exact FLANN-order values and the result equals the all-exact scan bit for bit
+          if (cnt == K && d > t.d[K - 1] * chi2_slack) continue;
+          d = exact_pair<DIST>(queries + min(q0 + q, Q - 1) * D, words + (n0 + c) * D, D);
+        }
         if (cnt == K && !cand_less(d, idx, t.d[K - 1], t.i[K - 1])) continue;
         int p = (cnt < K) ? cnt++ : K - 1;
         while (p > 0 && cand_less(d, idx, t.d[p - 1], t.i[p - 1])) {
