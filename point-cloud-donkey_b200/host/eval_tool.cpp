@@ -8,6 +8,8 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <thread>
+#include <memory>
 #include <map>
 #include <sstream>
 #include <string>
@@ -86,7 +88,8 @@ Options parse(int argc, char** argv) {
       {"--inputfile", "inputfile"}, {"-t", "train"}, {"--train", "train"}, {"-i", "inplace"}, {"--inplace", "inplace"},
       {"-m", "models"}, {"--models", "models"}, {"-c", "classes"}, {"--classes", "classes"}, {"-d", "detect"},
       {"--detect", "detect"}, {"-p", "pointclouds"}, {"--pointclouds", "pointclouds"}, {"-g", "groundtruth"},
-      {"--groundtruth", "groundtruth"}, {"--batch", "batch"}, {"--device", "device"}, {"--log", "log"}};
+      {"--groundtruth", "groundtruth"}, {"--batch", "batch"}, {"--device", "device"}, {"--gpus", "gpus"},
+      {"--log", "log"}};
   Options o;
   std::string cur;
   for (int i = 1; i < argc; ++i) {
@@ -116,7 +119,9 @@ int main(int argc, char** argv) {
                    "  -m <pcd...> -c <ids...>   training models and class ids on the command line\n"
                    "  -d <ism>       classify with a trained model\n"
                    "  -p <pcd...> -g <ids...>   test clouds and ground-truth ids on the command line\n"
-                   "  --batch N  clouds per GPU batch (default 256)   --device N  CUDA device\n";
+                   "  --batch N  clouds per GPU batch (default 256)   --device N  CUDA device\n"
+                   "  --gpus N   classification only: shard the test list over N GPUs (devices device..device+N-1),\n"
+                   "             one context and one host thread per GPU, no communication\n";
       return 0;
     }
     const int device = opt.has("device") ? std::stoi(opt.one("device")) : 0;
@@ -212,9 +217,52 @@ int main(int argc, char** argv) {
       auto t0 = std::chrono::steady_clock::now();
       std::vector<std::vector<ism3d::VotingMaximum>> all;
       std::map<std::string, double> times;
-      if (!ism.detectBatch(pointClouds, all, times, batch)) {
-        std::cerr << "classification failed" << std::endl;
-        return 1;
+      const int n_gpus = opt.has("gpus") ? std::max(1, std::stoi(opt.one("gpus"))) : 1;
+      if (n_gpus <= 1) {
+        if (!ism.detectBatch(pointClouds, all, times, batch)) {
+          std::cerr << "classification failed" << std::endl;
+          return 1;
+        }
+      } else {
+        // test clouds are independent: contiguous shards, codebook replicated, results concatenated
+        all.assign(pointClouds.size(), {});
+        std::vector<std::map<std::string, double>> shard_times((size_t)n_gpus);
+        std::vector<int> ok((size_t)n_gpus, 1);
+        std::vector<std::string> errors((size_t)n_gpus);
+        std::vector<std::thread> workers;
+        const size_t n = pointClouds.size();
+        for (int g = 0; g < n_gpus; ++g) {
+          const size_t lo = n * (size_t)g / (size_t)n_gpus, hi = n * (size_t)(g + 1) / (size_t)n_gpus;
+          workers.emplace_back([&, g, lo, hi]() {
+            try {
+              if (hi <= lo) return;
+              ism3d::ImplicitShapeModel* model = &ism;
+              std::unique_ptr<ism3d::ImplicitShapeModel> own;
+              if (g > 0) {  // rank 0 reuses the model already loaded on the first device
+                own.reset(new ism3d::ImplicitShapeModel(device + g));
+                own->setLogging(false);
+                if (!own->readObject(ismFile)) { ok[(size_t)g] = 0; errors[(size_t)g] = "could not read " + ismFile; return; }
+                model = own.get();
+              }
+              std::vector<std::string> part(pointClouds.begin() + (long)lo, pointClouds.begin() + (long)hi);
+              std::vector<std::vector<ism3d::VotingMaximum>> res;
+              if (!model->detectBatch(part, res, shard_times[(size_t)g], batch)) { ok[(size_t)g] = 0; return; }
+              for (size_t i = 0; i < res.size(); ++i) all[lo + i] = std::move(res[i]);
+            } catch (const std::exception& e) {
+              ok[(size_t)g] = 0;
+              errors[(size_t)g] = e.what();
+            }
+          });
+        }
+        for (auto& w : workers) w.join();
+        for (int g = 0; g < n_gpus; ++g)
+          if (!ok[(size_t)g]) {
+            std::cerr << "classification failed on GPU " << device + g << ": " << errors[(size_t)g] << std::endl;
+            return 1;
+          }
+        // the stage buckets of the GPUs overlap in time: report the slowest shard per bucket
+        for (auto& st : shard_times)
+          for (auto& kv : st) times[kv.first] = std::max(times[kv.first], kv.second);
       }
       int numCorrectClasses = 0, numCorrectInstances = 0;
       std::map<unsigned, std::pair<unsigned, unsigned>> acc;

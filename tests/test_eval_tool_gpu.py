@@ -106,3 +106,38 @@ def test_eval_tool_on_clouds_without_normals(tmp_path):
     labels, _, _ = ctx.classify_batch(xt, None, rt, ot)
     assert got == labels.tolist()
     ctx.close()
+
+
+def test_eval_tool_multi_gpu(tmp_path):
+    """--gpus 2: the test list is sharded over two devices (one context and host thread each, no communication);
+    the summary must be identical to the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    tool = os.path.join(HOST, "eval_tool")
+    names = ["cat", "horse", "wolf"]
+    P = 1536
+    tr_cls = [c for c in range(3) for _ in range(2)]
+    te_cls = [i % 3 for i in range(7)]
+    sets = {"train": (synth.make_clouds(tr_cls, [400 + i for i in range(len(tr_cls))], P), tr_cls),
+            "test": (synth.make_clouds(te_cls, [600 + i for i in range(len(te_cls))], P), te_cls)}
+    for name, ((x, n, r, o), cls) in sets.items():
+        with open(tmp_path / (name + ".txt"), "w") as f:
+            f.write("# %s\n" % name)
+            for i, c in enumerate(cls):
+                p = str(tmp_path / ("%s_%d.pcd" % (name, i)))
+                pcd.write_pcd(p, x[o[i]:o[i + 1]], n[o[i]:o[i + 1]], r[o[i]:o[i + 1]])
+                f.write("%s %s\n" % (p, names[c]))
+    cfg = os.path.join(ROOT, "config", "c2_synthetic.ism")
+    model = str(tmp_path / "model.ism")
+    r = subprocess.run([tool, "-t", cfg, "-f", str(tmp_path / "train.txt"), "-o", model], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    outs = []
+    for extra, tag in (([], "one"), (["--gpus", "2"], "two")):
+        outdir = str(tmp_path / tag)
+        r = subprocess.run([tool, "-d", model, "-f", str(tmp_path / "test.txt"), "-o", outdir] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        summary = open(os.path.join(outdir, "summary.txt")).read()
+        outs.append(re.findall(r"file: (\S+), ground truth class: (\d+), classified class: (-?\d+)", summary))
+    assert outs[0] == outs[1] and len(outs[0]) == len(te_cls)
