@@ -488,6 +488,38 @@ def test_classify_batch_labels_identical(api, orc, small_world):
     c.close()
 
 
+@pytest.mark.parametrize("with_normals", [True, False])
+def test_classify_batch_degenerate_clouds(api, orc, small_world, with_normals):
+    """Ragged batch: a normal cloud, an empty one, one made of NaNs only, one with three points (no reference frame can be
+    built), another normal one.  Degenerate clouds yield no maximum and label -1 (eval_classification.cpp:412-417) and
+    must not disturb their neighbours in the batch; also through the estimated-normals path."""
+    w = small_world
+    xt, nt, rt, ot, _ = w["test"]
+    a0, a1 = slice(ot[0], ot[1]), slice(ot[3], ot[4])
+    nanc = np.full((5, 3), np.nan, np.float32)
+    tiny = np.array([[0, 0, 0], [0.01, 0, 0], [0, 0.01, 0]], np.float32)
+    up = np.tile(np.array([0, 0, 1], np.float32), (8, 1))
+    xs = np.concatenate([xt[a0], nanc, tiny, xt[a1]])
+    ns = np.concatenate([nt[a0], up[:5], up[:3], nt[a1]])
+    cs = np.concatenate([rt[a0], np.zeros(8, np.uint32), rt[a1]])
+    n0, n1 = ot[1] - ot[0], ot[4] - ot[3]
+    off = np.array([0, n0, n0, n0 + 5, n0 + 8, n0 + 8 + n1], np.int64)
+    prm = w["prm"].copy()
+    prm.normal_radius = 0.08
+    c = api.Context(prm, w["cb"])
+    m = orc.Model(prm, w["cb"])
+    nrm = ns if with_normals else None
+    la, mxa, offa = c.classify_batch(xs, nrm, cs, off)
+    lb, mxb, offb = m.classify_batch(xs, nrm, cs, off)
+    assert np.array_equal(la, lb) and np.array_equal(offa, offb)
+    assert la[1] == -1 and la[2] == -1 and la[3] == -1
+    assert np.array_equal(mxa["class_id"], mxb["class_id"]) and np.array_equal(mxa["n_votes"], mxb["n_votes"])
+    if with_normals:  # the well-formed clouds classify exactly as they do alone
+        solo, _, _ = c.classify_batch(xt[a0], nt[a0], rt[a0], [0, n0], want_maxima=False)
+        assert solo[0] == la[0]
+    c.close()
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
 def test_classify_batch_random_parameter_sets(api, orc, small_world, seed):
     """End-to-end label / maxima parity under randomly drawn option combinations (activation K and ratio test, the four
