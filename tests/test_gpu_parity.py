@@ -287,7 +287,8 @@ def test_knn_small_codebook_and_ratio(api, orc):
 
 
 # ---- K6: tcgen05 GEMM + exact re-rank -------------------------------------------------------------------------------
-@pytest.mark.parametrize("N,Qn,k", [(20000, 700, 1), (9000, 130, 4), (70000, 2000, 1), (150000, 5000, 2)])
+@pytest.mark.parametrize("N,Qn,k", [(20000, 700, 1), (9000, 130, 4), (70000, 2000, 1), (150000, 5000, 2),
+                                    (12000, 300, 7), (12000, 300, 16)])
 def test_knn_gemm_matches_exact_scan(api, orc, N, Qn, k):
     rng = np.random.default_rng(N + k)
     W = _shot_like(rng, N, 352)
