@@ -216,15 +216,17 @@ def test_shot_known_answer_on_gpu(ctx):
     assert len(nz) == 5 and np.allclose(d[nz], 1 / np.sqrt(5), atol=2e-6) and (nz % 11 == 10).all()
 
 
-def test_shot_multi_chunk_neighbourhood(ctx, orc):
-    """More neighbours than one shared-memory chunk: the staged-chunk loop must give the same result."""
+@pytest.mark.parametrize("ft", [FEATURE_SHOT, FEATURE_CSHOT])
+def test_shot_dense_neighbourhood(ctx, orc, ft):
+    """More points in the 27 cells than the shared-memory stage holds: the dense mode (one filter sweep from L2 into
+    per-warp global lists, passes by index) must give the same frames and descriptors, colour channel included."""
     xyz, nrm, rgb, off = synth.make_clouds([3], [41], 12000)
     kp, kr, koff = orc.voxel_keypoints(xyz, rgb, off, 0.25)
     lrf_a = ctx.shot_lrf(xyz, off, kp, koff, 0.5)
     lrf_b = orc.shot_lrf(xyz, off, kp, koff, 0.5)
     _compare_lrf(lrf_a, lrf_b)
-    a = ctx.shot_describe(FEATURE_SHOT, xyz, nrm, rgb, off, kp, kr, lrf_b, koff, 0.6)
-    b = orc.shot_describe(FEATURE_SHOT, xyz, nrm, rgb, off, kp, kr, lrf_b, koff, 0.6)
+    a = ctx.shot_describe(ft, xyz, nrm, rgb, off, kp, kr, lrf_b, koff, 0.6)
+    b = orc.shot_describe(ft, xyz, nrm, rgb, off, kp, kr, lrf_b, koff, 0.6)
     assert np.abs(a - b).max() < DESC_TOL
 
 
