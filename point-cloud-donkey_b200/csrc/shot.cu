@@ -54,6 +54,12 @@ struct ShotArgs {
   const float* lab_lut;
   const long long* item_beg;  // [items][9] first sorted-surface index of each of the nine cell runs of an item
   const int* item_len;        // [items][9] run lengths (precomputed by k_item_ranges: no serial searches in k_shot)
+  int dense;         // 0: staged launch (CTA per item, skips dense items); 1: dense launch (warp per keypoint)
+  int stage_cap;     // points the launch stages per item (kChunk), 0 for the dense launch (no staging arrays)
+  long long n_kp;    // keypoints of the batch (sorted positions the dense launch walks)
+  const int* item_id;    // exclusive scan of the item heads over the sorted keypoints
+  const int* item_head;
+  int* work_counter_dense;
   unsigned* glist;   // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of in-radius points
   long long gcap;    // entries per warp (>= the largest 27-cell population of the batch)
 };
@@ -169,44 +175,70 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   constexpr int D = COLOR ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_pts = reinterpret_cast<float4*>(smem_raw);
-  float4* s_nrm = s_pts + kChunk;
-  float4* s_lab = s_nrm + kChunk;  // only touched when COLOR
-  unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(float4) * kChunk * (COLOR ? 3 : 2));
+  float4* s_nrm = s_pts + a.stage_cap;
+  float4* s_lab = s_nrm + a.stage_cap;  // only touched when COLOR
+  unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(float4) * a.stage_cap * (COLOR ? 3 : 2));
   // per-warp compacted list of the staged points inside the current search radius (positions in the chunk)
   unsigned short* s_list = reinterpret_cast<unsigned short*>(s_hist + (size_t)kWarps * D);
-  __shared__ long long s_rbeg[9];
-  __shared__ int s_rlen[9];
+  __shared__ long long s_rbeg_all[kWarps][9];  // staged launch: row 0 is the CTA's item; dense launch: one row per warp
+  __shared__ int s_rlen_all[kWarps][9];
   __shared__ int s_pref[10];
   __shared__ int s_item;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = *a.n_items_ptr;
   unsigned* hist = s_hist + (size_t)warp * D;
-  unsigned short* list = s_list + (size_t)warp * kChunk;
+  unsigned short* list = s_list + (size_t)warp * a.stage_cap;
+  const bool dense_launch = a.dense != 0;
+  long long* s_rbeg = s_rbeg_all[dense_launch ? warp : 0];
+  int* s_rlen = s_rlen_all[dense_launch ? warp : 0];
   unsigned* glist = a.glist ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
 
   while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= n_items) break;
-    const int k0 = a.item_start[item], k1 = a.item_start[item + 1];
-    if (threadIdx.x < 9) {
-      s_rbeg[threadIdx.x] = a.item_beg[(size_t)item * 9 + threadIdx.x];
-      s_rlen[threadIdx.x] = a.item_len[(size_t)item * 9 + threadIdx.x];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int acc = 0;
-      for (int r = 0; r < 9; ++r) {
-        s_pref[r] = acc;
-        acc += s_rlen[r];
+    int k0, k1, T;
+    if (!dense_launch) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1);
+      __syncthreads();
+      const int item = s_item;
+      if (item >= n_items) break;
+      k0 = a.item_start[item];
+      k1 = a.item_start[item + 1];
+      if (threadIdx.x < 9) {
+        s_rbeg[threadIdx.x] = a.item_beg[(size_t)item * 9 + threadIdx.x];
+        s_rlen[threadIdx.x] = a.item_len[(size_t)item * 9 + threadIdx.x];
       }
-      s_pref[9] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int r = 0; r < 9; ++r) {
+          s_pref[r] = acc;
+          acc += s_rlen[r];
+        }
+        s_pref[9] = acc;
+      }
+      __syncthreads();
+      T = s_pref[9];
+      if (T > kChunk && a.glist) continue;  // dense neighbourhood: left to the dense launch (block-uniform)
+    } else {
+      // Dense launch: nothing is shared between the warps of a CTA, so every warp walks the sorted keypoints on its own
+      // (a cell of a dense cloud holds 2-3 keypoints: tying 8 warps to it left most of them waiting at a barrier)
+      int p = 0;
+      if (lane == 0) p = atomicAdd(a.work_counter_dense, 1);
+      p = __shfl_sync(0xffffffffu, p, 0);
+      if (p >= a.n_kp) break;
+      const int item = a.item_id[p] + a.item_head[p] - 1;
+      if (lane < 9) {
+        s_rbeg[lane] = a.item_beg[(size_t)item * 9 + lane];
+        s_rlen[lane] = a.item_len[(size_t)item * 9 + lane];
+      }
+      __syncwarp();
+      T = 0;
+      for (int r = 0; r < 9; ++r) T += s_rlen[r];
+      if (T <= kChunk) continue;  // staged launch's item (warp-uniform)
+      k0 = p;
+      k1 = p + 1;
     }
-    __syncthreads();
-    const int T = s_pref[9];
     const float fix_scale = exp2f(floorf(log2f(4294967296.0f / (4.0f * (float)T + 4.0f))));
     const float fix_inv = 1.0f / fix_scale;
     const bool multi = T > kChunk;  // dense neighbourhood: no staging, per-warp global lists (see below)
@@ -224,13 +256,16 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         if (COLOR) s_lab[e] = a.slabS[src];
       }
     };
-    if (!multi && T > 0) stage(0);
-    __syncthreads();
+    if (!dense_launch) {
+      if (!multi && T > 0) stage(0);
+      __syncthreads();
+    }
     const float r2_max = fmaxf(a.do_lrf ? a.r2_lrf : 0.f, a.do_desc ? a.r2_shot : 0.f);
 
+    const int warp_off = dense_launch ? 0 : warp;
     for (int round = k0; round < k1; round += kWarps) {
-      const bool have = round + warp < k1;
-      const int kidx = have ? a.kp_order[round + warp] : -1;
+      const bool have = round + warp_off < k1;
+      const int kidx = have ? a.kp_order[round + warp_off] : -1;
       float kx = 0.f, ky = 0.f, kz = 0.f;
       unsigned krgb = 0;
       if (have) {
@@ -625,11 +660,12 @@ __global__ void k_item_population(const int* __restrict__ item_len, const int* _
 
 }  // namespace
 
-size_t shot_smem_bytes(bool color) {
+static size_t shot_smem_for(bool color, int stage_cap) {
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
-  return sizeof(float4) * kChunk * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D +
-         sizeof(unsigned short) * (size_t)kWarps * kChunk;
+  return sizeof(float4) * (size_t)stage_cap * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D +
+         sizeof(unsigned short) * (size_t)kWarps * stage_cap;
 }
+size_t shot_smem_bytes(bool color) { return shot_smem_for(color, kChunk); }
 
 // Runs the fused LRF + descriptor kernel over the keypoint items prepared by stage_grid.
 // smallest float f with sqrt((double)f) > r (strict) or >= r: "sqrt((double)d2) > r"  <=>  d2 >= f for float d2
@@ -701,9 +737,17 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   PCDB_CUDA(cudaStreamSynchronize(st));
   a.glist = nullptr;
   a.gcap = 0;
+  a.dense = 0;
+  a.stage_cap = kChunk;
+  a.n_kp = Q;
+  a.item_id = w.item_id.as<int>();
+  a.item_head = w.item_head.as<int>();
+  a.work_counter_dense = w.scalars.as<int>() + 2;
+  // dense launch: no staging arrays, so more CTAs fit; every warp takes keypoints on its own
+  const int dense_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * (color ? 2 : 3), cdiv(Q, kWarps));
   if (h_pop > (unsigned long long)kChunk) {
     a.gcap = (long long)((h_pop + 31) & ~31ull);
-    const size_t bytes = sizeof(unsigned) * (size_t)a.gcap * (size_t)grid * kWarps;
+    const size_t bytes = sizeof(unsigned) * (size_t)a.gcap * (size_t)dense_grid * kWarps;
     if (bytes > (16ull << 30))
       return ctx->fail(PCDB_E_INVALID, "a 27-cell neighbourhood holds %llu points: radius too large for this cloud density",
                        h_pop);
@@ -718,6 +762,16 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
     k_shot<false><<<grid, kThreads, smem, st>>>(a);
   }
   PCDB_LAUNCH_CHECK();
+  if (a.glist) {  // the keypoints whose 27 cells do not fit the stage: second launch, warp per keypoint
+    a.dense = 1;
+    a.stage_cap = 0;
+    const size_t dsmem = shot_smem_for(color, 0);
+    if (color)
+      k_shot<true><<<dense_grid, kThreads, dsmem, st>>>(a);
+    else
+      k_shot<false><<<dense_grid, kThreads, dsmem, st>>>(a);
+    PCDB_LAUNCH_CHECK();
+  }
   return PCDB_OK;
 }
 
