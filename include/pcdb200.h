@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PCDB_ABI_VERSION 2
+#define PCDB_ABI_VERSION 3
 
 typedef enum pcdb_status {
   PCDB_OK = 0,
@@ -230,9 +230,36 @@ int pcdb_classify_batch(pcdb_ctx* ctx, const float* xyz, const float* normals, c
 int pcdb_classify_batch_d(pcdb_ctx* ctx, const float* xyz_d, const float* normals_d, const uint32_t* rgb_d,
                           const int64_t* cloud_off, int32_t B, int32_t* label_out_d);
 
-/* ---- multi-GPU: row-sharded codebook --------------------------------- */
-/* Per-query merge of per-shard top-k lists.  cand_* : S x Q x k (shard-major), global row ids;
- * result: Q x k ascending (distance, row).  Runs on the device of ctx; used after an all-gather. */
+/* ---- multi-GPU (one process or thread per GPU, NCCL over NVLink / NVSwitch) ------------------------------- */
+/* SURVEY 8(b) `pcdb_comm_init`, 8(e).  The reference has a single FLANN index in one address space
+ * (utils/flann_helper.cpp:21-70, searched at codebook/codebook.cpp:483-538) and one keypoint loop
+ * (implicit_shape_model.cpp:583-712); these entry points split either over the GPUs of a box.
+ * All calls below, and every pcdb_knn / pcdb_classify_batch(_d) on a context whose codebook is sharded or whose
+ * keypoints are sharded, are COLLECTIVE: every rank makes them, in the same order.  NCCL is bound at run time
+ * (libnccl.so.2); without it pcdb_comm_* return PCDB_E_COMM and everything else works. */
+#define PCDB_COMM_ID_BYTES 128
+/* ncclGetUniqueId: rank 0 calls it, the host program hands the 128 bytes to the other ranks (MPI, torch, a file). */
+int pcdb_comm_unique_id(void* id_out, int32_t bytes);
+int pcdb_comm_init(pcdb_ctx* ctx, int32_t rank, int32_t n_ranks, const void* unique_id); /* ncclCommInitRank on ctx's device */
+int pcdb_comm_destroy(pcdb_ctx* ctx);
+int pcdb_comm_info(pcdb_ctx* ctx, int32_t* rank_out, int32_t* n_ranks_out, int32_t* nccl_version_out);
+/* Row-sharded codebook (config C4): this rank holds descriptor rows [row_lo, row_hi) of the N_total x D matrix
+ * (`words` points at row row_lo) and the COMPLETE vote tables (all arrays as in pcdb_set_codebook, indexed by global
+ * row).  Afterwards pcdb_knn and pcdb_classify_batch(_d) take THIS RANK's queries / clouds and return their results as
+ * an unsharded codebook would, bit for bit: query all-gather, local tcgen05 search, one all-to-all of
+ * (f32 distance, i32 row) x K per query, device-side merge (ties -> lower row), votes cast by the query's owner. */
+int pcdb_set_codebook_sharded(pcdb_ctx* ctx, const float* words, int64_t row_lo, int64_t row_hi, int64_t N_total,
+                              int32_t D, const int64_t* vote_off, const float* vote_xyz, const float* vote_weight,
+                              const uint32_t* vote_class, const uint32_t* vote_instance, const float* vote_bbox,
+                              const float* vote_class_weight, const float* kp_train, const int32_t* codeword_ids,
+                              const float* codeword_weight, const float* class_sigma2, int32_t n_classes);
+/* Keypoint-sharded scene (config C5): when enabled, pcdb_classify_batch(_d) with B == 1 is collective over ranks that
+ * all pass the SAME scene and hold the same (replicated) codebook: rank r processes the r-th contiguous slice of the
+ * voxel-grid keypoints, the votes are all-gathered in keypoint order and every rank returns the full result. */
+int pcdb_comm_shard_keypoints(pcdb_ctx* ctx, int32_t enable);
+
+/* Per-query merge of per-shard top-k lists held in HOST memory (the device-resident exchange above does not
+ * need it).  cand_* : S x Q x k (shard-major), global row ids; result: Q x k ascending (distance, row). */
 int pcdb_merge_topk(pcdb_ctx* ctx, const int32_t* cand_idx, const float* cand_dist, int32_t S, int64_t Q,
                     int32_t k, int32_t* idx_out, float* dist_out);
 
@@ -242,7 +269,11 @@ typedef struct pcdb_stats {
   int64_t knn_queries, knn_candidates, knn_fallback_queries;
   int64_t kernel_launches;  /* launches of this library's own kernels since the last reset */
   /* device time of the last classify batch (CUDA events on the context's stream) */
-  double features_ms, knn_ms, knn_gemm_ms /* tcgen05 activation kernel alone */, votes_ms, maxima_ms;
+  double features_ms, knn_ms, knn_gemm_ms /* tcgen05 activation kernel(s) alone */, votes_ms, maxima_ms;
+  /* multi-GPU exchange steps: bytes this rank received over NVLink since the last reset; device time of the last
+   * batch's exchanges (query all-gather + top-k all-to-all + merge, or the vote all-gather) */
+  int64_t comm_bytes;
+  double comm_ms;
 } pcdb_stats;
 int pcdb_get_stats(pcdb_ctx* ctx, pcdb_stats* out);
 int pcdb_reset_stats(pcdb_ctx* ctx);

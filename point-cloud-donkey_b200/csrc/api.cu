@@ -25,6 +25,7 @@ int download(pcdb_ctx* ctx, void* host, const void* dev, size_t bytes) {
 
 int check_offsets(pcdb_ctx* ctx, const int64_t* off, int B, const char* what) {
   if (B < 0 || !off) return ctx->fail(PCDB_E_INVALID, "%s: bad batch", what);
+  if (B > 65535) return ctx->fail(PCDB_E_INVALID, "%s: at most 65535 clouds per batch (16-bit cloud field of the sort keys)", what);
   if (off[0] != 0) return ctx->fail(PCDB_E_INVALID, "%s: offsets must start at 0", what);
   for (int b = 0; b < B; ++b)
     if (off[b + 1] < off[b]) return ctx->fail(PCDB_E_INVALID, "%s: offsets must be non-decreasing", what);
@@ -284,21 +285,43 @@ int prepare_explicit(pcdb_ctx* ctx, const float* surf_xyz, const float* surf_nor
   return PCDB_OK;
 }
 
-// kNN dispatch: tcgen05 GEMM + exact re-rank for squared-L2 on large codebooks, exact scan otherwise
+// kNN dispatch: tcgen05 GEMM + exact re-rank on large codebooks (squared L2 directly, chi^2 through the Hellinger
+// sandwich), exact scan otherwise
 int run_knn(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,
             float ratio_thr) {
+  return pcdb_run_knn(ctx, queries_d, Q, k, dist_type, mode, use_ratio, ratio_thr);
+}
+
+// this rank's queries against the codebook, whichever way it is laid out over the GPUs
+int activate(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,
+             float ratio_thr) {
+  if (comm_codebook_sharded(ctx)) return stage_knn_sharded(ctx, queries_d, Q, k, dist_type, mode, use_ratio, ratio_thr);
+  if (Q == 0) return PCDB_OK;
+  return pcdb_run_knn(ctx, queries_d, Q, k, dist_type, mode, use_ratio, ratio_thr);
+}
+
+}  // namespace
+
+int pcdb_run_knn(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,
+                 float ratio_thr) {
+  const int fam = dist_type == PCDB_DIST_CHISQUARED ? 1 : 0;
+  const bool big = ctx->cb.N >= 8192 && ctx->cb.N > k + 1;
+  if ((mode == PCDB_KNN_GEMM || (mode == PCDB_KNN_AUTO && big)) && !ctx->cb.gemm_tried[fam])
+    PCDB_TRY(gemm_prepare_codebook(ctx, dist_type));  // the operand copy of this distance family, built on first use
   bool gemm = false;
   if (mode == PCDB_KNN_GEMM) {
-    if (dist_type != PCDB_DIST_EUCLIDEAN) return ctx->fail(PCDB_E_UNSUPPORTED, "the GEMM activation is squared-L2 only");
-    if (!gemm_supported(ctx)) return ctx->fail(PCDB_E_UNSUPPORTED, "GEMM activation unavailable for this codebook");
+    if (!gemm_supported(ctx, dist_type) || ctx->cb.N <= k + 1)
+      return ctx->fail(PCDB_E_UNSUPPORTED, "GEMM activation unavailable for this codebook");
     gemm = true;
   } else if (mode == PCDB_KNN_AUTO) {
-    gemm = dist_type == PCDB_DIST_EUCLIDEAN && gemm_supported(ctx) && ctx->cb.N >= 8192 && ctx->cb.N > k + 1;
+    gemm = gemm_supported(ctx, dist_type) && big;
   }
   ctx->stats.knn_queries += Q;
-  if (gemm) return stage_knn_gemm(ctx, queries_d, Q, k, use_ratio, ratio_thr);
+  if (gemm) return stage_knn_gemm(ctx, queries_d, Q, k, dist_type, use_ratio, ratio_thr);
   return stage_knn_scan(ctx, queries_d, Q, k, dist_type, use_ratio, ratio_thr);
 }
+
+namespace {
 
 // keypoints -> LRF -> SHOT/CSHOT -> drop invalid, all on the device; leaves feat_* in the workspace
 int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_out, int64_t* Q_out) {
@@ -326,6 +349,10 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   if (err[0] & 1)
     return ctx->fail(PCDB_E_INVALID, "Keypoints.LeafSize too small for the cloud extent (pcl::VoxelGrid index overflow)");
   if (err[0] & 2) return ctx->fail(PCDB_E_INVALID, "Features radius too small for the cloud extent");
+  if (comm_keypoints_sharded(ctx)) {  // one scene on several GPUs: this rank keeps its contiguous slice
+    if (B != 1) return ctx->fail(PCDB_E_UNSUPPORTED, "keypoint sharding handles one scene per call (B == 1)");
+    PCDB_TRY(stage_slice_keypoints(ctx, B, Q, &Q));
+  }
   ctx->stats.n_keypoints += Q;
   *Q_out = Q;
   PCDB_CUDA(w.feat_off.ensure(sizeof(long long) * (B + 1)));
@@ -393,6 +420,89 @@ int fetch_maxima(pcdb_ctx* ctx, int B, int64_t M, pcdb_maximum* maxima_out, int6
     if (maxima_off_out) maxima_off_out[b + 1] = total;
   }
   ctx->stats.n_maxima += total;
+  return PCDB_OK;
+}
+
+
+// Validates everything first, uploads, and only then commits N / D / V: a failed call leaves the context WITHOUT a
+// codebook (cb.N == 0), never with stale sizes over unallocated buffers.
+// words: rows [word_lo, word_lo + n_words) of the table; the vote tables (CSR over N_table rows) are complete.
+int set_codebook_impl(pcdb_ctx* ctx, const float* words, int64_t n_words, int64_t N_table, int64_t word_lo, int32_t D,
+                      const int64_t* vote_off, const float* vote_xyz, const float* vote_weight,
+                      const uint32_t* vote_class, const uint32_t* vote_instance, const float* vote_bbox,
+                      const float* vote_class_weight, const float* kp_train, const int32_t* codeword_ids,
+                      const float* codeword_weight, const float* class_sigma2, int32_t n_classes, int64_t row_base) {
+  Codebook_d& cb = ctx->cb;
+  cb.gemm_ready[0] = cb.gemm_ready[1] = cb.gemm_tried[0] = cb.gemm_tried[1] = false;
+  cb.N = 0;  // no codebook until every check and upload below has succeeded
+  cb.V = 0;
+  cb.N_table = 0;
+  if (n_words < 0 || N_table < 0 || D <= 0 || n_classes <= 0) return ctx->fail(PCDB_E_INVALID, "bad codebook sizes");
+  if (N_table > 0x7fffff00ll || row_base < 0 || row_base + N_table > 0x7fffff00ll)
+    return ctx->fail(PCDB_E_INVALID, "codebook too large for 32-bit row ids");
+  if (word_lo < 0 || word_lo + n_words > N_table) return ctx->fail(PCDB_E_INVALID, "word rows outside the vote table");
+  if (!class_sigma2) return ctx->fail(PCDB_E_INVALID, "class_sigma2 is required");
+  if (N_table > 0 && (!vote_off || !kp_train)) return ctx->fail(PCDB_E_INVALID, "vote_off and kp_train are required");
+  if (n_words > 0 && !words) return ctx->fail(PCDB_E_INVALID, "words is required");
+  int64_t V = 0;
+  int mv = 0;
+  if (N_table > 0) {
+    if (vote_off[0] != 0) return ctx->fail(PCDB_E_INVALID, "vote_off must start at 0");
+    for (int64_t i = 0; i < N_table; ++i) {
+      const int64_t n = vote_off[i + 1] - vote_off[i];
+      if (n < 0) return ctx->fail(PCDB_E_INVALID, "vote_off must be non-decreasing (row %lld)", (long long)i);
+      if (n > 0x7fffffff) return ctx->fail(PCDB_E_INVALID, "too many votes on codeword %lld", (long long)i);
+      mv = std::max<int64_t>(mv, n);
+    }
+    V = vote_off[N_table];
+  }
+  if (V > 0x7fffff00ll) return ctx->fail(PCDB_E_INVALID, "more than 2^31 stored votes");
+  if (V > 0 && (!vote_xyz || !vote_weight || !vote_class || !vote_instance || !vote_bbox))
+    return ctx->fail(PCDB_E_INVALID, "the per-vote arrays are required when the table holds votes");
+  for (int64_t i = 0; i < V; ++i)
+    if (vote_class[i] >= (uint32_t)n_classes)
+      return ctx->fail(PCDB_E_INVALID, "vote %lld has class id %u >= n_classes %d", (long long)i, vote_class[i], n_classes);
+  PCDB_CUDA(cudaSetDevice(ctx->device));
+  PCDB_TRY(upload(ctx, cb.words, words, sizeof(float) * (size_t)n_words * D));
+  PCDB_TRY(upload(ctx, cb.vote_off, vote_off, sizeof(int64_t) * (N_table + 1)));
+  PCDB_TRY(upload(ctx, cb.vote_xyz, vote_xyz, sizeof(float) * 3 * V));
+  PCDB_TRY(upload(ctx, cb.vote_weight, vote_weight, sizeof(float) * V));
+  PCDB_TRY(upload(ctx, cb.vote_class, vote_class, sizeof(uint32_t) * V));
+  PCDB_TRY(upload(ctx, cb.vote_instance, vote_instance, sizeof(uint32_t) * V));
+  PCDB_TRY(upload(ctx, cb.vote_bbox, vote_bbox, sizeof(float) * 7 * V));
+  if (vote_class_weight)
+    PCDB_TRY(upload(ctx, cb.vote_class_weight, vote_class_weight, sizeof(float) * V));
+  else
+    cb.vote_class_weight.release();
+  PCDB_TRY(upload(ctx, cb.kp_train, kp_train, sizeof(float) * 3 * N_table));
+  if (codeword_ids)
+    PCDB_TRY(upload(ctx, cb.ids, codeword_ids, sizeof(int32_t) * N_table));
+  else
+    cb.ids.release();
+  std::vector<float> ones;
+  if (!codeword_weight) {
+    ones.assign((size_t)std::max<int64_t>(N_table, 1), 1.0f);
+    codeword_weight = ones.data();
+  }
+  PCDB_TRY(upload(ctx, cb.cw_weight, codeword_weight, sizeof(float) * N_table));
+  PCDB_TRY(upload(ctx, cb.sigma2, class_sigma2, sizeof(float) * n_classes));
+  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  // commit
+  cb.N = n_words;
+  cb.N_table = N_table;
+  cb.word_lo = word_lo;
+  cb.D = D;
+  cb.V = V;
+  cb.n_classes = n_classes;
+  cb.row_base = row_base;
+  cb.max_votes_per_word = mv;
+  if (n_words > 0) {
+    int rc = gemm_prepare_codebook(ctx, ctx->prm.distance_type);
+    if (rc != PCDB_OK) {
+      cb.N = 0;
+      return rc;
+    }
+  }
   return PCDB_OK;
 }
 
@@ -485,6 +595,7 @@ void pcdb_destroy(pcdb_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->ws.release();
   ctx->cb.release();
+  pcdb_comm_destroy(ctx);
   if (ctx->gemm_state && ctx->gemm_state_free) ctx->gemm_state_free(ctx->gemm_state);
   if (ctx->lab_lut_d) cudaFree(ctx->lab_lut_d);
   for (int i = 0; i < 8; ++i)
@@ -515,50 +626,21 @@ int pcdb_set_codebook(pcdb_ctx* ctx, const float* words, int64_t N, int32_t D, c
                       const float* kp_train, const int32_t* codeword_ids, const float* codeword_weight,
                       const float* class_sigma2, int32_t n_classes, int64_t row_base) {
   if (!ctx) return PCDB_E_INVALID;
-  if (N < 0 || D <= 0 || n_classes <= 0 || (N > 0 && (!words || !vote_off)))
-    return ctx->fail(PCDB_E_INVALID, "bad codebook arguments");
-  if (N > 0x7fffff00ll) return ctx->fail(PCDB_E_INVALID, "codebook shard too large for 32-bit row ids");
-  PCDB_CUDA(cudaSetDevice(ctx->device));
-  Codebook_d& cb = ctx->cb;
-  cb.gemm_ready = false;
-  cb.N = N;
-  cb.D = D;
-  cb.n_classes = n_classes;
-  cb.row_base = row_base;
-  const int64_t V = N > 0 ? vote_off[N] : 0;
-  cb.V = V;
-  for (int64_t i = 0; i < V; ++i)
-    if (vote_class[i] >= (uint32_t)n_classes)
-      return ctx->fail(PCDB_E_INVALID, "vote %lld has class id %u >= n_classes %d", (long long)i, vote_class[i], n_classes);
-  int mv = 0;
-  for (int64_t i = 0; i < N; ++i) mv = std::max<int64_t>(mv, vote_off[i + 1] - vote_off[i]);
-  cb.max_votes_per_word = mv;
-  PCDB_TRY(upload(ctx, cb.words, words, sizeof(float) * (size_t)N * D));
-  PCDB_TRY(upload(ctx, cb.vote_off, vote_off, sizeof(int64_t) * (N + 1)));
-  PCDB_TRY(upload(ctx, cb.vote_xyz, vote_xyz, sizeof(float) * 3 * V));
-  PCDB_TRY(upload(ctx, cb.vote_weight, vote_weight, sizeof(float) * V));
-  PCDB_TRY(upload(ctx, cb.vote_class, vote_class, sizeof(uint32_t) * V));
-  PCDB_TRY(upload(ctx, cb.vote_instance, vote_instance, sizeof(uint32_t) * V));
-  PCDB_TRY(upload(ctx, cb.vote_bbox, vote_bbox, sizeof(float) * 7 * V));
-  if (vote_class_weight)
-    PCDB_TRY(upload(ctx, cb.vote_class_weight, vote_class_weight, sizeof(float) * V));
-  else
-    cb.vote_class_weight.release();
-  PCDB_TRY(upload(ctx, cb.kp_train, kp_train, sizeof(float) * 3 * N));
-  if (codeword_ids)
-    PCDB_TRY(upload(ctx, cb.ids, codeword_ids, sizeof(int32_t) * N));
-  else
-    cb.ids.release();
-  std::vector<float> ones;
-  if (!codeword_weight) {
-    ones.assign((size_t)std::max<int64_t>(N, 1), 1.0f);
-    codeword_weight = ones.data();
-  }
-  PCDB_TRY(upload(ctx, cb.cw_weight, codeword_weight, sizeof(float) * N));
-  PCDB_TRY(upload(ctx, cb.sigma2, class_sigma2, sizeof(float) * n_classes));
-  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (N > 0) PCDB_TRY(gemm_prepare_codebook(ctx));
-  return PCDB_OK;
+  return set_codebook_impl(ctx, words, N, N, 0, D, vote_off, vote_xyz, vote_weight, vote_class, vote_instance, vote_bbox,
+                           vote_class_weight, kp_train, codeword_ids, codeword_weight, class_sigma2, n_classes, row_base);
+}
+
+int pcdb_set_codebook_sharded(pcdb_ctx* ctx, const float* words, int64_t row_lo, int64_t row_hi, int64_t N_total,
+                              int32_t D, const int64_t* vote_off, const float* vote_xyz, const float* vote_weight,
+                              const uint32_t* vote_class, const uint32_t* vote_instance, const float* vote_bbox,
+                              const float* vote_class_weight, const float* kp_train, const int32_t* codeword_ids,
+                              const float* codeword_weight, const float* class_sigma2, int32_t n_classes) {
+  if (!ctx) return PCDB_E_INVALID;
+  if (!comm_active(ctx)) return ctx->fail(PCDB_E_STATE, "pcdb_set_codebook_sharded before pcdb_comm_init");
+  if (row_lo < 0 || row_hi < row_lo || row_hi > N_total) return ctx->fail(PCDB_E_INVALID, "bad row shard");
+  return set_codebook_impl(ctx, words, row_hi - row_lo, N_total, row_lo, D, vote_off, vote_xyz, vote_weight, vote_class,
+                           vote_instance, vote_bbox, vote_class_weight, kp_train, codeword_ids, codeword_weight,
+                           class_sigma2, n_classes, 0);
 }
 
 int pcdb_voxel_keypoints(pcdb_ctx* ctx, const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B,
@@ -740,19 +822,22 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
              int32_t* idx_out, float* dist_out, int32_t* count_out) {
   if (!ctx) return PCDB_E_INVALID;
   PCDB_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->cb.N == 0) return ctx->fail(PCDB_E_STATE, "pcdb_knn before pcdb_set_codebook");
+  if (ctx->cb.N_table == 0) return ctx->fail(PCDB_E_STATE, "pcdb_knn before pcdb_set_codebook");
   if (k < 1 || k > PCDB_MAX_K) return ctx->fail(PCDB_E_INVALID, "k must be in 1..%d", PCDB_MAX_K);
   if (dist_type != PCDB_DIST_EUCLIDEAN && dist_type != PCDB_DIST_CHISQUARED)
     return ctx->fail(PCDB_E_INVALID, "invalid distance type %d", dist_type);
   if (Q < 0) return ctx->fail(PCDB_E_INVALID, "negative query count");
   Workspace& w = ctx->ws;
   PCDB_TRY(upload(ctx, w.feat_desc, queries, sizeof(float) * (size_t)ctx->cb.D * Q));
-  PCDB_TRY(run_knn(ctx, w.feat_desc.as<float>(), Q, k, dist_type, mode, ctx->prm.use_distance_ratio != 0,
-                   ctx->prm.distance_ratio_threshold));
+  ctx->comm_events_valid = false;
+  PCDB_TRY(activate(ctx, w.feat_desc.as<float>(), Q, k, dist_type, mode, ctx->prm.use_distance_ratio != 0,
+                    ctx->prm.distance_ratio_threshold));
+  ctx->stats.comm_ms = 0;
   PCDB_TRY(download(ctx, idx_out, w.knn_idx.p, sizeof(int) * Q * k));
   PCDB_TRY(download(ctx, dist_out, w.knn_dist.p, sizeof(float) * Q * k));
   PCDB_TRY(download(ctx, count_out, w.knn_cnt.p, sizeof(int) * Q));
   PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.comm_ms = comm_last_exchange_ms(ctx);
   return PCDB_OK;
 }
 
@@ -778,7 +863,7 @@ int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9
                     pcdb_vote* votes_out, int64_t* vote_off_out, int64_t vote_capacity) {
   if (!ctx) return PCDB_E_INVALID;
   PCDB_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->cb.N == 0) return ctx->fail(PCDB_E_STATE, "pcdb_cast_votes before pcdb_set_codebook");
+  if (ctx->cb.N_table == 0) return ctx->fail(PCDB_E_STATE, "pcdb_cast_votes before pcdb_set_codebook");
   PCDB_TRY(check_offsets(ctx, feat_off, B, "feat_off"));
   if (k < 1 || k > PCDB_MAX_K) return ctx->fail(PCDB_E_INVALID, "k must be in 1..%d", PCDB_MAX_K);
   Workspace& w = ctx->ws;
@@ -788,7 +873,7 @@ int pcdb_cast_votes(pcdb_ctx* ctx, const float* feat_xyz, const float* feat_lrf9
     for (int j = 0; j < knn_count[i] && j < k; ++j) {
       if (knn_idx[i * k + j] < 0) continue;  // masked: the row lives in another codebook shard
       int64_t r = (int64_t)knn_idx[i * k + j] - ctx->cb.row_base;
-      if (r < 0 || r >= ctx->cb.N) return ctx->fail(PCDB_E_INVALID, "activated row %d outside this codebook shard", knn_idx[i * k + j]);
+      if (r < 0 || r >= ctx->cb.N_table) return ctx->fail(PCDB_E_INVALID, "activated row %d outside this codebook shard", knn_idx[i * k + j]);
     }
   PCDB_TRY(upload(ctx, w.feat_xyz, feat_xyz, sizeof(float) * 3 * F));
   PCDB_TRY(upload(ctx, w.feat_lrf, feat_lrf9, sizeof(float) * 9 * F));
@@ -872,6 +957,7 @@ static void record_stage_times(pcdb_ctx* ctx, const float t[4]) {
     float g = 0;
     if (cudaEventElapsedTime(&g, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->stats.knn_gemm_ms = g;
   }
+  ctx->stats.comm_ms = comm_last_exchange_ms(ctx);
 }
 
 // device-resident core of detect(): inputs already in ws.in_* / ws.cloud_off
@@ -879,23 +965,38 @@ static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, bool has
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const pcdb_params& p = ctx->prm;
-  if (ctx->cb.N == 0) return ctx->fail(PCDB_E_STATE, "classify before pcdb_set_codebook");
+  if (ctx->cb.N_table == 0) return ctx->fail(PCDB_E_STATE, "classify before pcdb_set_codebook");
+  if (comm_codebook_sharded(ctx) && comm_keypoints_sharded(ctx))
+    return ctx->fail(PCDB_E_UNSUPPORTED, "a sharded codebook and sharded keypoints cannot be combined");
   const int D = p.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   if (ctx->cb.D != D) return ctx->fail(PCDB_E_INVALID, "codebook dimension %d does not match Features.Type (%d)", ctx->cb.D, D);
   ctx->gemm_events_valid = false;
   PCDB_CUDA(cudaEventRecord(ctx->ev[7], st));
+  if (B == 0) {  // nothing of this rank's own to classify; a sharded codebook still needs its rows searched
+    for (int i = 0; i < 2; ++i) PCDB_CUDA(cudaEventRecord(ctx->ev[i], st));
+    ctx->comm_events_valid = false;
+    if (comm_codebook_sharded(ctx))
+      PCDB_TRY(activate(ctx, nullptr, 0, p.knn_k, p.distance_type, PCDB_KNN_AUTO, p.use_distance_ratio != 0,
+                        p.distance_ratio_threshold));
+    for (int i = 2; i < 5; ++i) PCDB_CUDA(cudaEventRecord(ctx->ev[i], st));
+    ctx->last_V = ctx->last_M = ctx->last_members = 0;
+    ctx->last_B = 0;
+    *M_out = 0;
+    return PCDB_OK;
+  }
   if (!has_normals) PCDB_TRY(stage_normals(ctx, B, P, nullptr));  // "normals" bucket of the reference's timing table
   PCDB_CUDA(cudaEventRecord(ctx->ev[0], st));
   int64_t F = 0, Q = 0;
   PCDB_TRY(features_pipeline(ctx, B, P, has_rgb, &F, &Q));
   PCDB_CUDA(cudaEventRecord(ctx->ev[1], st));
-  if (F > 0)
-    PCDB_TRY(run_knn(ctx, w.feat_desc.as<float>(), F, p.knn_k, p.distance_type, PCDB_KNN_AUTO,
-                     p.use_distance_ratio != 0, p.distance_ratio_threshold));
+  ctx->comm_events_valid = false;
+  PCDB_TRY(activate(ctx, w.feat_desc.as<float>(), F, p.knn_k, p.distance_type, PCDB_KNN_AUTO,
+                    p.use_distance_ratio != 0, p.distance_ratio_threshold));
   PCDB_CUDA(cudaEventRecord(ctx->ev[2], st));
   int64_t V = 0;
   PCDB_TRY(stage_cast_votes(ctx, w.feat_xyz.as<float>(), w.feat_lrf.as<float>(), w.feat_off.as<long long>(),
                             w.feat_cloud.as<int>(), B, F, p.knn_k, &V));
+  if (comm_keypoints_sharded(ctx)) PCDB_TRY(stage_gather_votes(ctx, B, V, &V));
   PCDB_CUDA(cudaEventRecord(ctx->ev[3], st));
   int64_t M = 0, members = 0;
   PCDB_TRY(stage_find_maxima(ctx, B, V, &M, &members));

@@ -54,20 +54,22 @@ struct CloudInfo {
 };
 
 struct Codebook_d {
-  int64_t N = 0, V = 0, row_base = 0;
+  // Rows: the vote tables (CSR) cover N_table codewords; the descriptor rows held on this device are table rows
+  // [word_lo, word_lo + N).  Unsharded: word_lo = 0, N = N_table.  Row ids leaving the kNN kernels are
+  // row_base + word_lo + local row ("global" ids); vote casting maps id - row_base to a table row.
+  int64_t N = 0, V = 0, row_base = 0, N_table = 0, word_lo = 0;
   int D = 0, n_classes = 0;
-  int Dh = 0;              // padded fp16 row length (multiple of 32)
-  float cmax_norm = 0;     // max ||c||
-  float cmax_err = 0;      // max ||c - fp16(c)||
-  DevBuf words, words_h, cnorm, vote_off, vote_xyz, vote_weight, vote_class, vote_instance, vote_bbox,
+  DevBuf words, vote_off, vote_xyz, vote_weight, vote_class, vote_instance, vote_bbox,
       vote_class_weight, kp_train, ids, cw_weight, sigma2;
   int max_votes_per_word = 0;
-  bool gemm_ready = false;
+  // tensor-core operands (knn_gemm.cu owns the buffers): [0] squared-L2 rows, [1] sqrt rows for the chi^2 sandwich
+  bool gemm_ready[2] = {false, false};
+  bool gemm_tried[2] = {false, false};
   void release() {
-    DevBuf* all[] = {&words, &words_h, &cnorm, &vote_off, &vote_xyz, &vote_weight, &vote_class, &vote_instance,
+    DevBuf* all[] = {&words, &vote_off, &vote_xyz, &vote_weight, &vote_class, &vote_instance,
                      &vote_bbox, &vote_class_weight, &kp_train, &ids, &cw_weight, &sigma2};
     for (DevBuf* b : all) b->release();
-    N = V = 0;
+    N = V = N_table = 0;
   }
 };
 
@@ -121,6 +123,10 @@ struct pcdb_ctx {
   float grid_inv_cell = 0.f;  // 1 / search-grid cell edge of the current batch
   void* gemm_state = nullptr;            // knn_gemm.cu's per-context buffers / tensor map (opaque here)
   void (*gemm_state_free)(void*) = nullptr;
+  void* comm_state = nullptr;            // comm.cu's NCCL communicator and exchange buffers (opaque here)
+  void (*comm_state_free)(void*) = nullptr;
+  cudaEvent_t ev_comm[4] = {nullptr, nullptr, nullptr, nullptr};  // brackets of the last exchange steps
+  bool comm_events_valid = false;
   float* lab_lut_d = nullptr;  // 256 + 4000 floats, built on the host with powf (features_cshot.cpp:52-71)
   // host mirrors of the last batch (for pcdb_get_votes / pcdb_get_maximum_votes)
   int64_t last_V = 0, last_M = 0, last_members = 0;

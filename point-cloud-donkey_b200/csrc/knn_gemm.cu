@@ -44,6 +44,7 @@
 // per-query norms are computed in the query-prep kernel, codebook maxima at upload time.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -225,7 +226,25 @@ struct GemmArgs {
   int* cand_cnt;         // [2][Q], appended with atomics (zeroed before the launch)
   float* bound;          // [Q] running upper bound on the k-th best approximate distance (+inf before the launch)
   int2* stage;           // [CTAs][EPI_THREADS][CAND_CAP] private staging lists of the epilogue threads
+  // POOL variant (second pass of the chi^2 sandwich): `margin` holds a FIXED per-query threshold on the accumulator
+  // (-inf = skip the query) and every column at or below it is appended to one global pool of (query, row) pairs
+  int2* pool_rc;         // (row, accumulator bits)
+  int* pool_q;
+  unsigned long long* pool_count;  // entries wanted so far (may run past pool_cap: the host grows the pool and re-runs)
+  long long pool_cap;
+  int* q_cnt;            // [Q] pool entries per query (for the CSR the re-rank works on)
 };
+
+// moves a thread's staged candidates into the global pool: one returning atomic per flush
+__device__ __forceinline__ void pool_flush(const GemmArgs& g, long long row, const int2* stage, int cnt) {
+  const unsigned long long pos = atomicAdd(g.pool_count, (unsigned long long)cnt);
+  atomicAdd(g.q_cnt + row, cnt);
+  for (int i = 0; i < cnt; ++i)
+    if ((long long)(pos + i) < g.pool_cap) {
+      g.pool_rc[pos + i] = stage[i];
+      g.pool_q[pos + i] = (int)row;
+    }
+}
 
 struct __align__(16) Barriers {
   float cn[2][BN];  // streaming-query variant only: |c|^2 of the tile in each accumulator buffer
@@ -233,7 +252,7 @@ struct __align__(16) Barriers {
   unsigned tmem_base;
 };
 
-template <bool A_RES, int KT>
+template <bool A_RES, int KT, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -379,13 +398,13 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       const int t0 = split * g.tiles_per_split, t1 = min(g.n_ntiles, t0 + g.tiles_per_split);
       const long long row = (long long)(mp * 2 + (int)rank) * BM + grp * 32 + lane;
       const bool active = row < g.Q;
-      const float margin = active ? g.margin[row] : 0.f;
+      const float margin = active ? g.margin[row] : (POOL ? __int_as_float(0xff800000) : 0.f);
       float best[KT];
 #pragma unroll
       for (int i = 0; i < KT; ++i) best[i] = __int_as_float(0x7f800000);
       // bound carried over from the slices already swept for this query (any stale value is still an upper bound)
-      const float gb = active ? __ldcg(g.bound + row) : __int_as_float(0x7f800000);
-      float thr = gb + margin;
+      const float gb = (active && !POOL) ? __ldcg(g.bound + row) : __int_as_float(0x7f800000);
+      float thr = POOL ? margin : gb + margin;
       // Candidates of this unit are staged in a list private to this thread (plain stores, local counter) and moved
       // to the query's shared list at the end of the unit with ONE atomic reservation: a returning global atomic per
       // append put a ~1 us round trip into the filter loop (C4: 1724 -> 1412 TFLOP/s).
@@ -435,15 +454,23 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                             \
         const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c */                               \
         if (d <= thr && active && n_base + e < g.N) {                                              \
-          if (cnt < CAND_CAP) stage[cnt] = make_int2(n_base + e, __float_as_int(d));               \
-          ++cnt;                                                                                   \
-          float x = d;                                                                             \
-          _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                         \
-            float lo = fminf(best[i], x);                                                          \
-            x = fmaxf(best[i], x);                                                                 \
-            best[i] = lo;                                                                          \
+          if (POOL) {                                                                              \
+            stage[cnt] = make_int2(n_base + e, __float_as_int(d));                                 \
+            if (++cnt == CAND_CAP) {                                                               \
+              pool_flush(g, row, stage, cnt);                                                      \
+              cnt = 0;                                                                             \
+            }                                                                                      \
+          } else {                                                                                 \
+            if (cnt < CAND_CAP) stage[cnt] = make_int2(n_base + e, __float_as_int(d));             \
+            ++cnt;                                                                                 \
+            float x = d;                                                                           \
+            _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                       \
+              float lo = fminf(best[i], x);                                                        \
+              x = fmaxf(best[i], x);                                                               \
+              best[i] = lo;                                                                        \
+            }                                                                                      \
+            thr = fminf(best[KT - 1], gb) + margin;                                                \
           }                                                                                        \
-          thr = fminf(best[KT - 1], gb) + margin;                                                  \
         }                                                                                          \
       }                                                                                            \
     }                                                                                              \
@@ -466,7 +493,9 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           acc_phase ^= 1;
         }
       }
-      if (active && cnt > 0) {
+      if (POOL) {
+        if (active && cnt > 0) pool_flush(g, row, stage, cnt);
+      } else if (active && cnt > 0) {
         if (best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
         // a staging list that overflowed, or a shared list above its capacity, marks the query for the exact-scan
         // fallback (the count is pushed past any capacity)
@@ -492,16 +521,23 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 // One warp per row: the fp16 operand row of the augmented GEMM (pitch D + K_AUG), |row|^2 (double accumulate),
 // |fp16(row)|, |row - fp16(row)|.  CODEBOOK rows are stored as [-2 fp16(c), hi, lo, 0 x 14] with hi + lo = |c|^2 split
 // into two halves; query rows as [fp16(q), 1, 1, 0 x 14]: the accumulator of the GEMM is |c|^2 - 2 qh.ch.
-template <bool CODEBOOK>
+// SQRT: the row is sqrt-transformed first (chi^2 sandwich, see stage_knn_gemm): everything above then refers to the
+// fp32 vector s = fl(sqrt(x)); rows with a negative or non-finite entry are flagged (the sandwich needs x >= 0).
+template <bool CODEBOOK, bool SQRT>
 __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int aug, __half* xh, float* norm2,
-                            float* norm, float* err) {
+                            float* norm, float* err, int* row_bad, int* any_bad) {
   const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= n) return;
   const int Dh = D + (aug ? K_AUG : 0);  // aug == 0: plain fp16 copy (streaming-query variant)
   double s2 = 0, e2 = 0, h2 = 0;
+  bool bad = false;
   for (int j = lane; j < D; j += 32) {
     float v = x[r * D + j];
+    if (SQRT) {
+      bad |= !(v >= 0.f) || !(v < __int_as_float(0x7f800000));
+      v = __fsqrt_rn(fmaxf(v, 0.f));
+    }
     __half h = __float2half_rn(v);
     float hv = __half2float(h);
     xh[r * Dh + j] = (CODEBOOK && aug) ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
@@ -513,6 +549,13 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int
   s2 = warp_sum(s2);
   e2 = warp_sum(e2);
   h2 = warp_sum(h2);
+  if (SQRT) {
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      if (row_bad) row_bad[r] = bad ? 1 : 0;
+      if (bad && any_bad) atomicOr(any_bad, 1);
+    }
+  }
   if (aug && lane < K_AUG) {
     __half a = __float2half_rn(0.f);
     if (CODEBOOK) {
@@ -551,9 +594,11 @@ __global__ void k_max2(const float* __restrict__ a, const float* __restrict__ b,
   }
 }
 
-// margin[q] = 2 * eps_d(q); eps_d bounds |accumulator - (|c|^2 - 2 q.c)|
+// margin[q] = 2 * eps_d(q); eps_d bounds |accumulator - (|c|^2 - 2 q.c)|.  eps_out (optional) receives eps_d itself,
+// in the chi^2 sandwich enlarged by the rounding of the fp32 square roots (the bound then holds against the
+// real-arithmetic Hellinger form sum (sqrt(q_i) - sqrt(c_i))^2 - sum q_i).
 __global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restrict__ qerr, long long Q, int D, int aug,
-                         float cmax_h, float cerr_max, float cmax2, float* margin) {
+                         float cmax_h, float cerr_max, float cmax2, int sqrt_rows, float* margin, float* eps_out) {
   long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= Q) return;
   // |q.c - fl(qh.ch)| <= |q-qh||c| + |qh||c-ch| + accumulation error; |c| <= |ch| + |c-ch|
@@ -568,7 +613,14 @@ __global__ void k_margin(const float* __restrict__ qnorm_h, const float* __restr
   if (!aug)  // epilogue-side |c|^2: fp32 dot accumulation + one fmaf with a correctly rounded |c|^2
     eps_d = 2.0 * (eps_dot + (double)D * p22 * (double)qnorm_h[q] * (double)cmax_h) +
             2.0 * 5.9604644775390625e-08 /* 2^-24 */ * ((double)cmax2 + 2.0);
+  if (sqrt_rows) {
+    // s = fl(sqrt(x)) is within 2^-24 relative of the real root: | |s - t|^2 - H^2 | <= 2 H eta + eta^2 with
+    // eta = 2^-24 (|s| + |t|) and H <= |s| + |t|
+    double st = (double)qnorm_h[q] + (double)qerr[q] + cmax;
+    eps_d += 1.25 * p22 * 0.5 * st * st;
+  }
   margin[q] = (float)(2.0 * eps_d * 1.0001);
+  if (eps_out) eps_out[q] = (float)(eps_d * 1.0001);
 }
 
 __global__ void k_fill_f32(float* a, long long n, float v) {
@@ -584,13 +636,16 @@ __global__ void k_final_thr(const float* __restrict__ bound, const float* __rest
   thr[Q + q] = t;
 }
 
-// queries whose candidate list overflowed in some split -> exact-scan fallback list
-__global__ void k_overflow_flags(const int* __restrict__ cand_cnt, int S, long long Q, int cap, int* flag) {
+// queries whose candidate list overflowed in some split, or (chi^2) that hold a negative entry -> exact-scan fallback
+__global__ void k_overflow_flags(const int* __restrict__ cand_cnt, int S, long long Q, int cap,
+                                 const int* __restrict__ row_bad, int* flag) {
   long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q > Q) return;
   int f = 0;
-  if (q < Q)
+  if (q < Q) {
     for (int s = 0; s < S; ++s) f |= cand_cnt[(size_t)s * Q + q] > cap;
+    if (row_bad) f |= row_bad[q];
+  }
   flag[q] = f;
 }
 __global__ void k_overflow_gather(const int* __restrict__ flag, const int* __restrict__ pos, long long Q, int D,
@@ -613,6 +668,27 @@ __global__ void k_overflow_scatter(const int* __restrict__ list, int n, int k, c
     dist_out[(size_t)q * k + j] = dist[(size_t)i * k + j];
   }
   cnt_out[q] = cnt[i];
+}
+
+// Chi^2 sandwich, threshold of the second pass.  For non-negative rows  H^2 <= chi^2 <= 2 H^2  with
+// H^2 = sum (sqrt(a_i) - sqrt(b_i))^2  (term by term: (a-b)^2/(a+b) = (sqrt a - sqrt b)^2 (1 + 2 sqrt(ab)/(a+b))).
+// U = the K-th smallest FLANN-order chi^2 over ANY K codewords bounds the K-th smallest overall; a row of the true top
+// K therefore has  H^2 <= chi^2_real <= chi^2_fl / (1 - g) <= U (1 + 1.01 g)  with g = (D + 8) 2^-24 bounding the
+// rounding of the functor's D sequential non-negative fp32 terms, and its accumulator value (H^2 - sum q_i, known to
+// within eps) is at most  U (1 + 1.01 g) - qn + eps.
+__global__ void k_chi_thr(const float* __restrict__ part_d, int K, const float* __restrict__ qn2,
+                          const float* __restrict__ eps, const int* __restrict__ skip, long long Q, int D, float* thr) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  if (skip[q]) {
+    thr[q] = __int_as_float(0xff800000);
+    return;
+  }
+  const double g = 1.01 * (double)(D + 8) * 5.9604644775390625e-08;
+  const double t = (double)part_d[q * K + K - 1] * (1.0 + g) - (double)qn2[q] * (1.0 - 2.4e-7) + (double)eps[q] + 1e-12;
+  float f = (float)t;
+  if ((double)f < t) f = __uint_as_float(__float_as_uint(f) + (f >= 0.f ? 1u : -1u));  // round up
+  thr[q] = f;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -645,15 +721,31 @@ int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, in
   return PCDB_OK;
 }
 
-struct GemmState {
+// codebook-side operand of one distance family: [0] the rows themselves (squared L2), [1] their square roots (chi^2)
+struct GemmOperand {
   CUtensorMap map_b;
-  DevBuf cnorm_h, cerr, qnorm_h, qerr, margin, bound, stage, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  DevBuf words_h, cnorm, cnorm_h, cerr;
   float cmax_h = 0, cerr_max = 0, cmax2 = 0;
+  void release() {
+    DevBuf* all[] = {&words_h, &cnorm, &cnorm_h, &cerr};
+    for (DevBuf* b : all) b->release();
+  }
+};
+
+struct GemmState {
+  GemmOperand op[2];
+  DevBuf qnorm_h, qerr, qn2, qbad, margin, eps, bound, stage, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  // chi^2 second pass: pooled candidates and their CSR by query
+  DevBuf thr2, pool_rc, pool_q, q_cnt, q_off, q_fill, csr_row, csr_q, csr_d;
+  int64_t pool_cap = 0;
   int max_clusters[2] = {0, 0};  // co-resident CTA pairs of the streaming / resident-query kernel on this device
   ~GemmState() {
-    DevBuf* all[] = {&cnorm_h, &cerr, &qnorm_h, &qerr, &margin, &bound, &stage, &fb_q, &fb_flag, &fb_pos, &fb_idx, &fb_dist, &fb_cnt,
-                     &fb_list};
+    DevBuf* all[] = {&qnorm_h, &qerr, &qn2, &qbad, &margin, &eps, &bound, &stage, &fb_q, &fb_flag, &fb_pos, &fb_idx,
+                     &fb_dist, &fb_cnt, &fb_list, &thr2, &pool_rc, &pool_q, &q_cnt, &q_off, &q_fill, &csr_row, &csr_q,
+                     &csr_d};
     for (DevBuf* b : all) b->release();
+    op[0].release();
+    op[1].release();
   }
 };
 // owned by the context (freed by pcdb_destroy through gemm_state_free)
@@ -665,14 +757,14 @@ GemmState* state_of(pcdb_ctx* ctx) {
   return static_cast<GemmState*>(ctx->gemm_state);
 }
 
-template <bool A_RES, int KT>
+template <bool A_RES, int KT, bool POOL>
 int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, int grid) {
   const size_t smem = (A_RES ? KB_RES_MAX * A_BOX_BYTES : 0) +
                       (size_t)(A_RES ? 7 : 6) * (B_BOX_BYTES + (A_RES ? 0 : A_BOX_BYTES)) + sizeof(Barriers) + 64;
   // co-resident CTA pairs: GPCs with an odd number of usable SMs leave one SM without a partner, and a pair that
   // cannot be resident from the start would run after the others and double the sweep time
-  PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int& max_clusters = state_of(ctx)->max_clusters[A_RES ? 1 : 0];  // same footprint for every KT
+  PCDB_CUDA(cudaFuncSetAttribute(k_knn_gemm<A_RES, KT, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int& max_clusters = state_of(ctx)->max_clusters[A_RES ? 1 : 0];  // same footprint for every KT / POOL
   if (max_clusters == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
@@ -686,12 +778,12 @@ int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    PCDB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_knn_gemm<A_RES, KT>, &cfg));
+    PCDB_CUDA(cudaOccupancyMaxActiveClusters(&n, k_knn_gemm<A_RES, KT, POOL>, &cfg));
     if (n < 1) return ctx->fail(PCDB_E_CUDA, "no CTA pair of k_knn_gemm can be resident on this device");
     max_clusters = n;
   }
   grid = 2 * std::min(grid / 2, max_clusters);
-  k_knn_gemm<A_RES, KT><<<grid, THREADS, smem, ctx->stream>>>(map_a, map_b, g);
+  k_knn_gemm<A_RES, KT, POOL><<<grid, THREADS, smem, ctx->stream>>>(map_a, map_b, g);
   PCDB_LAUNCH_CHECK();
   return PCDB_OK;
 }
@@ -699,63 +791,87 @@ int launch_gemm(pcdb_ctx* ctx, const CUtensorMap& map_a, const CUtensorMap& map_
 template <bool A_RES>
 int launch_gemm_kt(pcdb_ctx* ctx, int K, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g,
                    int grid) {
-  if (K <= 1) return launch_gemm<A_RES, 1>(ctx, map_a, map_b, g, grid);
-  if (K <= 2) return launch_gemm<A_RES, 2>(ctx, map_a, map_b, g, grid);
-  if (K <= 4) return launch_gemm<A_RES, 4>(ctx, map_a, map_b, g, grid);
-  if (K <= 8) return launch_gemm<A_RES, 8>(ctx, map_a, map_b, g, grid);
-  return launch_gemm<A_RES, 17>(ctx, map_a, map_b, g, grid);
+  if (K <= 1) return launch_gemm<A_RES, 1, false>(ctx, map_a, map_b, g, grid);
+  if (K <= 2) return launch_gemm<A_RES, 2, false>(ctx, map_a, map_b, g, grid);
+  if (K <= 4) return launch_gemm<A_RES, 4, false>(ctx, map_a, map_b, g, grid);
+  if (K <= 8) return launch_gemm<A_RES, 8, false>(ctx, map_a, map_b, g, grid);
+  return launch_gemm<A_RES, 17, false>(ctx, map_a, map_b, g, grid);
 }
 
 }  // namespace
 
-bool gemm_supported(const pcdb_ctx* ctx) { return ctx->cb.gemm_ready; }
+bool gemm_supported(const pcdb_ctx* ctx, int dist_type) { return ctx->cb.gemm_ready[dist_type == PCDB_DIST_CHISQUARED]; }
 
-// fp16 copy of the codebook, |c|^2, error maxima and the codebook-side tensor map (called by pcdb_set_codebook)
-int gemm_prepare_codebook(pcdb_ctx* ctx) {
+// fp16 operand copy of the codebook for one distance family (the rows, or their square roots for chi^2), |c|^2, error
+// maxima and the codebook-side tensor map.  Called by pcdb_set_codebook for the context's DistanceType and lazily by the
+// first search that uses the other one.
+int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
   Codebook_d& cb = ctx->cb;
   cudaStream_t st = ctx->stream;
-  cb.gemm_ready = false;
+  const int fam = dist_type == PCDB_DIST_CHISQUARED ? 1 : 0;
+  cb.gemm_ready[fam] = false;
+  cb.gemm_tried[fam] = true;
   if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
   const int aug = (cb.D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;  // resident-query variant <=> augmented operands
   const int Dh = cb.D + (aug ? K_AUG : 0);
   GemmState* gs = state_of(ctx);
+  GemmOperand& op = gs->op[fam];
   const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
-  PCDB_CUDA(cb.words_h.ensure(sizeof(__half) * (size_t)cb.N * Dh + 256));
-  PCDB_CUDA(cb.cnorm.ensure(sizeof(float) * (n_pad + 4)));
-  PCDB_CUDA(gs->cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
-  PCDB_CUDA(gs->cerr.ensure(sizeof(float) * (cb.N + 1)));
+  PCDB_CUDA(op.words_h.ensure(sizeof(__half) * (size_t)cb.N * Dh + 256));
+  PCDB_CUDA(op.cnorm.ensure(sizeof(float) * (n_pad + 4)));
+  PCDB_CUDA(op.cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
+  PCDB_CUDA(op.cerr.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(ctx->ws.scalars.ensure(256));
-  k_prep_rows<true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(cb.words.as<float>(), cb.N, cb.D, aug, cb.words_h.as<__half>(),
-                                                    cb.cnorm.as<float>(), gs->cnorm_h.as<float>(),
-                                                    gs->cerr.as<float>());
+  unsigned* mx = reinterpret_cast<unsigned*>(ctx->ws.scalars.as<char>() + 128);
+  PCDB_CUDA(cudaMemsetAsync(mx, 0, 32, st));
+  if (fam)
+    k_prep_rows<true, true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(
+        cb.words.as<float>(), cb.N, cb.D, aug, op.words_h.as<__half>(), op.cnorm.as<float>(), op.cnorm_h.as<float>(),
+        op.cerr.as<float>(), nullptr, reinterpret_cast<int*>(mx + 4));
+  else
+    k_prep_rows<true, false><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(
+        cb.words.as<float>(), cb.N, cb.D, aug, op.words_h.as<__half>(), op.cnorm.as<float>(), op.cnorm_h.as<float>(),
+        op.cerr.as<float>(), nullptr, nullptr);
   PCDB_LAUNCH_CHECK();
   if (n_pad > cb.N) {
-    k_pad_inf<<<cdiv(n_pad - cb.N, 256), 256, 0, st>>>(cb.cnorm.as<float>(), cb.N, n_pad);
+    k_pad_inf<<<cdiv(n_pad - cb.N, 256), 256, 0, st>>>(op.cnorm.as<float>(), cb.N, n_pad);
     PCDB_LAUNCH_CHECK();
   }
-  unsigned* mx = reinterpret_cast<unsigned*>(ctx->ws.scalars.as<char>() + 128);
-  PCDB_CUDA(cudaMemsetAsync(mx, 0, 16, st));
-  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(gs->cnorm_h.as<float>(), gs->cerr.as<float>(), cb.N, mx);
+  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(op.cnorm_h.as<float>(), op.cerr.as<float>(), cb.N, mx);
   PCDB_LAUNCH_CHECK();
-  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(cb.cnorm.as<float>(), cb.cnorm.as<float>(), cb.N, mx + 2);
+  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(op.cnorm.as<float>(), op.cnorm.as<float>(), cb.N, mx + 2);
   PCDB_LAUNCH_CHECK();
-  float h[4];
-  PCDB_CUDA(cudaMemcpyAsync(h, mx, 16, cudaMemcpyDeviceToHost, st));
+  float h[8];
+  PCDB_CUDA(cudaMemcpyAsync(h, mx, 32, cudaMemcpyDeviceToHost, st));
   PCDB_CUDA(cudaStreamSynchronize(st));
-  gs->cmax_h = h[0];
-  gs->cerr_max = h[1];
-  gs->cmax2 = h[2];
-  if (!std::isfinite(h[0]) || !std::isfinite(h[2])) return PCDB_OK;  // non-finite codewords: scan path only
-  PCDB_TRY(make_map(ctx, &gs->map_b, cb.words_h.p, cb.N, Dh, BN_HALF));
-  cb.gemm_ready = true;
+  op.cmax_h = h[0];
+  op.cerr_max = h[1];
+  op.cmax2 = h[2];
+  int any_bad = 0;
+  std::memcpy(&any_bad, &h[4], sizeof(int));
+  if (!std::isfinite(h[0]) || !std::isfinite(h[2]) || any_bad) {
+    op.release();  // non-finite codewords, or negative entries under chi^2: scan path only
+    return PCDB_OK;
+  }
+  PCDB_TRY(make_map(ctx, &op.map_b, op.words_h.p, cb.N, Dh, BN_HALF));
+  cb.gemm_ready[fam] = true;
   return PCDB_OK;
 }
 
-int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool use_ratio, float ratio_thr) {
+// Exact kNN on the tensor cores.
+//   Euclidean: one sweep with the running-bound filter, exact fp32 re-rank of the candidates.
+//   ChiSquared: the Hellinger sandwich, two sweeps over the sqrt-transformed operands.  Sweep 1 is the Euclidean
+//   machinery on sqrt rows (its candidates, re-ranked with the exact chi^2 functor, give U = the K-th smallest chi^2
+//   of K real codewords); sweep 2 collects EVERY row whose Hellinger value can still be <= U into a pooled list, and
+//   the exact FLANN-order chi^2 of those rows decides.  The result is the exact scan's, bit for bit.
+int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
+                   float ratio_thr) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const Codebook_d& cb = ctx->cb;
   GemmState* gs = state_of(ctx);
+  const bool chi = dist_type == PCDB_DIST_CHISQUARED;
+  GemmOperand& op = gs->op[chi ? 1 : 0];
   PCDB_CUDA(w.knn_idx.ensure(sizeof(int) * (Q * k + 1)));
   PCDB_CUDA(w.knn_dist.ensure(sizeof(float) * (Q * k + 1)));
   PCDB_CUDA(w.knn_cnt.ensure(sizeof(int) * (Q + 1)));
@@ -769,15 +885,27 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   PCDB_CUDA(gs->qnorm_h.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->qerr.ensure(sizeof(float) * (Q + 1)));
   PCDB_CUDA(gs->margin.ensure(sizeof(float) * (Q + 1)));
-  k_prep_rows<false><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, aug, w.feat_h.as<__half>(), nullptr,
-                                                 gs->qnorm_h.as<float>(), gs->qerr.as<float>());
+  if (chi) {
+    PCDB_CUDA(gs->qn2.ensure(sizeof(float) * (Q + 1)));
+    PCDB_CUDA(gs->qbad.ensure(sizeof(int) * (Q + 1)));
+    PCDB_CUDA(gs->eps.ensure(sizeof(float) * (Q + 1)));
+    k_prep_rows<false, true><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, aug, w.feat_h.as<__half>(),
+                                                               gs->qn2.as<float>(), gs->qnorm_h.as<float>(),
+                                                               gs->qerr.as<float>(), gs->qbad.as<int>(), nullptr);
+  } else {
+    k_prep_rows<false, false><<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, aug, w.feat_h.as<__half>(), nullptr,
+                                                                gs->qnorm_h.as<float>(), gs->qerr.as<float>(), nullptr,
+                                                                nullptr);
+  }
   PCDB_LAUNCH_CHECK();
-  k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, aug, gs->cmax_h,
-                                         gs->cerr_max, gs->cmax2, gs->margin.as<float>());
+  k_margin<<<cdiv(Q, 256), 256, 0, st>>>(gs->qnorm_h.as<float>(), gs->qerr.as<float>(), Q, D, aug, op.cmax_h,
+                                         op.cerr_max, op.cmax2, chi ? 1 : 0, gs->margin.as<float>(),
+                                         chi ? gs->eps.as<float>() : nullptr);
   PCDB_LAUNCH_CHECK();
   CUtensorMap map_a;
   PCDB_TRY(make_map(ctx, &map_a, w.feat_h.p, Q, Dh, BM));
   GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
   g.Q = Q;
   g.N = cb.N;
   g.D = Dh;
@@ -802,7 +930,7 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
   g.n_splits = S;
   g.margin = gs->margin.as<float>();
-  g.cnorm = cb.cnorm.as<float>();
+  g.cnorm = op.cnorm.as<float>();
   const int S2 = 2;  // candidate lists: one per column half, shared by all slices
   // Slices of one query tile run one after the other when there are more tile pairs than CTA pairs; with few queries
   // they run side by side, each starting from an empty bound and contributing its own descending staircase
@@ -829,26 +957,77 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
   PCDB_CUDA(cudaEventRecord(e0, st));
   if (a_res)
-    PCDB_TRY((launch_gemm_kt<true>(ctx, K, map_a, gs->map_b, g, grid)));
+    PCDB_TRY((launch_gemm_kt<true>(ctx, K, map_a, op.map_b, g, grid)));
   else
-    PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, gs->map_b, g, grid)));
-  PCDB_CUDA(cudaEventRecord(e1, st));
-  ctx->gemm_events_valid = true;
+    PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, op.map_b, g, grid)));
+  if (!chi) {
+    PCDB_CUDA(cudaEventRecord(e1, st));
+    ctx->gemm_events_valid = true;
+  }
   k_final_thr<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, g.margin, Q, w.cand_thr.as<float>());
   PCDB_LAUNCH_CHECK();
-  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, k, K, S2, g.cand_cap, use_ratio, ratio_thr));
-  // overflow fallback: exact scan of the affected queries (still on the GPU)
+  // exact functor values of the candidates, the K best per query -> ws.knn_part_*
+  PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, K, S2, g.cand_cap, dist_type));
+  // queries that need the exact scan instead: an overflowed candidate list (or, chi^2, a negative entry)
   PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
   PCDB_CUDA(gs->fb_pos.ensure(sizeof(int) * (Q + 2)));
-  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, g.cand_cap, gs->fb_flag.as<int>());
+  k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, g.cand_cap,
+                                                     chi ? gs->qbad.as<int>() : nullptr, gs->fb_flag.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
+
+  if (chi) {
+    // ---- sweep 2: every row whose Hellinger value can still be <= U, pooled
+    PCDB_CUDA(gs->thr2.ensure(sizeof(float) * (Q + 1)));
+    k_chi_thr<<<cdiv(Q, 256), 256, 0, st>>>(w.knn_part_d.as<float>(), K, gs->qn2.as<float>(), gs->eps.as<float>(),
+                                            gs->fb_flag.as<int>(), Q, D, gs->thr2.as<float>());
+    PCDB_LAUNCH_CHECK();
+    PCDB_CUDA(gs->q_cnt.ensure(sizeof(int) * (Q + 2)));
+    PCDB_CUDA(gs->q_off.ensure(sizeof(int) * (Q + 2)));
+    PCDB_CUDA(gs->q_fill.ensure(sizeof(int) * (Q + 2)));
+    unsigned long long* pool_count = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 72);
+    GemmArgs g2 = g;
+    g2.margin = gs->thr2.as<float>();
+    g2.pool_count = pool_count;
+    g2.q_cnt = gs->q_cnt.as<int>();
+    unsigned long long total = 0;
+    for (int attempt = 0;; ++attempt) {
+      const int64_t want = std::max<int64_t>(gs->pool_cap, std::max<int64_t>((int64_t)1 << 22, Q * 64));
+      PCDB_CUDA(gs->pool_rc.ensure(sizeof(int2) * (size_t)want));
+      PCDB_CUDA(gs->pool_q.ensure(sizeof(int) * (size_t)want));
+      gs->pool_cap = want;
+      g2.pool_rc = gs->pool_rc.as<int2>();
+      g2.pool_q = gs->pool_q.as<int>();
+      g2.pool_cap = want;
+      PCDB_CUDA(cudaMemsetAsync(pool_count, 0, 8, st));
+      PCDB_CUDA(cudaMemsetAsync(gs->q_cnt.p, 0, sizeof(int) * (Q + 1), st));
+      if (a_res)
+        PCDB_TRY((launch_gemm<true, 1, true>(ctx, map_a, op.map_b, g2, grid)));
+      else
+        PCDB_TRY((launch_gemm<false, 1, true>(ctx, map_a, op.map_b, g2, grid)));
+      PCDB_CUDA(cudaMemcpyAsync(&total, pool_count, 8, cudaMemcpyDeviceToHost, st));
+      PCDB_CUDA(cudaStreamSynchronize(st));
+      if ((int64_t)total <= gs->pool_cap) break;
+      if (attempt >= 2 || total > 0x7fff0000ull)
+        return ctx->fail(PCDB_E_CAPACITY, "chi^2 candidate pool: %llu entries for %lld queries", total, (long long)Q);
+      gs->pool_cap = (int64_t)(total + total / 4);  // grow and sweep again (first batches of a new workload only)
+    }
+    PCDB_CUDA(cudaEventRecord(e1, st));
+    ctx->gemm_events_valid = true;
+    ctx->stats.knn_candidates += (int64_t)total;
+    PCDB_TRY(stage_knn_chi_pool(ctx, queries_d, Q, K, (int64_t)total, gs->pool_rc.as<int2>(), gs->pool_q.as<int>(),
+                                gs->q_cnt.as<int>(), gs->q_off.as<int>(), gs->q_fill.as<int>(), &gs->csr_row,
+                                &gs->csr_q, &gs->csr_d));
+  }
+  PCDB_TRY(stage_knn_finish(ctx, Q, k, K, use_ratio, ratio_thr));
+
+  // overflow fallback: exact scan of the affected queries (still on the GPU)
   int n_fb = 0;
   unsigned long long n_eval = 0;
   PCDB_CUDA(cudaMemcpyAsync(&n_fb, gs->fb_pos.as<int>() + Q, sizeof(int), cudaMemcpyDeviceToHost, st));
   PCDB_CUDA(cudaMemcpyAsync(&n_eval, w.scalars.as<char>() + 64, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
   PCDB_CUDA(cudaStreamSynchronize(st));
-  ctx->stats.knn_candidates += (int64_t)n_eval;
+  if (!chi) ctx->stats.knn_candidates += (int64_t)n_eval;
   ctx->stats.knn_fallback_queries += n_fb;
   if (n_fb > 0) {
     PCDB_CUDA(gs->fb_q.ensure(sizeof(float) * (size_t)n_fb * D));
@@ -863,7 +1042,7 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool
     PCDB_CUDA(cudaMemcpyAsync(gs->fb_idx.p, w.knn_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
     PCDB_CUDA(cudaMemcpyAsync(gs->fb_dist.p, w.knn_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
     PCDB_CUDA(cudaMemcpyAsync(gs->fb_cnt.p, w.knn_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
-    PCDB_TRY(stage_knn_scan(ctx, gs->fb_q.as<float>(), n_fb, k, PCDB_DIST_EUCLIDEAN, use_ratio, ratio_thr));
+    PCDB_TRY(stage_knn_scan(ctx, gs->fb_q.as<float>(), n_fb, k, dist_type, use_ratio, ratio_thr));
     k_overflow_scatter<<<cdiv(n_fb, 128), 128, 0, st>>>(gs->fb_list.as<int>(), n_fb, k, w.knn_idx.as<int>(),
                                                         w.knn_dist.as<float>(), w.knn_cnt.as<int>(),
                                                         gs->fb_idx.as<int>(), gs->fb_dist.as<float>(),

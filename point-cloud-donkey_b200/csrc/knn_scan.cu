@@ -352,6 +352,72 @@ __global__ void k_pair_dist(const float* __restrict__ a, const float* __restrict
   out[i] = acc;
 }
 
+// ---- chi^2 sandwich, pooled second pass -------------------------------------------------------------------------
+__global__ void k_pool_scatter(const int2* __restrict__ pool_rc, const int* __restrict__ pool_q, long long n,
+                               const int* __restrict__ q_off, int* q_fill, int* csr_row, int* csr_q) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int q = pool_q[e];
+  const int p = q_off[q] + atomicAdd(q_fill + q, 1);
+  csr_row[p] = pool_rc[e].x;
+  csr_q[p] = q;
+}
+__global__ void __launch_bounds__(128) k_chi_eval(const float* __restrict__ queries, const float* __restrict__ words,
+                                                  int D, long long n, const int* __restrict__ csr_row,
+                                                  const int* __restrict__ csr_q, float* csr_d) {
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  csr_d[e] = exact_pair<PCDB_DIST_CHISQUARED>(queries + (long long)csr_q[e] * D, words + (long long)csr_row[e] * D, D);
+}
+// one warp per query: K successive minima over (distance, row); the order inside a CSR segment is arbitrary
+__global__ void k_chi_select(long long Q, int K, const int* __restrict__ q_off, const int* __restrict__ csr_row,
+                             const float* __restrict__ csr_d, float* part_d, int* part_i) {
+  const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  const int beg = q_off[q], end = q_off[q + 1];
+  float last_d = -1.f;
+  int last_i = -1;
+  for (int j = 0; j < K; ++j) {
+    float bd = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int c = beg + lane; c < end; c += 32) {
+      const float d = csr_d[c];
+      const int idx = csr_row[c];
+      if (!(d < __int_as_float(0x7f800000))) continue;
+      if (!cand_less(last_d, last_i, d, idx)) continue;  // already emitted
+      if (cand_less(d, idx, bd, bi)) {
+        bd = d;
+        bi = idx;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float od = __shfl_xor_sync(0xffffffffu, bd, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (cand_less(od, oi, bd, bi)) {
+        bd = od;
+        bi = oi;
+      }
+    }
+    const bool ok = bi != 0x7fffffff;
+    if (lane == 0) {
+      part_d[q * K + j] = ok ? bd : __int_as_float(0x7f800000);
+      part_i[q * K + j] = ok ? bi : -1;
+    }
+    last_d = bd;
+    last_i = bi;
+    if (!ok) {
+      for (int jj = j + 1; jj < K; ++jj)
+        if (lane == 0) {
+          part_d[q * K + jj] = __int_as_float(0x7f800000);
+          part_i[q * K + jj] = -1;
+        }
+      break;
+    }
+  }
+}
+
 }  // namespace
 
 int stage_pair_distances(pcdb_ctx* ctx, const float* a_d, const float* b_d, int64_t n, int D, int dist_type,
@@ -380,12 +446,12 @@ int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   if (cb.N <= k) {
     if (dist_type == PCDB_DIST_CHISQUARED)
       k_all_rows<PCDB_DIST_CHISQUARED><<<cdiv(Q * k, 128), 128, 0, st>>>(queries_d, Q, cb.words.as<float>(),
-                                                                         (int)cb.N, cb.D, k, cb.row_base,
+                                                                         (int)cb.N, cb.D, k, cb.row_base + cb.word_lo,
                                                                          w.knn_idx.as<int>(), w.knn_dist.as<float>(),
                                                                          w.knn_cnt.as<int>());
     else
       k_all_rows<PCDB_DIST_EUCLIDEAN><<<cdiv(Q * k, 128), 128, 0, st>>>(queries_d, Q, cb.words.as<float>(),
-                                                                        (int)cb.N, cb.D, k, cb.row_base,
+                                                                        (int)cb.N, cb.D, k, cb.row_base + cb.word_lo,
                                                                         w.knn_idx.as<int>(), w.knn_dist.as<float>(),
                                                                         w.knn_cnt.as<int>());
     PCDB_LAUNCH_CHECK();
@@ -413,15 +479,14 @@ int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
                                                           w.knn_part_i.as<int>());
   PCDB_LAUNCH_CHECK();
   k_knn_merge<<<cdiv(Q, 128), 128, 0, st>>>(w.knn_part_d.as<float>(), w.knn_part_i.as<int>(), S, Q, K, k,
-                                            use_ratio ? 1 : 0, ratio_thr, cb.row_base, w.knn_idx.as<int>(),
+                                            use_ratio ? 1 : 0, ratio_thr, cb.row_base + cb.word_lo, w.knn_idx.as<int>(),
                                             w.knn_dist.as<float>(), w.knn_cnt.as<int>());
   PCDB_LAUNCH_CHECK();
   return PCDB_OK;
 }
 
-// Exact re-rank of the GEMM candidate lists (see knn_gemm.cu) followed by the same merge epilogue.
-int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int K, int S, int cap, bool use_ratio,
-                     float ratio_thr) {
+// Exact re-rank of the GEMM candidate lists (see knn_gemm.cu): the K best per query by the exact functor -> ws.knn_part_*.
+int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int S, int cap, int dist_type) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const Codebook_d& cb = ctx->cb;
@@ -429,16 +494,65 @@ int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, in
   PCDB_CUDA(w.knn_part_i.ensure(sizeof(int) * (Q * K + 1)));
   PCDB_CUDA(w.cand_exact.ensure(sizeof(float) * ((int64_t)Q * S * cap + 1)));
   const size_t smem = sizeof(float) * 8 * cb.D;
-  PCDB_CUDA(cudaFuncSetAttribute(k_rerank<PCDB_DIST_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-  k_rerank<PCDB_DIST_EUCLIDEAN><<<cdiv(Q, 8), 256, smem, st>>>(
-      queries_d, Q, cb.words.as<float>(), cb.D, S, cap, w.cand_idx.as<int>(), w.cand_apx.as<float>(),
-      w.cand_cnt.as<int>(), w.cand_thr.as<float>(), K, w.cand_exact.as<float>(), w.knn_part_d.as<float>(),
-      w.knn_part_i.as<int>(), reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 64));
+  unsigned long long* n_eval = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 64);
+  if (dist_type == PCDB_DIST_CHISQUARED) {
+    PCDB_CUDA(cudaFuncSetAttribute(k_rerank<PCDB_DIST_CHISQUARED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    k_rerank<PCDB_DIST_CHISQUARED><<<cdiv(Q, 8), 256, smem, st>>>(
+        queries_d, Q, cb.words.as<float>(), cb.D, S, cap, w.cand_idx.as<int>(), w.cand_apx.as<float>(),
+        w.cand_cnt.as<int>(), w.cand_thr.as<float>(), K, w.cand_exact.as<float>(), w.knn_part_d.as<float>(),
+        w.knn_part_i.as<int>(), n_eval);
+  } else {
+    PCDB_CUDA(cudaFuncSetAttribute(k_rerank<PCDB_DIST_EUCLIDEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    k_rerank<PCDB_DIST_EUCLIDEAN><<<cdiv(Q, 8), 256, smem, st>>>(
+        queries_d, Q, cb.words.as<float>(), cb.D, S, cap, w.cand_idx.as<int>(), w.cand_apx.as<float>(),
+        w.cand_cnt.as<int>(), w.cand_thr.as<float>(), K, w.cand_exact.as<float>(), w.knn_part_d.as<float>(),
+        w.knn_part_i.as<int>(), n_eval);
+  }
   PCDB_LAUNCH_CHECK();
-  k_knn_merge<<<cdiv(Q, 128), 128, 0, st>>>(w.knn_part_d.as<float>(), w.knn_part_i.as<int>(), 1, Q, K, k,
-                                            use_ratio ? 1 : 0, ratio_thr, cb.row_base, w.knn_idx.as<int>(),
-                                            w.knn_dist.as<float>(), w.knn_cnt.as<int>());
+  return PCDB_OK;
+}
+
+// ws.knn_part_* (one ascending list of K per query) -> ws.knn_idx / knn_dist / knn_cnt with the N<=k and ratio-test
+// semantics of activateKNN and global row ids
+int stage_knn_finish(pcdb_ctx* ctx, int64_t Q, int k, int K, bool use_ratio, float ratio_thr) {
+  Workspace& w = ctx->ws;
+  const Codebook_d& cb = ctx->cb;
+  k_knn_merge<<<cdiv(Q, 128), 128, 0, ctx->stream>>>(w.knn_part_d.as<float>(), w.knn_part_i.as<int>(), 1, Q, K, k,
+                                                     use_ratio ? 1 : 0, ratio_thr, cb.row_base + cb.word_lo,
+                                                     w.knn_idx.as<int>(), w.knn_dist.as<float>(), w.knn_cnt.as<int>());
+  PCDB_LAUNCH_CHECK();
+  return PCDB_OK;
+}
+
+// Second half of the chi^2 sandwich (knn_gemm.cu): the pooled (query, row) pairs of the second sweep are grouped by
+// query (count -> scan -> scatter), every pair gets the exact FLANN-order chi^2 (one thread per pair, a flat and
+// therefore balanced launch: a query with 10^4 survivors costs what 10^4 queries with one survivor cost), and one warp
+// per query picks its K best by (distance, row).
+int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, const int2* pool_rc,
+                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_q,
+                       DevBuf* csr_d) {
+  Workspace& w = ctx->ws;
+  cudaStream_t st = ctx->stream;
+  const Codebook_d& cb = ctx->cb;
+  PCDB_CUDA(w.knn_part_d.ensure(sizeof(float) * (Q * K + 1)));
+  PCDB_CUDA(w.knn_part_i.ensure(sizeof(int) * (Q * K + 1)));
+  PCDB_CUDA(csr_row->ensure(sizeof(int) * (size_t)(total + 1)));
+  PCDB_CUDA(csr_q->ensure(sizeof(int) * (size_t)(total + 1)));
+  PCDB_CUDA(csr_d->ensure(sizeof(float) * (size_t)(total + 1)));
+  PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, q_cnt, q_off, Q + 1));
+  PCDB_CUDA(cudaMemsetAsync(q_fill, 0, sizeof(int) * (Q + 1), st));
+  if (total > 0) {
+    k_pool_scatter<<<cdiv(total, 256), 256, 0, st>>>(pool_rc, pool_q, total, q_off, q_fill, csr_row->as<int>(),
+                                                     csr_q->as<int>());
+    PCDB_LAUNCH_CHECK();
+    k_chi_eval<<<cdiv(total, 128), 128, 0, st>>>(queries_d, cb.words.as<float>(), cb.D, total, csr_row->as<int>(),
+                                                 csr_q->as<int>(), csr_d->as<float>());
+    PCDB_LAUNCH_CHECK();
+  }
+  k_chi_select<<<cdiv(Q * 32, 256), 256, 0, st>>>(Q, K, q_off, csr_row->as<int>(), csr_d->as<float>(),
+                                                  w.knn_part_d.as<float>(), w.knn_part_i.as<int>());
   PCDB_LAUNCH_CHECK();
   return PCDB_OK;
 }

@@ -21,16 +21,20 @@ int stage_shot_counts(pcdb_ctx* ctx, unsigned long long out[2]);  // syncs
 // knn_scan.cu
 int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
                    float ratio_thr);
-int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int K, int S, int cap, bool use_ratio,
-                     float ratio_thr);
+int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int S, int cap, int dist_type);
+int stage_knn_finish(pcdb_ctx* ctx, int64_t Q, int k, int K, bool use_ratio, float ratio_thr);
+int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, const int2* pool_rc,
+                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_q,
+                       DevBuf* csr_d);
 
 int stage_pair_distances(pcdb_ctx* ctx, const float* a_d, const float* b_d, int64_t n, int D, int dist_type,
                          float* out_d);
 
 // knn_gemm.cu
-int gemm_prepare_codebook(pcdb_ctx* ctx);  // fp16 copy, norms, error bounds, tensor map (after words upload)
-int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, bool use_ratio, float ratio_thr);
-bool gemm_supported(const pcdb_ctx* ctx);
+int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type);  // fp16 operand copy, norms, error bounds, tensor map
+int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
+                   float ratio_thr);
+bool gemm_supported(const pcdb_ctx* ctx, int dist_type);
 
 // votes.cu
 int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_lrf_d, const long long* feat_off_d,
@@ -39,3 +43,17 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
 // meanshift.cu
 int stage_votes_unpack(pcdb_ctx* ctx, int B, int64_t V);
 int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* members_out);  // syncs
+
+// api.cu: exact kNN of device-resident queries against this context's descriptor rows (GEMM or scan by `mode`)
+int pcdb_run_knn(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,
+                 float ratio_thr);
+
+// comm.cu (collective calls: every rank of the communicator must make them in the same order)
+bool comm_active(const pcdb_ctx* ctx);
+bool comm_codebook_sharded(const pcdb_ctx* ctx);   // descriptor rows sharded over the ranks, vote tables replicated
+bool comm_keypoints_sharded(const pcdb_ctx* ctx);  // one scene per call, keypoints sharded over the ranks
+int stage_knn_sharded(pcdb_ctx* ctx, const float* queries_d, int64_t Q_local, int k, int dist_type, int mode,
+                      bool use_ratio, float ratio_thr);
+int stage_slice_keypoints(pcdb_ctx* ctx, int B, int64_t Q, int64_t* Q_local_out);
+int stage_gather_votes(pcdb_ctx* ctx, int B, int64_t V_local, int64_t* V_out);  // syncs
+float comm_last_exchange_ms(pcdb_ctx* ctx);

@@ -7,6 +7,8 @@
 // a gather from the CSR vote table of the activated codeword rows and one coalesced 80-byte record per vote.
 // The rotation goes through the same float quaternion route as Utils::rotateBack (utils/utils.cpp:136-178,342-394,
 // 560-566) with boost::math::quaternion's operator*= evaluation order and no FMA contraction.
+#include <algorithm>
+
 #include "common.cuh"
 #include "stages.h"
 
@@ -150,7 +152,7 @@ __global__ void k_vote_write(VoteArgs a, const int* __restrict__ pos, const int*
     Quat r = qmul(qmul(qconj(rq), p), rq);
     Quat bq{a.vote_bbox[7 * v], a.vote_bbox[7 * v + 1], a.vote_bbox[7 * v + 2], a.vote_bbox[7 * v + 3]};
     Quat nb = qmul(bq, rq);  // :162-164
-    pcdb_vote out;
+    alignas(16) pcdb_vote out;
     out.position[0] = __fadd_rn(kx, r.b);
     out.position[1] = __fadd_rn(ky, r.c);
     out.position[2] = __fadd_rn(kz, r.d);
@@ -201,7 +203,7 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
   const pcdb_params& P = ctx->prm;
   PCDB_CUDA(w.vote_off.ensure(sizeof(long long) * (B + 1)));
   *V_out = 0;
-  if (F == 0 || cb.N == 0) {
+  if (F == 0 || cb.N_table == 0) {
     PCDB_CUDA(cudaMemsetAsync(w.vote_off.p, 0, sizeof(long long) * (B + 1), st));
     return PCDB_OK;
   }
@@ -232,6 +234,9 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
   a.use_codeword_weight = P.use_codeword_weight;
   a.abs_is_int = P.filter_abs_is_int;
   const int64_t T = F * k;
+  if (T * std::max(1, cb.max_votes_per_word) > 0x7fffff00ll)
+    return ctx->fail(PCDB_E_INVALID, "more than 2^31 votes possible in one batch (%lld activations x %d votes per word)",
+                     (long long)T, cb.max_votes_per_word);
   PCDB_CUDA(w.vote_cnt.ensure(sizeof(int) * (T + 2)));
   PCDB_CUDA(w.vote_pos.ensure(sizeof(int) * (T + 2)));
   k_vote_count<<<cdiv(T + 1, 128), 128, 0, st>>>(a, w.vote_cnt.as<int>());

@@ -22,8 +22,19 @@ SYMBOLS = [
     "pcdb_set_stream", "pcdb_set_codebook", "pcdb_voxel_keypoints", "pcdb_radius_neighbours", "pcdb_shot_lrf",
     "pcdb_shot_describe", "pcdb_compute_normals", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
     "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
-    "pcdb_get_stats", "pcdb_reset_stats",
+    "pcdb_get_stats", "pcdb_reset_stats", "pcdb_comm_unique_id", "pcdb_comm_init", "pcdb_comm_destroy", "pcdb_comm_info",
+    "pcdb_set_codebook_sharded", "pcdb_comm_shard_keypoints",
 ]
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    rc = lib().pcdb_comm_unique_id(buf, COMM_ID_BYTES)
+    if rc != 0:
+        raise PcdbError(rc, "NCCL unavailable (libnccl.so.2 could not be loaded)")
+    return bytes(buf)
 
 
 class PcdbError(RuntimeError):
@@ -89,6 +100,34 @@ class Context:
             ptr(cb.vote_weight, F), ptr(cb.vote_class, U32), ptr(cb.vote_instance, U32), ptr(cb.vote_bbox, F),
             ptr(cb.vote_class_weight, F), ptr(cb.kp_train, F), ptr(cb.codeword_ids, I32),
             ptr(cb.codeword_weight, F), ptr(cb.sigma2, F), cb.n_classes, I64(row_base)))
+
+    # ---- multi-GPU -------------------------------------------------------------------------------------------
+    def comm_init(self, rank, n_ranks, unique_id):
+        """Collective: ncclCommInitRank on this context's device."""
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(lib().pcdb_comm_init(self.h, int(rank), int(n_ranks), buf))
+
+    def comm_destroy(self):
+        self._check(lib().pcdb_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, n, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(lib().pcdb_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
+        return {"rank": r.value, "n_ranks": n.value, "nccl_version": v.value}
+
+    def comm_shard_keypoints(self, enable=True):
+        self._check(lib().pcdb_comm_shard_keypoints(self.h, 1 if enable else 0))
+
+    def set_codebook_sharded(self, cb: Codebook, row_lo, row_hi):
+        """Descriptor rows [row_lo, row_hi) on this rank, complete vote tables.  `cb` may hold all
+        rows (the shard is sliced out here) — only the slice is uploaded."""
+        self.cb = cb
+        words = np.ascontiguousarray(cb.words[row_lo:row_hi])
+        self._check(lib().pcdb_set_codebook_sharded(
+            self.h, ptr(words, F), I64(row_lo), I64(row_hi), I64(cb.N), cb.D, ptr(cb.vote_off, I64),
+            ptr(cb.vote_xyz, F), ptr(cb.vote_weight, F), ptr(cb.vote_class, U32), ptr(cb.vote_instance, U32),
+            ptr(cb.vote_bbox, F), ptr(cb.vote_class_weight, F), ptr(cb.kp_train, F), ptr(cb.codeword_ids, I32),
+            ptr(cb.codeword_weight, F), ptr(cb.sigma2, F), cb.n_classes))
 
     # ---- stage-level entry points ---------------------------------------------------------------------------
     def voxel_keypoints(self, xyz, rgb, cloud_off, leaf):

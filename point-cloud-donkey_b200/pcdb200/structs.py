@@ -130,7 +130,8 @@ class Stats(C.Structure):
             "n_points n_keypoints n_features n_neighbours_lrf n_neighbours_shot n_votes n_maxima "
             "knn_queries knn_candidates knn_fallback_queries kernel_launches"
         ).split()
-    ] + [(n, C.c_double) for n in "features_ms knn_ms knn_gemm_ms votes_ms maxima_ms".split()]
+    ] + [(n, C.c_double) for n in "features_ms knn_ms knn_gemm_ms votes_ms maxima_ms".split()] + [
+        ("comm_bytes", C.c_int64), ("comm_ms", C.c_double)]
 
 
 def ptr(a, ctype):
