@@ -34,6 +34,26 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  NCCL (NCCL_DEBUG=INFO, as the driver may set it to count ranks) writes to
+    fd 1 by default: keep a private handle on the real stdout for the JSON line and point fd 1 at stderr, so the NCCL
+    lines stay visible to the caller without ending up in the JSON stream."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -111,6 +131,85 @@ def build_world(name, n_words_override, ctx, rank_log=True):
     return wl, prm, cb
 
 
+class _CpuTrainCtx:
+    """Stands in for pcdb200.api.Context inside train.train_codebook on the REFERENCE arm, so that arm never touches
+    libpcdb200 or a GPU.  Training activates every feature against the codebook made of those same features with K = 1
+    (codebook.cpp:64-127): the nearest codeword of feature i is row i itself at distance 0 — or the first identical row,
+    ties -> lower row — so the N x N search reduces to grouping identical descriptors ("identity rule")."""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def set_params(self, prm):
+        pass
+
+    def set_codebook(self, cb):
+        pass
+
+    def knn(self, desc, k=1, dist_type=0, mode=0):
+        if k != 1:
+            raise ValueError("the CPU-only world builder handles K = 1 (all bench workloads)")
+        n = desc.shape[0]
+        # group identical rows through a 64-bit hash of their bit patterns, then verify the (rare) groups exactly
+        bits = np.ascontiguousarray(desc).view(np.uint32).astype(np.uint64)
+        mult = np.random.default_rng(12345).integers(1, 2 ** 63, desc.shape[1], dtype=np.uint64) | np.uint64(1)
+        h = (bits * mult[None, :]).sum(1, dtype=np.uint64)
+        _, first, inv = np.unique(h, return_index=True, return_inverse=True)
+        idx = first[inv].astype(np.int32)  # np.unique returns the FIRST occurrence: ties -> lower row
+        moved = np.nonzero(idx != np.arange(n))[0]
+        if len(moved) and not np.array_equal(desc[moved], desc[idx[moved]]):  # a hash collision: do it the slow way
+            keys = np.ascontiguousarray(desc).view(np.dtype((np.void, desc.dtype.itemsize * desc.shape[1]))).ravel()
+            _, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+            idx = first[inv].astype(np.int32)
+        return idx.reshape(-1, 1), np.zeros((n, 1), np.float32), np.ones(n, np.int32)
+
+    def distance_pairs(self, a, b, dist_type):
+        return self.orc.distance(a, b, dist_type)
+
+
+def build_world_cpu(name, n_words_override, orc):
+    """build_world on the host cores only (oracle features + identity-rule training): the reference arm's set-up."""
+    wl = synth.WORKLOADS[name]
+    prm = synth.workload_params(name)
+    n_cls, P = wl["n_classes"], wl["P"]
+    n_words = n_words_override or wl["n_words"]
+    t0 = time.time()
+    x, n, c, o = synth.make_clouds(list(range(min(n_cls, 8))), [10_000 + i for i in range(min(n_cls, 8))], P,
+                                   scale=wl["scale"], jitter=0.002)
+    per_cloud = max(1.0, orc.compute_features(prm, x, n, c, o)[0].shape[0] / min(n_cls, 8))
+    per_class = max(1, int(round(n_words / per_cloud / n_cls)))
+    tr_cls = [cc for cc in range(n_cls) for _ in range(per_class)]
+    seeds = [1_000_000 + i for i in range(len(tr_cls))]
+    fx, fl, fd, counts, bbs = [], [], [], [], []
+    for s_ in range(0, len(tr_cls), 256):
+        x, n, c, o = synth.make_clouds(tr_cls[s_:s_ + 256], seeds[s_:s_ + 256], P, scale=wl["scale"], jitter=0.002)
+        a = orc.compute_features(prm, x, n, c, o)
+        fx.append(a[0]), fl.append(a[1]), fd.append(a[2]), counts.append(np.diff(a[3]))
+        bbs.extend(train.aabb(x[o[i]:o[i + 1]]) for i in range(len(o) - 1))
+    foff = np.concatenate([[0], np.cumsum(np.concatenate(counts))]).astype(np.int64)
+    fx, fl, fd = np.concatenate(fx), np.concatenate(fl), np.concatenate(fd)
+    cb = train.train_codebook(_CpuTrainCtx(orc), prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), np.stack(bbs),
+                              n_cls)
+    log("codebook (host cores only): %d training clouds -> N=%d words (D=%d) in %.1fs"
+        % (len(tr_cls), cb.N, cb.D, time.time() - t0))
+    return wl, prm, cb
+
+
+def workload_config(name, wl, cb, batch, n_words=0):
+    workload_name = {"c1": "C1 quick-start stand-in", "c2": "C2 ModelNet10-shaped", "c3": "C3 ModelNet40-shaped",
+                     "c4": "C4 Washington-shaped CSHOT",
+                     "c5": "C5 cluttered scenes (%d objects + table + clutter per cloud)"
+                           % synth.WORKLOADS["c5"].get("scene_objects", 0)}[name]
+    n_words = n_words or wl["n_words"] or cb.N
+    return {"workload": "%s synthetic: %d classes, P=%d points/cloud, %s-%d, ~%d codewords, K=1, Euclidean, exact "
+                        "activation" % (workload_name, wl["n_classes"], wl["P"], "CSHOT" if cb.D == 1344 else "SHOT",
+                                        cb.D, n_words),
+            "batch_clouds_per_gpu": batch,
+            "sharding": "test clouds sharded over GPUs, codebook replicated, no collective",
+            "l2": "inputs larger than L2: codebook ~%.2f GB fp16 + ~%.2f GB fp32 streamed every step (L2 126 MB)"
+                  % (n_words * cb.D * 2 / 1e9, n_words * cb.D * 4 / 1e9)}
+
+
 def test_batch(wl, batch, rank, step):
     if "scene_objects" in wl:  # C5: every "cloud" of the batch is one cluttered scene
         xs, ns, cs, off, first = [], [], [], [0], []
@@ -155,6 +254,136 @@ def cpu_approx_baseline(model, batch, ctx=None, n_clouds=96):
     return out
 
 
+def sharded_legs(args, rank, world, local_rank, stream, dist, torch, api):
+    """The two multi-GPU modes that communicate, measured after the headline run, one record each:
+    C4 with the codebook row-sharded over the ranks (query all-gather + top-k all-to-all inside the library) and
+    C5 with the keypoints of one scene sharded over the ranks (vote all-gather inside the library)."""
+    from pcdb200 import sharded
+    out = {}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- C4: row-sharded codebook -----------------------------------------------------------------------------------
+    try:
+        ctx = api.Context(device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        wl, prm, cb = build_world("c4", args.words, ctx, rank_log=(rank == 0))
+        batch = args.shard_batch
+        x, n, c, o, _ = test_batch(wl, batch, rank, 0)
+        dx, dn, dc = torch.from_numpy(x).cuda(), torch.from_numpy(n).cuda(), torch.from_numpy(c.astype(np.int32)).cuda()
+        lab_rep = torch.empty(batch, dtype=torch.int32, device="cuda")
+        lab_sh = torch.empty(batch, dtype=torch.int32, device="cuda")
+
+        def run(cx, lab, steps):
+            for _ in range(2):
+                cx.classify_batch_device(dx.data_ptr(), dn.data_ptr(), dc.data_ptr(), o, lab.data_ptr())
+            barrier()
+            cx.reset_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            comm_ms = []
+            for _ in range(steps):
+                cx.classify_batch_device(dx.data_ptr(), dn.data_ptr(), dc.data_ptr(), o, lab.data_ptr())
+                comm_ms.append(cx.stats()["comm_ms"])
+            e1.record(stream)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / steps, cx.stats(), float(np.mean(comm_ms))
+
+        steps = max(2, min(args.steps, 5))
+        ms_rep, st_rep, _ = run(ctx, lab_rep, steps)                       # replicated codebook, same clouds
+        sh = api.Context(prm, device=local_rank)
+        sh.set_stream(stream.cuda_stream)
+        sharded.init_comm(sh, dist)
+        lo, hi = sharded.shard_codebook(sh, cb, dist)
+        ms_sh, st_sh, comm_ms = run(sh, lab_sh, steps)
+        same = bool(torch.equal(lab_rep, lab_sh))
+        flag = torch.tensor([int(same)], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        q_local = st_sh["n_features"] / steps
+        out["sharded_codebook"] = {
+            "workload": "C4 Washington-shaped CSHOT-1344, N=%d codewords row-sharded over %d GPUs (%d rows = %.2f GB "
+                        "fp32 + %.2f GB fp16 per GPU instead of %.2f + %.2f), vote tables replicated, %d clouds per GPU "
+                        "per step" % (cb.N, world, hi - lo, (hi - lo) * cb.D * 4 / 1e9, (hi - lo) * cb.D * 2 / 1e9,
+                                      cb.N * cb.D * 4 / 1e9, cb.N * cb.D * 2 / 1e9, batch),
+            "value": world * batch / (ms_sh / 1e3), "unit": "clouds/s", "ms_per_step": ms_sh,
+            "replicated_codebook_same_clouds": {"value": world * batch / (ms_rep / 1e3), "ms_per_step": ms_rep},
+            "exchange_ms_per_step_rank0": comm_ms,
+            "exchange": "query all-gather(v) + all-to-all of (f32 distance, i32 row) x K + device merge, NCCL on the "
+                        "compute stream",
+            "nvlink_bytes_received_per_step_rank0": st_sh["comm_bytes"] / steps,
+            "queries_per_step_rank0": q_local, "labels_identical_to_replicated_all_ranks": bool(flag.item()),
+            "gemm_ms_per_step_rank0": st_sh["knn_gemm_ms"], "stage_ms_last_step_rank0": {
+                "features": st_sh["features_ms"], "activation_incl_exchange": st_sh["knn_ms"],
+                "votes": st_sh["votes_ms"], "maxima": st_sh["maxima_ms"]},
+            "nccl_version": sh.comm_info()["nccl_version"], "comm_n_ranks": sh.comm_info()["n_ranks"]}
+        sh.close()
+        ctx.close()
+    except Exception as e:  # a failing leg must not take the headline line with it
+        out["sharded_codebook"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        log("sharded_codebook leg failed:", e)
+
+    # ---- C5: one scene, keypoints sharded ---------------------------------------------------------------------------
+    try:
+        ctx = api.Context(device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        wl, prm, cb = build_world("c5", args.words, ctx, rank_log=(rank == 0))
+        x, n, c, o, _ = test_batch(wl, 1, 0, 0)                           # the SAME scene on every rank
+        dx, dn, dc = torch.from_numpy(x).cuda(), torch.from_numpy(n).cuda(), torch.from_numpy(c.astype(np.int32)).cuda()
+        lab = torch.empty(1, dtype=torch.int32, device="cuda")
+        sharded.init_comm(ctx, dist)
+
+        def scene_ms(reps):
+            for _ in range(2):
+                ctx.classify_batch_device(dx.data_ptr(), dn.data_ptr(), dc.data_ptr(), o, lab.data_ptr())
+            barrier()
+            ctx.reset_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                ctx.classify_batch_device(dx.data_ptr(), dn.data_ptr(), dc.data_ptr(), o, lab.data_ptr())
+            e1.record(stream)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / reps, ctx.stats()
+
+        ms1, st1 = scene_ms(8)
+        _, m1, mo1 = ctx.classify_batch(x, n, c, o)
+        ctx.comm_shard_keypoints(True)
+        msn, stn = scene_ms(8)
+        _, mn, mon = ctx.classify_batch(x, n, c, o)
+        same = bool(np.array_equal(mo1, mon) and m1.tobytes() == mn.tobytes())
+        flag = torch.tensor([int(same)], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["sharded_scene"] = {
+            "workload": "C5: one cluttered scene of %d points (%d objects + table + clutter), %d keypoints, codebook "
+                        "N=%d replicated, keypoints sharded over %d GPUs, votes all-gathered"
+                        % (len(x), wl["scene_objects"], int(st1["n_keypoints"] / 8), cb.N, world),
+            "ms_per_scene": msn, "ms_per_scene_one_gpu_same_box": ms1, "speedup_vs_one_gpu": ms1 / msn if msn else None,
+            "unit": "ms", "maxima": int(mon[1]), "maxima_identical_to_one_gpu_all_ranks": bool(flag.item()),
+            "vote_gather_ms_rank0": stn["comm_ms"], "nvlink_bytes_received_per_scene_rank0": stn["comm_bytes"] / 8,
+            "stage_ms_rank0": {"features": stn["features_ms"], "activation": stn["knn_ms"],
+                               "votes_incl_gather": stn["votes_ms"], "maxima": stn["maxima_ms"]},
+            "stage_ms_one_gpu": {"features": st1["features_ms"], "activation": st1["knn_ms"], "votes": st1["votes_ms"],
+                                 "maxima": st1["maxima_ms"]}}
+        ctx.close()
+    except Exception as e:
+        out["sharded_scene"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        log("sharded_scene leg failed:", e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,7 +393,14 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="clouds per step per GPU (default 1024; 4 scenes for c5)")
     ap.add_argument("--words", type=int, default=0, help="override the codebook size (debug)")
+    ap.add_argument("--dist", default="", choices=["", "euclidean", "chisquared"],
+                    help="override the workload's DistanceType (chisquared = as the reference's configs ship)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-legs", default="auto", choices=["auto", "on", "off"],
+                    help="also measure the sharded-codebook (C4) and keypoint-sharded scene (C5) modes; auto = when "
+                         "launched on more than one GPU")
+    ap.add_argument("--shard-batch", type=int, default=256, help="clouds per GPU per step of the sharded-codebook leg")
+    ap.add_argument("--label-check", type=int, default=64, help="clouds whose labels are compared with the oracle")
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = 4 if args.workload == "c5" else 1024
@@ -174,41 +410,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference" and rank != 0:
-        return 0  # rank 0 alone runs and prints the reference arm
-
-    import torch
-    import torch.distributed as dist
-    from pcdb200 import api
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local_rank)
-    if world > 1 and args.impl == "b200":
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION prints a banner on stdout; keep it to the JSON line
-        if os.environ.get("PCDB_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = os.environ["PCDB_NCCL_DEBUG"]
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    ctx = api.Context(device=local_rank)
-    wl, prm, cb = build_world(args.workload, args.words, ctx, rank_log=(rank == 0))
-    workload_name = {"c1": "C1 quick-start stand-in", "c2": "C2 ModelNet10-shaped", "c3": "C3 ModelNet40-shaped",
-                     "c4": "C4 Washington-shaped CSHOT",
-                     "c5": "C5 cluttered scenes (%d objects + table + clutter per cloud)"
-                           % synth.WORKLOADS["c5"].get("scene_objects", 0)}[args.workload]
-    config = {"workload": "%s synthetic: %d classes, P=%d points/cloud, SHOT-%d, N=%d codewords, K=1, Euclidean, exact "
-                          "activation" % (workload_name, wl["n_classes"], wl["P"], cb.D, cb.N),
-              "batch_clouds_per_gpu": args.batch, "sharding": "test clouds sharded over GPUs, codebook replicated, no "
-                                                              "collective",
-              "l2": "inputs larger than L2: codebook %.2f GB fp16 + %.2f GB fp32 streamed every step (L2 126 MB)"
-                    % (cb.N * cb.D * 2 / 1e9, cb.N * cb.D * 4 / 1e9)}
+    claim_stdout()
 
     # -------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
+        if rank != 0:
+            return 0  # rank 0 alone runs and prints the reference arm
+        # host cores only: no libpcdb200, no CUDA context (the codebook is trained on the CPU by the identity rule)
         from oracle import oracle_py as orc
         orc.set_num_threads(os.cpu_count() or 1)
+        wl, prm, cb = build_world_cpu(args.workload, args.words, orc)
+        if args.dist:
+            prm.distance_type = 1 if args.dist == "chisquared" else 0
+        config = workload_config(args.workload, wl, cb, args.batch, args.words)
         model = orc.Model(prm, cb)
         cores = orc.num_threads()
         x, n, c, o, _ = test_batch(wl, 16, 0, 0)
@@ -222,22 +436,43 @@ def main():
                 times.append(t)
         total = sum(times)
         val = per_step * len(times) / total
+        sample = "%d steps x %d clouds of the same workload on the host cores, exact (FLANNExactMatch) activation" % (
+            len(times), per_step)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clouds/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, sample="%d clouds per step on the host cores" % per_step),
-                "cpu_baseline": {"value": val, "unit": "clouds/s", "cores": cores, "kind": "port",
-                                 "sample": "%d steps x %d clouds of the same workload, exact (FLANNExactMatch) activation"
-                                           % (len(times), per_step)},
+                "config": config, "sample": sample,
+                "cpu_baseline": {"value": val, "unit": "clouds/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
                 "approximate_mode": cpu_approx_baseline(model, test_batch(wl, 96, 0, 1)),
-                "note": "FLANNExactMatch=true on both arms (the only mode whose labels can be compared); the reference's "
-                        "default approximate search is timed beside it in approximate_mode. "
-                        "oracle port of the reference CPU path (the reference needs PCL/FLANN and cannot be built here); "
-                        "the codebook is built by the untimed set-up on the GPU"}
-        print(json.dumps(line), flush=True)
+                "note": "one host process on all cores whatever --gpus says. FLANNExactMatch=true on both arms (the only "
+                        "mode whose labels can be compared); the reference's DEFAULT approximate search is timed beside "
+                        "it in approximate_mode and is the figure a CPU ratio should be quoted against. Oracle port of "
+                        "the reference CPU path (the reference needs PCL/FLANN and cannot be built here); this arm "
+                        "loads neither libpcdb200 nor CUDA"}
+        emit(line)
         return 0
+
+    import torch
+    import torch.distributed as dist
+    from pcdb200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = api.Context(device=local_rank)
+    wl, prm, cb = build_world(args.workload, args.words, ctx, rank_log=(rank == 0))
+    if args.dist:
+        prm.distance_type = 1 if args.dist == "chisquared" else 0
+        ctx.set_params(prm)
+    config = workload_config(args.workload, wl, cb, args.batch, args.words)
+    if args.dist == "chisquared":
+        config["workload"] = config["workload"].replace("Euclidean", "ChiSquared")
 
     # -------------------------------------------------------------------------------------------- B200 arm
     stream = torch.cuda.current_stream()
@@ -296,15 +531,17 @@ def main():
     value = world * args.batch * args.steps / (ms_total / 1e3)
     launches = int(st["kernel_launches"])
     q_per_step = st["knn_queries"] / max(1, args.steps)
-    flop_per_launch = 2.0 * q_per_step * cb.N * cb.D
+    chi = prm.distance_type == 1
+    flop_per_launch = 2.0 * q_per_step * cb.N * cb.D * (2 if chi else 1)  # the chi^2 sandwich sweeps the codebook twice
     avg_gemm_ms = float(np.mean(gemm_ms)) if gemm_ms else 0.0
     achieved = flop_per_launch / (avg_gemm_ms / 1e3) / 1e12 if avg_gemm_ms > 0 else 0.0
     pk = peaks()
     traffic = None  # DRAM bytes per GEMM launch from the committed ncu capture of this very workload, else null
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json")))
-        if tr["workload"] == args.workload and tr["batch_clouds"] == args.batch and not args.words:
-            traffic = tr["traffic_bytes_per_launch"]
+        for rec in (tr if isinstance(tr, list) else [tr]):
+            if rec["workload"] == args.workload and rec["batch_clouds"] == args.batch and not args.words and not chi:
+                traffic = rec["traffic_bytes_per_launch"]
     except Exception:
         pass
 
@@ -334,12 +571,14 @@ def main():
         lat.append((time.perf_counter() - t0) * 1e3)
     single_ms = float(np.median(lat[2:]))
 
-    # correctness spot check against the oracle (outside the timed region) ---------------------------------------------
+    # correctness check against the oracle (outside the timed region) ------------------------------------------------
     parity = None
+    parity_detail = None
     acc = float((host_labels == batches[(args.steps - 1) % n_distinct][4]).mean())
     if "scene_objects" in wl:
         acc = None  # a scene has no single ground-truth label; localisation is checked in tests/test_gpu_parity.py
     cpu_base = None
+    cpu_approx = None
     if rank == 0:
         from oracle import oracle_py as orc
         orc.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
@@ -352,6 +591,7 @@ def main():
         gl = ctx.classify_batch(x[:o[2]], n[:o[2]], c[:o[2]], o[:3], want_maxima=False)[0]
         t1, ol = cpu_time_clouds(model, x, n, c, o, 0, 2)
         parity = bool(np.array_equal(gl, ol))
+        n_checked = 2
         if world == 1 and not args.no_cpu_baseline and "scene_objects" not in wl:
             per = t1 / 2
             extra = int(max(0, min(14, round(15.0 / max(per, 1e-3)) - 2)))
@@ -362,15 +602,38 @@ def main():
                                         o[2:3 + extra] - o[2], want_maxima=False)[0]
                 parity = parity and bool(np.array_equal(g2, ol2))
                 tt, cnt = tt + t2, cnt + extra
+                n_checked += extra
             cpu_base = {"value": cnt / tt, "unit": "clouds/s", "cores": orc.num_threads(), "kind": "port",
                         "sample": "%d clouds of the timed batch, exact (FLANNExactMatch) activation, %.1f s"
                                   % (cnt, tt), "stage_ms_per_cloud": {k: round(v / cnt, 2) for k, v in model.last_times.items()}}
-            cpu_base["approximate_mode"] = cpu_approx_baseline(model, batches[0], ctx)
+            cpu_approx = cpu_approx_baseline(model, batches[0], ctx)
+            cpu_base["approximate_mode"] = cpu_approx
         elif world == 1 and not args.no_cpu_baseline:
             cpu_base = {"value": 2 / t1, "unit": "clouds/s", "cores": orc.num_threads(), "kind": "port",
                         "sample": "2 REDUCED scenes (6 objects of 2048 points, 12k points each; a full scene takes the "
-                                  "exact CPU search minutes), exact activation, %.1f s" % t1,
-                        "approximate_mode": cpu_approx_baseline(model, batches[0], ctx, n_clouds=2)}
+                                  "exact CPU search minutes), exact activation, %.1f s" % t1}
+            cpu_approx = cpu_approx_baseline(model, batches[0], ctx, n_clouds=2)
+            cpu_base["approximate_mode"] = cpu_approx
+        # >= 64 labels against the oracle with its exact search done by sgemm proposals + the FLANN-order
+        # functor (oracle_py.knn_exact_pruned: the linear scan's result by construction, at a fraction of its cost)
+        if "scene_objects" not in wl and args.label_check > n_checked and not prm.use_distance_ratio:
+            nb = min(args.label_check, len(o) - 1)
+            tq = time.time()
+            ol3 = orc.classify_batch_pruned(model, x[:o[nb]], n[:o[nb]], c[:o[nb]], o[:nb + 1])
+            g3 = ctx.classify_batch(x[:o[nb]], n[:o[nb]], c[:o[nb]], o[:nb + 1], want_maxima=False)[0]
+            parity = parity and bool(np.array_equal(g3, ol3))
+            parity_detail = {"clouds_checked": int(nb), "labels_equal": int((g3 == ol3).sum()),
+                             "oracle_seconds": round(time.time() - tq, 1),
+                             "oracle_search": "exact: sgemm proposals + FLANN-order functor (first %d clouds also by the "
+                                              "plain linear scan)" % n_checked}
+        else:
+            parity_detail = {"clouds_checked": int(n_checked)}
+
+    legs = {}
+    if args.shard_legs == "on" or (args.shard_legs == "auto" and world > 1):
+        ctx.close()
+        ctx = None
+        legs = sharded_legs(args, rank, world, local_rank, stream, dist if world > 1 else _SoloDist(), torch, api)
 
     if rank == 0:
         fm = np.mean(np.array(stage_ms), axis=0) if stage_ms else np.zeros(4)
@@ -389,6 +652,8 @@ def main():
             "votes": {"bound": "hbm", "bytes_per_step": vote_bytes, "ms_per_step": float(fm[2]),
                       "achieved": vote_bytes / (float(fm[2]) / 1e3) / 1e9 if fm[2] > 0 else None, "peak": pk["hbm"],
                       "unit": "GB/s"}}
+        step_s = ms_total / args.steps / 1e3
+        floor_s = flop_per_launch / (pk["tflops_burst"] * 1e12) if pk["tflops_burst"] else None
         line = {
             "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -403,11 +668,23 @@ def main():
                          "traffic_unit": "DRAM bytes per launch (ncu, profiles/gemm_traffic.json)",
                          "peak_source": pk["src"], "peak_burst": pk["tflops_burst"],
                          "frac_of_burst_peak": achieved / pk["tflops_burst"] if pk["tflops_burst"] else None,
-                         "flop_note": "algorithmic 2*Q*N*D with D = the descriptor length; the kernel issues (D+16)/D of "
-                                      "that (|c|^2 rides in one extra K step)",
+                         "flop_note": "algorithmic 2*Q*N*D with D = the descriptor length (x2 for ChiSquared: two "
+                                      "sweeps); the resident-query kernel issues (D+16)/D of that (|c|^2 rides in one "
+                                      "extra K step)",
                          "flop_per_launch": flop_per_launch, "ms_per_launch": avg_gemm_ms,
                          "share_of_step": avg_gemm_ms / (ms_total / args.steps) if ms_total else None},
+            # what exact activation costs on one GPU whatever the kernel: 2QND flop at the measured burst tensor peak
+            "flop_ceiling": {"flop_per_step": flop_per_launch, "seconds_at_burst_peak": floor_s,
+                             "clouds_per_s_per_gpu_at_burst_peak": args.batch / floor_s if floor_s else None,
+                             "note": "upper bound for ANY exact dense activation of this workload on one GPU"},
             "cpu_baseline": cpu_base,
+            # the reference's DEFAULT activation is approximate: the CPU ratio to quote leads with this one
+            "cpu_baseline_approximate": cpu_approx,
+            "speedup_vs_cpu": None if not cpu_base else {
+                "e2e_over_approximate_default": e2e_value / cpu_approx["value"] if cpu_approx else None,
+                "e2e_over_exact": e2e_value / cpu_base["value"], "cores": cpu_base["cores"],
+                "note": "one GPU against all host cores of this box; the approximate figure is the reference's default "
+                        "mode (FLANN kd-forest stand-in), the exact one is the mode both arms run for label parity"},
             "roofline_stages": stage_roofs,
             "clocks": sampler.summary(),
             "stage_ms_per_step": {"features": float(fm[0]), "activation": float(fm[1]), "votes": float(fm[2]),
@@ -416,14 +693,43 @@ def main():
                                                                   "n_neighbours_lrf", "n_neighbours_shot", "n_votes",
                                                                   "knn_candidates", "knn_fallback_queries")},
             "single_cloud_latency_ms": single_ms,
-            "label_parity_vs_oracle": parity, "label_accuracy_vs_truth": acc,
+            "label_parity_vs_oracle": parity, "label_parity_detail": parity_detail, "label_accuracy_vs_truth": acc,
         }
-        print(json.dumps(line), flush=True)
+        line.update(legs)
+        emit(line)
     if world > 1:
         dist.barrier()  # rank 0 checks labels against the oracle after the timed region; leave together
         dist.destroy_process_group()
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     return 0
+
+
+class _SoloDist:
+    """torch.distributed stand-in for a single process (the sharded legs at N = 1: communicator of one rank)."""
+
+    class ReduceOp:
+        MIN = MAX = None
+
+    @staticmethod
+    def get_rank():
+        return 0
+
+    @staticmethod
+    def get_world_size():
+        return 1
+
+    @staticmethod
+    def broadcast_object_list(objs, src=0):
+        return None
+
+    @staticmethod
+    def barrier():
+        return None
+
+    @staticmethod
+    def all_reduce(t, op=None):
+        return None
 
 
 if __name__ == "__main__":

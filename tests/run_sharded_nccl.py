@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""Row-sharded codebook over real NCCL: run with
+"""Multi-GPU exchange paths of libpcdb200 over real NCCL, one process per GPU:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
-        tests/run_sharded_nccl.py [--out result.json]
-Every rank uploads its row shard of a CSHOT-1344 codebook (row_base = first global row), all ranks see the same
-query batch; the exchange step is one all-gather of the per-shard top-k lists followed by pcdb_merge_topk on the
-device, then the owners cast the votes and all ranks receive them.  Checked on every rank against the unsharded
-codebook on the same GPU: identical rows, bit-identical distances, the same vote multiset, the same labels; on rank 0
-also against the oracle.  A second section shards the KEYPOINTS of one cluttered scene over the ranks (C5) and checks
-that the all-gathered votes and the maxima equal the single-GPU fused path bit for bit.  (The world-size-2 gloo twin of this script is tests/test_sharding_cpu.py.)
-"""
+        tests/run_sharded_nccl.py [--words 0] [--out result.json]
+
+Section 1 — row-sharded codebook (config C4): every rank uploads descriptor rows [lo, hi) of a CSHOT-1344 codebook plus
+the complete vote tables (pcdb_set_codebook_sharded) and classifies ITS OWN test clouds; the query all-gather, the
+top-k all-to-all and the merge all happen inside the library on the device.  Checked on every rank against an
+unsharded context on the same GPU: identical rows, bit-identical distances (k = 2, the k = 1 distance-ratio test,
+Euclidean and ChiSquared), byte-identical vote lists, maxima and labels.
+Section 2 — keypoint-sharded scene (config C5): all ranks pass the same cluttered scene, the votes are all-gathered
+inside the library; votes and maxima must equal the single-GPU fused path byte for byte.
+
+torch.distributed (gloo) is used only to hand out the NCCL unique id and to reduce the pass/fail flags.
+--words 0 builds the full 1.07 M x 1344 codebook of the C4 bench (about a minute of set-up per rank)."""
 import argparse
 import json
 import os
@@ -22,112 +26,148 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
 
 
+def shard_bounds(n_rows, world):
+    base, rem = divmod(n_rows, world)
+    return [r * base + min(r, rem) for r in range(world + 1)]
+
+
+def new_comm(ctx, rank, world, dist, api):
+    ids = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(rank, world, ids[0])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
-    ap.add_argument("--train-per-class", type=int, default=6)
+    ap.add_argument("--words", type=int, default=20000, help="codebook size (0 = the C4 bench's 1.07 M words)")
+    ap.add_argument("--clouds", type=int, default=8, help="test clouds per rank")
+    ap.add_argument("--scene-points", type=int, default=4096, help="points per scene object")
+    ap.add_argument("--chi-scan-check", type=int, default=1,
+                    help="compare the sharded ChiSquared search with the unsharded exact SCAN on this many clouds' queries")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from pcdb200 import api, sharded, synth, train
+    import bench
+    from pcdb200 import api, synth
+    from pcdb200.structs import DIST_CHISQUARED, DIST_EUCLIDEAN, KNN_SCAN
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION prints a banner on stdout; keep it to the JSON line
-    if os.environ.get("PCDB_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["PCDB_NCCL_DEBUG"]
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo")
 
-    wl = synth.WORKLOADS["c4"]
-    prm = synth.workload_params("c4", knn_k=2)
-    n_cls, P = 6, 4096
-    full = api.Context(prm, device=local)
-    tr_cls = [c for c in range(n_cls) for _ in range(args.train_per_class)]
-    x, n, c, o = synth.make_clouds(tr_cls, [4000 + i for i in range(len(tr_cls))], P, scale=wl["scale"])
-    fx, fl, fd, foff = full.compute_features(x, n, c, o)
-    bbs = np.stack([train.aabb(x[o[i]:o[i + 1]]) for i in range(len(tr_cls))])
-    cb = train.train_codebook(full, prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), bbs, n_cls)
-    full.set_codebook(cb)
-    bounds = sharded.shard_bounds(cb.N, world)
+    full = api.Context(device=local)
+    t0 = time.time()
+    wl, prm, cb = bench.build_world("c4", args.words if args.words > 0 else 0, full, rank_log=(rank == 0))
+    setup_s = time.time() - t0
+    bounds = shard_bounds(cb.N, world)
     lo, hi = bounds[rank], bounds[rank + 1]
-    shard = api.Context(prm, cb.rows(lo, hi), device=local, row_base=lo)
+    sh = api.Context(prm, device=local)
+    new_comm(sh, rank, world, dist, api)
+    sh.set_codebook_sharded(cb, lo, hi)
+    info = sh.comm_info()
 
-    te = [c % n_cls for c in range(12)]
-    xt, nt, ct, ot = synth.make_clouds(te, [9000 + i for i in range(len(te))], P, scale=wl["scale"])
+    # this rank's own test clouds (different on every rank, different counts too: ragged all-gather)
+    n_te = args.clouds + (rank % 2)
+    te = [(rank * 5 + c) % wl["n_classes"] for c in range(n_te)]
+    xt, nt, ct, ot = synth.make_clouds(te, [9000 + rank * 100 + i for i in range(n_te)], wl["P"], scale=wl["scale"],
+                                       jitter=0.002)
     tx, tl, td, toff = full.compute_features(xt, nt, ct, ot)
+    res = {"world": world, "codewords": int(cb.N), "D": int(cb.D), "rows_this_rank": [int(lo), int(hi)],
+           "queries_rank0": int(td.shape[0]), "nccl_version": info["nccl_version"], "setup_seconds": setup_s}
+    ok = {}
 
+    def same(a, b):
+        return bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+                    and np.array_equal(a[2], b[2]))
+
+    # ---- 1a. activation: k = 2, Euclidean
+    ok["knn_k2_l2"] = same(sh.knn(td, k=2, dist_type=DIST_EUCLIDEAN), full.knn(td, k=2, dist_type=DIST_EUCLIDEAN))
+    # ---- 1b. the distance-ratio test needs the GLOBAL second neighbour
+    rp = prm.copy()
+    rp.use_distance_ratio, rp.distance_ratio_threshold = 1, 0.8
+    sh.set_params(rp), full.set_params(rp)
+    a, b = sh.knn(td, k=1, dist_type=DIST_EUCLIDEAN), full.knn(td, k=1, dist_type=DIST_EUCLIDEAN)
+    ok["knn_ratio_l2"] = same(a, b) and bool((b[2] == 0).any()) and bool((b[2] == 1).any())
+    sh.set_params(prm), full.set_params(prm)
+    # ---- 1c. ChiSquared (tensor-core sandwich on every shard) vs the unsharded sandwich and vs the unsharded exact scan
+    a = sh.knn(td, k=2, dist_type=DIST_CHISQUARED)
+    ok["knn_k2_chi2"] = same(a, full.knn(td, k=2, dist_type=DIST_CHISQUARED))
+    nq = int(toff[min(args.chi_scan_check, n_te)])
+    # every rank must take part in the collective even when it checks fewer queries: run the scan on the full context only
+    s_idx, s_dst, s_cnt = full.knn(td[:nq], k=2, dist_type=DIST_CHISQUARED, mode=KNN_SCAN)
+    ok["knn_k2_chi2_vs_scan"] = same((a[0][:nq], a[1][:nq], a[2][:nq]), (s_idx, s_dst, s_cnt))
+
+    # ---- 1d. the fused path: this rank's clouds through the sharded codebook
     torch.cuda.synchronize()
     dist.barrier()
-    t0 = time.perf_counter()
-    idx, dst, cnt = sharded.sharded_knn(shard, td, 2, prm.distance_type, device=dev)
-    votes, voff = sharded.sharded_cast_votes(shard, lo, hi, tx, tl, toff, idx, dst, cnt, device=dev)
-    mx, moff, _, _ = full.find_maxima(votes, voff)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    sh.reset_stats()
+    t1 = time.perf_counter()
+    labels, mx, moff = sh.classify_batch(xt, nt, ct, ot)
+    dt = time.perf_counter() - t1
+    st = sh.stats()
+    votes, voff = sh.get_votes(n_te, int(st["n_votes"]) + 16)
+    rlabels, rmx, rmoff = full.classify_batch(xt, nt, ct, ot)
+    rvotes, rvoff = full.get_votes(n_te, len(votes) + 16)
+    ok["labels"] = bool(np.array_equal(labels, rlabels))
+    ok["maxima"] = bool(np.array_equal(moff, rmoff) and mx.tobytes() == rmx.tobytes())
+    ok["votes"] = bool(np.array_equal(voff, rvoff) and votes.tobytes() == rvotes.tobytes() and len(votes) > 0)
+    res.update({"sharded_classify_seconds_rank0": dt, "exchange_ms_rank0": st["comm_ms"],
+                "nvlink_bytes_received_rank0": int(st["comm_bytes"]), "labels": labels.tolist(), "truth": te,
+                "knn_fallback_queries": int(st["knn_fallback_queries"])})
+    # an empty batch on one rank must not break the collective
+    e = np.zeros((0, 3), np.float32)
+    if rank == world - 1:
+        l0, _, _ = sh.classify_batch(e, e, np.zeros(0, np.uint32), np.array([0], np.int64))
+        ok["empty_rank"] = len(l0) == 0
+    else:
+        l1, _, _ = sh.classify_batch(xt, nt, ct, ot)
+        ok["empty_rank"] = bool(np.array_equal(l1, rlabels))
 
-    ridx, rdst, rcnt = full.knn(td, k=2)
-    ok_knn = bool(np.array_equal(idx, ridx) and np.array_equal(dst.view(np.uint32), rdst.view(np.uint32))
-                  and np.array_equal(cnt, rcnt))
-    rvotes, rvoff = full.cast_votes(tx, tl, toff, ridx, rdst, rcnt)
-    ok_votes = bool(np.array_equal(voff, rvoff))
-    for b in range(len(toff) - 1):
-        a = np.sort(votes[voff[b]:voff[b + 1]].view(np.uint8).reshape(-1, 80), axis=0)
-        r = np.sort(rvotes[rvoff[b]:rvoff[b + 1]].view(np.uint8).reshape(-1, 80), axis=0)
-        ok_votes = ok_votes and bool(np.array_equal(a, r))
-    rmx, rmoff, _, _ = full.find_maxima(rvotes, rvoff)
-    labels = np.array([mx["class_id"][moff[b]] if moff[b + 1] > moff[b] else -1 for b in range(len(te))])
-    rlabels = np.array([rmx["class_id"][rmoff[b]] if rmoff[b + 1] > rmoff[b] else -1 for b in range(len(te))])
-    ok_labels = bool(np.array_equal(labels, rlabels))
-    ok_oracle = None
-    if rank == 0:
-        from oracle import oracle_py as orc
-        orc.set_num_threads(os.cpu_count() or 1)
-        m = orc.Model(prm, cb)
-        oidx, odst, ocnt = m.knn(td[:64], k=2)
-        ok_oracle = bool(np.array_equal(idx[:64], oidx) and np.array_equal(cnt[:64], ocnt))
-
-    # C5: one scene, keypoints sharded over the ranks, votes all-gathered; must equal the single-GPU fused path
+    # ---- 2. one scene, keypoints sharded over the ranks, votes all-gathered in the library
     sprm = synth.workload_params("c4", knn_k=1, single_object_mode=0, min_votes_threshold=3)
     full.set_params(sprm)
-    sx_, sn_, sc_, truth = synth.make_scene([0, 1, 2, 3, 4, 5], 21, P, scale=wl["scale"], plane_points=30000,
-                                            clutter_points=5000)
+    sx_, sn_, sc_, _ = synth.make_scene([0, 1, 2, 3, 4, 5], 21, args.scene_points, scale=wl["scale"],
+                                        plane_points=30000, clutter_points=5000)
     soff_ = np.array([0, len(sx_)], np.int64)
+    _, rmx2, rmoff2 = full.classify_batch(sx_, sn_, sc_, soff_)
+    rv2, rvoff2 = full.get_votes(1, int(1e6))
+    new_comm(full, rank, world, dist, api)
+    full.comm_shard_keypoints(True)
     torch.cuda.synchronize()
     dist.barrier()
-    t1 = time.perf_counter()
-    sv, svoff = sharded.sharded_scene_votes(full, sprm, sx_, sn_, sc_, device=dev)
-    smx, smoff, _, _ = full.find_maxima(sv, svoff)
-    torch.cuda.synchronize()
-    dt_scene = time.perf_counter() - t1
-    _, rmx2, rmoff2 = full.classify_batch(sx_, sn_, sc_, soff_)
-    rv2, rvoff2 = full.get_votes(1, len(sv) + 16)
-    ok_scene = bool(np.array_equal(svoff, rvoff2) and sv.tobytes() == rv2.tobytes() and len(sv) > 0
-                    and np.array_equal(smoff, rmoff2) and np.array_equal(smx["class_id"], rmx2["class_id"])
-                    and np.array_equal(smx["weight"].view(np.uint32), rmx2["weight"].view(np.uint32)))
-    full.set_params(prm)
+    full.reset_stats()
+    t2 = time.perf_counter()
+    _, smx, smoff = full.classify_batch(sx_, sn_, sc_, soff_)
+    dt_scene = time.perf_counter() - t2
+    sst = full.stats()
+    sv, svoff = full.get_votes(1, len(rv2) + 16)
+    ok["scene"] = bool(np.array_equal(svoff, rvoff2) and sv.tobytes() == rv2.tobytes() and len(sv) > 0
+                       and np.array_equal(smoff, rmoff2) and smx.tobytes() == rmx2.tobytes())
+    full.comm_shard_keypoints(False)
+    res.update({"scene_points": int(len(sx_)), "scene_votes": int(len(sv)), "scene_maxima": int(smoff[1]),
+                "scene_seconds_rank0": dt_scene, "scene_keypoints_this_rank": int(sst["n_keypoints"]),
+                "scene_vote_gather_ms_rank0": sst["comm_ms"]})
 
-    flags = torch.tensor([int(ok_knn), int(ok_votes), int(ok_labels), int(ok_scene)], device=dev)
+    names = sorted(ok)
+    flags = torch.tensor([int(bool(ok[n])) for n in names])
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    res = {"world": world, "codewords": int(cb.N), "D": int(cb.D), "queries": int(td.shape[0]), "k": 2,
-           "knn_identical": bool(flags[0].item()), "votes_identical": bool(flags[1].item()),
-           "labels_identical": bool(flags[2].item()), "knn_vs_oracle_first64": ok_oracle,
-           "scene_keypoint_sharding_identical_to_one_gpu": bool(flags[3].item()), "scene_points": int(len(sx_)),
-           "scene_votes": int(len(sv)), "scene_maxima": int(smoff[1]), "scene_seconds_rank0": dt_scene,
-           "labels": labels.tolist(), "truth": te, "sharded_path_seconds_rank0": dt}
+    res["identical_to_unsharded"] = {n: bool(f) for n, f in zip(names, flags.tolist())}
+    res["this_rank"] = {n: bool(ok[n]) for n in names}
     if rank == 0:
         print(json.dumps(res), flush=True)
         if args.out:
             with open(args.out, "w") as f:
                 json.dump(res, f)
+    elif not all(ok.values()):
+        print("rank %d: %s" % (rank, {n: bool(ok[n]) for n in names}), file=sys.stderr, flush=True)
     dist.barrier()
-    dist.destroy_process_group()
-    shard.close()
+    sh.close()
     full.close()
-    ok = (res["knn_identical"] and res["votes_identical"] and res["labels_identical"] and ok_oracle in (None, True)
-          and res["scene_keypoint_sharding_identical_to_one_gpu"])
-    return 0 if ok else 1
+    dist.destroy_process_group()
+    return 0 if all(res["identical_to_unsharded"].values()) else 1
 
 
 if __name__ == "__main__":

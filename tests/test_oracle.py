@@ -497,3 +497,24 @@ def test_oracle_reproduces_the_committed_path_fixture(orc):
     labels, mx, moff = m.classify_batch(xt, nt, rt, ot)
     assert labels.tolist() == G["labels"].tolist() == te_cls
     assert np.array_equal(moff, G["maxima_off"]) and mx.tobytes() == G["maxima"].tobytes()
+
+
+def test_pruned_exact_search_equals_the_linear_scan(orc, small_world):
+    """oracle_py.knn_exact_pruned (sgemm proposals + FLANN-order functor, used by bench.py to check >= 64 labels at the
+    1 M-word scale) must return exactly what the linear scan returns: rows, distance bits, counts — both functors — and
+    classify_batch_pruned the same labels as classify_batch."""
+    prm, cb = small_world["prm"], small_world["cb"]
+    m = orc.Model(prm, cb)
+    _, _, fd, _ = small_world["feats"]
+    xt, nt, rt, ot, _ = small_world["test"]
+    q = orc.compute_features(prm, xt, nt, rt, ot)[2][:300]
+    q = np.concatenate([q, fd[:20]])  # exact hits (distance 0) included
+    for dist_type in (0, 1):
+        for k in (1, 3):
+            a = orc.knn_exact_pruned(m, q, k=k, dist_type=dist_type)
+            b = m.knn(q, k=k, dist_type=dist_type)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+            assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    lab = orc.classify_batch_pruned(m, xt, nt, rt, ot)
+    ref, _, _ = m.classify_batch(xt, nt, rt, ot, want_maxima=False)
+    assert np.array_equal(lab, ref)

@@ -1,65 +1,64 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: test-set sharding needs no exchange; the row-sharded
-codebook path (all-gather of per-shard top-k + merge, owner casts votes) must reproduce the unsharded result.
-The GPU calls are replaced by the oracle (test infrastructure) — the collective logic under test is the product's."""
+"""World-size-2 gloo tests (CPU) of the multi-GPU exchange protocol.  csrc/comm.cu runs the protocol on the device over
+NCCL (tests/run_sharded_nccl.py checks that on real GPUs); here the SAME steps — ragged query all-gather, per-shard
+search of all queries for K = k (+1 with the ratio test), exchange of the (distance, global row) lists, per-query merge
+with ties -> lower row, then activateKNN's N <= k and distance-ratio semantics — are restated on the host with the
+oracle standing in for the per-shard search, and must reproduce the unsharded oracle bit for bit.  Test-set sharding
+(the default multi-GPU mode) needs no exchange and is checked too."""
 import os
 import sys
 
 import numpy as np
-import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class OracleShardCtx:
-    """One codebook shard served by the oracle, with global row ids (stands in for api.Context on CPU)."""
+def _gather_np(arr, dist, torch):
+    """Ragged all-gather of equally typed numpy arrays (first axis ragged)."""
+    objs = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, np.ascontiguousarray(arr))
+    return objs
 
-    def __init__(self, orc, prm, cb_full, lo, hi):
-        self.orc, self.lo, self.hi = orc, lo, hi
-        self.cb = cb_full.rows(lo, hi)
-        self.m = orc.Model(prm, self.cb)
 
-    def knn(self, q, k=None, dist_type=None, mode=0):
-        idx, d, c = self.m.knn(q, k=k, dist_type=dist_type)
-        return np.where(idx >= 0, idx + self.lo, -1).astype(np.int32), d, c
-
-    def merge_topk(self, i, d):
-        return self.orc.merge_topk(i, d)
-
-    # stage entry points used by the keypoint-sharded scene path
-    def voxel_keypoints(self, xyz, rgb, off, leaf):
-        return self.orc.voxel_keypoints(xyz, rgb, off, leaf)
-
-    def shot_lrf(self, sx, soff, kx, koff, radius):
-        return self.orc.shot_lrf(sx, soff, kx, koff, radius)
-
-    def shot_describe(self, ft, sx, sn, sc, soff, kx, kc, lrf, koff, radius):
-        return self.orc.shot_describe(ft, sx, sn, sc, soff, kx, kc, lrf, koff, radius)
-
-    def find_maxima(self, votes, voff):
-        return self.m.find_maxima(votes, voff)
-
-    def cast_votes(self, fx, fl, foff, idx, dst, cnt):
-        # the oracle has no mask support: cast per (feature, j) for owned rows only
-        local = np.where(idx >= 0, idx - self.lo, -1).astype(np.int32)
-        votes, off = [], [0]
-        from pcdb200.structs import VOTE_DTYPE
-        B = len(foff) - 1
-        for b in range(B):
-            for f in range(int(foff[b]), int(foff[b + 1])):
-                for j in range(int(cnt[f])):
-                    if local[f, j] < 0:
-                        continue
-                    v, _ = self.m.cast_votes(fx[f:f + 1], fl[f:f + 1], [0, 1], local[f:f + 1, j:j + 1], dst[f:f + 1, j:j + 1],
-                                             np.ones(1, np.int32))
-                    votes.append(v)
-            off.append(sum(len(v) for v in votes))
-        return (np.concatenate(votes) if votes else np.zeros(0, VOTE_DTYPE)), np.asarray(off, np.int64)
+def protocol_knn(shard_model, row_lo, n_total, queries, k, dist_type, use_ratio, ratio_thr, dist, torch):
+    """Host model of comm.cu:stage_knn_sharded for this rank's `queries`."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    parts = _gather_np(queries, dist, torch)                       # every rank sees every query
+    counts = [len(p) for p in parts]
+    q_all = np.concatenate(parts)
+    K = k + 1 if use_ratio else k
+    idx, dst, cnt = shard_model.knn(q_all, k=K, dist_type=dist_type)  # no ratio test on a shard
+    j = np.arange(K)[None, :]
+    valid = (j < cnt[:, None]) & (idx >= 0)
+    idx = np.where(valid, idx + row_lo, -1).astype(np.int32)       # global row ids
+    dst = np.where(valid, dst, np.inf).astype(np.float32)
+    lists = _gather_np(np.stack([idx.astype(np.int64), dst.view(np.uint32).astype(np.int64)], -1), dist, torch)
+    o = sum(counts[:rank])
+    mine = np.stack([p[o:o + counts[rank]] for p in lists])         # [world][Q_local][K][2] — what the all-to-all delivers
+    Q = counts[rank]
+    out_i = np.full((Q, k), -1, np.int32)
+    out_d = np.full((Q, k), np.nan, np.float32)
+    out_c = np.zeros(Q, np.int32)
+    by_row = n_total <= k
+    for q in range(Q):
+        cand = [(np.array([d], np.uint32).view(np.float32)[0], int(i))
+                for s in range(world) for i, d in mine[s, q] if i >= 0]
+        cand.sort(key=(lambda t: t[1]) if by_row else (lambda t: (t[0], t[1])))
+        cand = cand[:K]
+        use = min(len(cand), k)
+        if not by_row and use_ratio and k == 1 and len(cand) >= 2:
+            if np.float32(cand[0][0]) / np.float32(cand[1][0]) > np.float32(ratio_thr):
+                use = 0
+        for t in range(use):
+            out_d[q, t], out_i[q, t] = cand[t]
+        out_c[q] = n_total if by_row else use
+    return out_i, out_d, out_c
 
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
+    import torch
     import torch.distributed as dist
     from oracle import oracle_py as orc
     from pcdb200 import sharded, synth
@@ -73,49 +72,89 @@ def _worker(rank, world, port, q):
         fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
         bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(5)])
         cb = orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(5)), bb, 3)
-        xt, nt, rt, ot = synth.make_clouds([0, 1, 2], [700, 701, 702], 900)
+        # every rank has its OWN test clouds (ragged: rank 0 two clouds, rank 1 three)
+        n_te = 2 + rank
+        xt, nt, rt, ot = synth.make_clouds(list(range(n_te)), [700 + 10 * rank + i for i in range(n_te)], 900)
         tx, tl, td, toff = orc.compute_features(prm, xt, nt, rt, ot)
         bounds = sharded.shard_bounds(cb.N, world)
-        ctx = OracleShardCtx(orc, prm, cb, bounds[rank], bounds[rank + 1])
-        idx, dst, cnt = sharded.sharded_knn(ctx, td, 2, prm.distance_type)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        shard = orc.Model(prm, cb.rows(lo, hi))
         full = orc.Model(prm, cb)
-        ridx, rdst, rcnt = full.knn(td, k=2)
-        ok = np.array_equal(idx, ridx) and np.array_equal(dst.view(np.uint32), rdst.view(np.uint32)) and np.array_equal(cnt, rcnt)
-        votes, voff = sharded.sharded_cast_votes(ctx, bounds[rank], bounds[rank + 1], tx, tl, toff, idx, dst, cnt)
+        ok = True
+        for dist_type in (0, 1):
+            idx, dst, cnt = protocol_knn(shard, lo, cb.N, td, 2, dist_type, False, 0.0, dist, torch)
+            ridx, rdst, rcnt = full.knn(td, k=2, dist_type=dist_type)
+            ok = ok and np.array_equal(idx, ridx) and np.array_equal(dst.view(np.uint32), rdst.view(np.uint32)) \
+                and np.array_equal(cnt, rcnt)
+        # the k = 1 distance-ratio test needs the GLOBAL second neighbour: applied after the merge, never on a shard
+        rp = prm.copy()
+        rp.use_distance_ratio, rp.distance_ratio_threshold, rp.knn_k = 1, 0.8, 1
+        full_r = orc.Model(rp, cb)
+        idx, dst, cnt = protocol_knn(shard, lo, cb.N, td, 1, 0, True, 0.8, dist, torch)
+        ridx, rdst, rcnt = full_r.knn(td, k=1, dist_type=0)
+        ok = ok and np.array_equal(idx, ridx) and np.array_equal(cnt, rcnt) and 0 < int(rcnt.sum()) < len(rcnt)
+        ok = ok and np.array_equal(dst.view(np.uint32)[rcnt > 0], rdst.view(np.uint32)[rcnt > 0])
+        # the merged activation feeds the owner's (replicated) vote tables: votes equal the unsharded ones, in order
+        idx, dst, cnt = protocol_knn(shard, lo, cb.N, td, 2, 0, False, 0.0, dist, torch)
+        votes, voff = full.cast_votes(tx, tl, toff, idx, dst, cnt)
+        ridx, rdst, rcnt = full.knn(td, k=2, dist_type=0)
         rvotes, rvoff = full.cast_votes(tx, tl, toff, ridx, rdst, rcnt)
-        ok = ok and np.array_equal(voff, rvoff)
-        # same multiset of votes per cloud (order inside a cloud is rank-major)
-        for b in range(len(toff) - 1):
-            a = np.sort(votes[voff[b]:voff[b + 1]].view(np.uint8).reshape(-1, 80), axis=0)
-            r = np.sort(rvotes[rvoff[b]:rvoff[b + 1]].view(np.uint8).reshape(-1, 80), axis=0)
-            ok = ok and np.array_equal(a, r)
-        mx, moff, _, _ = full.find_maxima(votes, voff)
-        rmx, rmoff, _, _ = full.find_maxima(rvotes, rvoff)
-        ok = ok and np.array_equal(moff, rmoff) and np.array_equal(mx["class_id"], rmx["class_id"])
+        ok = ok and np.array_equal(voff, rvoff) and votes.tobytes() == rvotes.tobytes() and len(votes) > 0
+        # N_total <= k: every codeword, in id order (activation_strategy_knn.h:50-54)
+        tiny = cb.rows(0, 3)
+        tb = sharded.shard_bounds(3, world)
+        tshard = orc.Model(prm, tiny.rows(tb[rank], tb[rank + 1])) if tb[rank + 1] > tb[rank] else None
+
+        class _Empty:
+            def knn(self, qq, k=None, dist_type=None):
+                return (np.full((len(qq), k), -1, np.int32), np.full((len(qq), k), np.nan, np.float32),
+                        np.zeros(len(qq), np.int32))
+        idx, dst, cnt = protocol_knn(tshard or _Empty(), tb[rank], 3, td[:5], 4, 0, False, 0.0, dist, torch)
+        ridx, rdst, rcnt = orc.Model(prm, tiny).knn(td[:5], k=4, dist_type=0)
+        ok = ok and np.array_equal(idx[:, :3], ridx[:, :3]) and np.array_equal(cnt, rcnt) \
+            and np.array_equal(dst[:, :3].view(np.uint32), rdst[:, :3].view(np.uint32))
         # test-set sharding: ranks classify disjoint contiguous shards, labels concatenate to the unsharded answer
-        lab_all, _, _ = full.classify_batch(xt, nt, rt, ot, want_maxima=False)
-        B = len(ot) - 1
-        cuts = sharded.shard_bounds(B, world)
-        lo, hi = cuts[rank], cuts[rank + 1]
-        lab, _, _ = full.classify_batch(xt[ot[lo]:ot[hi]], nt[ot[lo]:ot[hi]], rt[ot[lo]:ot[hi]], ot[lo:hi + 1] - ot[lo],
-                                        want_maxima=False) if hi > lo else (np.zeros(0, np.int32), None, None)
-        ok = ok and np.array_equal(lab, lab_all[lo:hi])
-        # one scene, keypoints sharded over the ranks (C5): the gathered votes are the single-rank votes, bit for bit
+        xa, na, ra, oa = synth.make_clouds([0, 1, 2], [800, 801, 802], 900)
+        lab_all, _, _ = full.classify_batch(xa, na, ra, oa, want_maxima=False)
+        cuts = sharded.shard_bounds(3, world)
+        a, b = cuts[rank], cuts[rank + 1]
+        lab, _, _ = full.classify_batch(xa[oa[a]:oa[b]], na[oa[a]:oa[b]], ra[oa[a]:oa[b]], oa[a:b + 1] - oa[a],
+                                        want_maxima=False) if b > a else (np.zeros(0, np.int32), None, None)
+        ok = ok and np.array_equal(lab, lab_all[a:b])
+        # one scene, keypoints sharded contiguously over the ranks (C5): the rank-ordered concatenation of the slices'
+        # votes is the single-rank vote list, bit for bit
         sprm = synth.workload_params("c2", knn_k=2, single_object_mode=0, min_votes_threshold=3)
         sx_, sn_, sc_, _ = synth.make_scene([0, 1, 2], 5, 900, plane_points=1500, clutter_points=300)
         sx_[7] = np.nan
-        whole = OracleShardCtx(orc, sprm, cb, 0, cb.N)
-        sv, svoff = sharded.sharded_scene_votes(whole, sprm, sx_, sn_, sc_)
+        sm = orc.Model(sprm, cb)
+        fin = np.isfinite(sx_).all(1)
+        pts, col, nr = sx_[fin], sc_[fin], sn_[fin]
+        kp, kr, _ = orc.voxel_keypoints(pts, col, [0, len(pts)], sprm.leaf_size)
+        cuts = sharded.shard_bounds(len(kp), world)
+        a, b = cuts[rank], cuts[rank + 1]
+        surf = np.isfinite(nr).all(1)
+        sxx, snn, scc, soff = pts[surf], nr[surf], col[surf], [0, int(surf.sum())]
+        kx, kc = kp[a:b], kr[a:b]
+        lrf = orc.shot_lrf(sxx, soff, kx, [0, len(kx)], sprm.lrf_radius)
+        good = np.isfinite(lrf[:, 0]) & np.isfinite(lrf[:, 3]) & np.isfinite(lrf[:, 6])
+        kx, kc, lrf = kx[good], kc[good], lrf[good]
+        desc = orc.shot_describe(sprm.feature_type, sxx, snn, scc, soff, kx, kc, lrf, [0, len(kx)], sprm.feature_radius)
+        good = ~np.isnan(desc).any(1)
+        kx, lrf, desc = kx[good], lrf[good], desc[good]
+        i1, d1, c1 = sm.knn(desc, k=2)
+        v_mine, _ = sm.cast_votes(kx, lrf, [0, len(kx)], i1, d1, c1)
+        parts = _gather_np(v_mine, dist, torch)
+        sv = np.concatenate(parts)
         fx1, fl1, fd1, fo1 = orc.compute_features(sprm, sx_, sn_, sc_, [0, len(sx_)])
-        i1, d1, c1 = orc.Model(sprm, cb).knn(fd1, k=2)
-        rv, rvo = orc.Model(sprm, cb).cast_votes(fx1, fl1, fo1, i1, d1, c1)
-        ok = ok and np.array_equal(svoff, rvo) and sv.tobytes() == rv.tobytes() and len(sv) > 0
+        i1, d1, c1 = sm.knn(fd1, k=2)
+        rv, rvo = sm.cast_votes(fx1, fl1, fo1, i1, d1, c1)
+        ok = ok and sv.tobytes() == rv.tobytes() and len(sv) > 0
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-def test_world2_sharded_codebook_and_test_set():
+def test_world2_exchange_protocol_matches_the_unsharded_oracle():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
