@@ -298,10 +298,10 @@ def merge_topk(cand_idx, cand_dist):
     return idx, dist
 
 
-def knn_exact_pruned(model, queries, k=1, dist_type=0, chunk=512):
+def knn_exact_pruned(model, queries, k=1, dist_type=0, chunk=320):
     """The exact search of Model.knn by a cheaper route, for label checks over many clouds at bench scale: a BLAS sgemm
     (squared-L2 expansion; for chi^2 the Hellinger sandwich H^2 <= chi^2 <= 2 H^2 on sqrt rows) proposes every row that
-    can still be among the k best given a rigorous bound on the sgemm's rounding, and the FLANN-order functor
+    can still be among the k best given a rigorous bound on the fp32 rounding, and the FLANN-order functor
     (orc_distance) decides among them by (distance, row).  Same result as the linear scan by construction; the CPU test
     suite checks it against Model.knn.  (k+1)-th neighbour / ratio test are not handled: callers pass plain k."""
     cb = model.cb
@@ -309,44 +309,52 @@ def knn_exact_pruned(model, queries, k=1, dist_type=0, chunk=512):
     Q = f32(queries)
     D = W.shape[1]
     chi = dist_type == 1
+    if chi and ((W < 0).any() or (Q < 0).any()):
+        return model.knn(Q, k=k, dist_type=dist_type)
     cache = getattr(model, "_pruned_cache", None)
     if cache is None or cache[0] != chi:
-        Wt = np.sqrt(np.maximum(W, 0)) if chi else W
-        cache = (chi, np.ascontiguousarray(Wt), (Wt.astype(np.float64) ** 2).sum(1))
+        Wt = np.sqrt(W) if chi else W
+        wn = (Wt.astype(np.float64) ** 2).sum(1)
+        cache = (chi, np.ascontiguousarray(Wt.T), wn.astype(np.float32), float(np.sqrt(wn.max())), float(wn.max()))
         model._pruned_cache = cache
-    _, Wt, wn = cache
+    _, WtT, wn32, wmax, wn_max = cache
     idx_out = np.full((len(Q), k), -1, np.int32)
     dst_out = np.full((len(Q), k), np.nan, np.float32)
     cnt_out = np.zeros(len(Q), np.int32)
-    if chi and ((W < 0).any() or (Q < 0).any()):
-        return model.knn(Q, k=k, dist_type=dist_type)
     u = 2.0 ** -24
-    wmax = float(np.sqrt(wn.max()))
+    try:
+        from threadpoolctl import threadpool_limits
+        limit = threadpool_limits(limits=os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    except Exception:
+        limit = None
     for s in range(0, len(Q), chunk):
         q = Q[s:s + chunk]
         qt = np.sqrt(q) if chi else q
         qn = (qt.astype(np.float64) ** 2).sum(1)
-        dot = qt @ Wt.T                                            # fp32 sgemm
-        approx = qn[:, None] + wn[None, :] - 2.0 * dot.astype(np.float64)
-        # |fl(q.c) - q.c| <= gamma_D |q||c| for any summation order, gamma_D = D u / (1 - D u); x2 in the distance; the
-        # fp32 sqrt adds 2^-23 (|s|+|t|)^2
-        eps = 2.0 * (D * u / (1 - D * u)) * np.sqrt(qn) * wmax * 1.01 + (2.0 ** -22) * (np.sqrt(qn) + wmax) ** 2
-        kth = np.partition(approx, k - 1, axis=1)[:, k - 1]
+        a = qt @ WtT                                               # fp32 sgemm, [chunk, N]
+        a *= np.float32(-2.0)
+        a += wn32[None, :]                                         # |c|^2 - 2 q.c (the per-query |q|^2 is a constant)
+        # |fl(q.c) - q.c| <= gamma_D |q||c| for any summation order (gamma_D = D u / (1 - D u)), doubled in the distance;
+        # three fp32 roundings of values up to |c|^2 + 2|q||c|; the fp32 sqrt adds 2^-23 (|s|+|t|)^2
+        eps = (2.0 * (D * u / (1 - D * u)) * np.sqrt(qn) * wmax * 1.01 + 4 * u * (wn_max + 2 * np.sqrt(qn) * wmax)
+               + (2.0 ** -22) * (np.sqrt(qn) + wmax) ** 2)
+        kth = a.min(axis=1) if k == 1 else np.partition(a, k - 1, axis=1)[:, k - 1]
         for i in range(len(q)):
             if chi:
                 # U = k-th smallest exact chi^2 among the k approx-nearest rows bounds the k-th smallest overall
-                near = np.argpartition(approx[i], k - 1)[:k]
+                near = np.argpartition(a[i], k - 1)[:k] if k > 1 else np.array([int(np.argmin(a[i]))])
                 U = float(np.sort(distance(W[near], np.repeat(q[i:i + 1], len(near), 0), 1))[k - 1])
-                thr = U * (1 + 1.01 * (D + 8) * u) + eps[i]
+                thr = U * (1 + 1.01 * (D + 8) * u) - qn[i] + eps[i]
             else:
-                thr = kth[i] + 2 * eps[i]
-            cand = np.nonzero(approx[i] <= thr)[0]
+                thr = float(kth[i]) + 2 * eps[i]
+            cand = np.nonzero(a[i] <= np.float32(thr) + np.float32(1e-30))[0]
             ex = distance(W[cand], np.repeat(q[i:i + 1], len(cand), 0), dist_type)  # functor(codeword, query)
             order = np.lexsort((cand, ex))[:k]
             n = len(order)
             idx_out[s + i, :n] = cand[order]
             dst_out[s + i, :n] = ex[order]
             cnt_out[s + i] = n
+    del limit
     return idx_out, dst_out, cnt_out
 
 

@@ -63,7 +63,7 @@ constexpr int MAX_STAGES = 7;
 constexpr unsigned kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's even CTA
 constexpr int KB_RES_MAX = 6;             // resident K-blocks (D + 16 <= 384)
 constexpr int K_AUG = 16;                 // extra K columns carrying the |c|^2 term (one UMMA_K step)
-constexpr int CAND_CAP = 64;              // candidates per (query, codebook split)
+constexpr int CAND_CAP_MAX = 256;         // private staging entries per epilogue thread (64 / 128 / 256 by K)
 constexpr unsigned TMEM_COLS = 512;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -220,12 +220,13 @@ struct GemmArgs {
   int n_mpairs, n_ntiles, tiles_per_split, n_splits;  // n_mpairs: 256-query tile pairs
   const float* cnorm;    // streaming-query variant only: |c|^2, padded to a multiple of BN with +inf
   const float* margin;   // per query: 2 * (bound on |approx - exact|)
-  int cand_cap;          // capacity of one shared list: CAND_CAP x (slices of one query tile that can be in flight at once)
+  int cand_cap;          // capacity of one shared list: stage_cap x (slices of one query tile that can be in flight at once)
   int* cand_idx;         // [Q][2][cand_cap]: one list per (query, column half), shared by all codebook slices
   float* cand_apx;
   int* cand_cnt;         // [2][Q], appended with atomics (zeroed before the launch)
   float* bound;          // [Q] running upper bound on the k-th best approximate distance (+inf before the launch)
-  int2* stage;           // [CTAs][EPI_THREADS][CAND_CAP] private staging lists of the epilogue threads
+  int2* stage;           // [CTAs][EPI_THREADS][stage_cap] private staging lists of the epilogue threads
+  int stage_cap;         // entries of one private list: 64 for K <= 4, 128 for K <= 8, 256 beyond (longer staircases)
   // POOL variant (second pass of the chi^2 sandwich): `margin` holds a FIXED per-query threshold on the accumulator
   // (-inf = skip the query) and every column at or below it is appended to one global pool of (query, row) pairs
   int2* pool_rc;         // (row, accumulator bits)
@@ -409,7 +410,8 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // to the query's shared list at the end of the unit with ONE atomic reservation: a returning global atomic per
       // append put a ~1 us round trip into the filter loop (C4: 1724 -> 1412 TFLOP/s).
       int cnt = 0;
-      int2* stage = g.stage + ((size_t)blockIdx.x * EPI_THREADS + (size_t)((warp - 4) * 32 + lane)) * CAND_CAP;
+      int2* stage = g.stage + ((size_t)blockIdx.x * EPI_THREADS + (size_t)((warp - 4) * 32 + lane)) * g.stage_cap;
+      const int stage_cap = g.stage_cap;
       // Streaming-query variant (D = 1344): the operands are not augmented (a 17th partial K block would cost a full
       // 64 KB stage per tile pair on a kernel that already sits on the L2->SM limit), so |c|^2 is added here from a
       // shared-memory staged tile, one column per epilogue thread, software-prefetched.
@@ -456,12 +458,12 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         if (d <= thr && active && n_base + e < g.N) {                                              \
           if (POOL) {                                                                              \
             stage[cnt] = make_int2(n_base + e, __float_as_int(d));                                 \
-            if (++cnt == CAND_CAP) {                                                               \
+            if (++cnt == stage_cap) {                                                              \
               pool_flush(g, row, stage, cnt);                                                      \
               cnt = 0;                                                                             \
             }                                                                                      \
           } else {                                                                                 \
-            if (cnt < CAND_CAP) stage[cnt] = make_int2(n_base + e, __float_as_int(d));             \
+            if (cnt < stage_cap) stage[cnt] = make_int2(n_base + e, __float_as_int(d));            \
             ++cnt;                                                                                 \
             float x = d;                                                                           \
             _Pragma("unroll") for (int i = 0; i < KT; ++i) {                                       \
@@ -499,9 +501,9 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         if (best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
         // a staging list that overflowed, or a shared list above its capacity, marks the query for the exact-scan
         // fallback (the count is pushed past any capacity)
-        const int base = atomicAdd(g.cand_cnt + (size_t)half * g.Q + row, cnt > CAND_CAP ? (1 << 24) : cnt);
+        const int base = atomicAdd(g.cand_cnt + (size_t)half * g.Q + row, cnt > stage_cap ? (1 << 24) : cnt);
         const size_t cbase = ((size_t)row * 2 + half) * g.cand_cap;
-        for (int i = 0; i < min(cnt, CAND_CAP) && base + i < g.cand_cap; ++i) {
+        for (int i = 0; i < min(cnt, stage_cap) && base + i < g.cand_cap; ++i) {
           const int2 c = stage[i];
           g.cand_idx[cbase + base + i] = c.x;
           g.cand_apx[cbase + base + i] = __int_as_float(c.y);
@@ -935,7 +937,8 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   // Slices of one query tile run one after the other when there are more tile pairs than CTA pairs; with few queries
   // they run side by side, each starting from an empty bound and contributing its own descending staircase
   const int in_flight = std::min(S, (int)cdiv(max_pairs, g.n_mpairs));
-  g.cand_cap = CAND_CAP * std::max(1, in_flight);
+  g.stage_cap = K <= 4 ? 64 : (K <= 8 ? 128 : CAND_CAP_MAX);
+  g.cand_cap = g.stage_cap * std::max(1, in_flight);
   const size_t nc = (size_t)Q * S2 * g.cand_cap;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
   PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
@@ -948,7 +951,7 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   g.cand_cnt = w.cand_cnt.as<int>();
   PCDB_CUDA(gs->bound.ensure(sizeof(float) * (Q + 1)));
   g.bound = gs->bound.as<float>();
-  PCDB_CUDA(gs->stage.ensure(sizeof(int2) * (size_t)ctx->sm_count * EPI_THREADS * CAND_CAP));
+  PCDB_CUDA(gs->stage.ensure(sizeof(int2) * (size_t)ctx->sm_count * EPI_THREADS * CAND_CAP_MAX));
   g.stage = gs->stage.as<int2>();
   PCDB_CUDA(cudaMemsetAsync(w.cand_cnt.p, 0, sizeof(int) * (size_t)Q * S2, st));
   k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, Q, INFINITY);

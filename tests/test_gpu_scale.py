@@ -22,7 +22,7 @@ def _descriptor_codebook(api, name, n_words, n_test_clouds):
     ctx = api.Context(prm)
     probe = synth.make_clouds(list(range(4)), [10_000 + i for i in range(4)], wl["P"], scale=wl["scale"])
     per_cloud = max(1.0, ctx.compute_features(*probe)[0].shape[0] / 4)
-    n_clouds = int(np.ceil(n_words / per_cloud))
+    n_clouds = int(np.ceil(1.05 * n_words / per_cloud))
     rows = []
     for s in range(0, n_clouds, 256):
         m = min(256, n_clouds - s)
@@ -30,6 +30,7 @@ def _descriptor_codebook(api, name, n_words, n_test_clouds):
                                wl["P"], scale=wl["scale"])
         rows.append(ctx.compute_features(*cl)[2])
     W = np.concatenate(rows)[:n_words]
+    assert W.shape[0] >= 0.97 * n_words
     te = synth.make_clouds([i % wl["n_classes"] for i in range(n_test_clouds)],
                            [50_000_000 + i for i in range(n_test_clouds)], wl["P"], scale=wl["scale"])
     Q = ctx.compute_features(*te)[2]
@@ -88,7 +89,7 @@ def test_c3_headline_scale_gemm_equals_scan(api, orc):
 
 
 def test_c4_headline_scale_gemm_equals_scan(api, orc):
-    ctx, prm, cb, Q = _descriptor_codebook(api, "c4", 1_000_000, 12)
+    ctx, prm, cb, Q = _descriptor_codebook(api, "c4", 1_070_000, 12)
     assert cb.N >= 1_000_000 and Q.shape[0] >= 2_000 and Q.shape[1] == 1344
     Q = Q[:4096]
     a = ctx.knn(Q, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
