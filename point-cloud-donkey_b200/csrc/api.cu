@@ -9,6 +9,22 @@
 #include "common.cuh"
 #include "stages.h"
 
+#include <chrono>
+#include <cstdlib>
+
+void pcdb_trace_point(pcdb_ctx* ctx, const char* name) {
+  static const bool on = [] { const char* e = getenv("PCDB_TRACE"); return e && e[0] == '1'; }();
+  if (!on) return;
+  static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  const auto t_call = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(ctx->stream);
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[pcdb trace] %-28s host %8.3f ms, drain %8.3f ms\n", name,
+          std::chrono::duration<double, std::milli>(t_call - last).count(),
+          std::chrono::duration<double, std::milli>(now - t_call).count());
+  last = now;
+}
+
 namespace {
 
 thread_local std::string g_create_err;
@@ -94,7 +110,7 @@ __global__ void k_feat_valid(const float* __restrict__ lrf, const float* __restr
 __global__ void k_feat_compact(const float4* __restrict__ kp4, const int* __restrict__ kp_cloud,
                                const float* __restrict__ lrf, const float* __restrict__ desc, long long Q, int D,
                                const int* __restrict__ valid, const int* __restrict__ pos, float* fxyz, float* flrf,
-                               float* fdesc, int* fcloud) {
+                               float* fdesc, int* fcloud, int* fkp) {
   const long long q = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= Q || !valid[q]) return;
@@ -105,6 +121,7 @@ __global__ void k_feat_compact(const float4* __restrict__ kp4, const int* __rest
     fxyz[3 * o + 1] = k.y;
     fxyz[3 * o + 2] = k.z;
     fcloud[o] = kp_cloud[q];
+    fkp[o] = (int)q;  // the keypoint this feature came from (keypoint-sharded scenes restore the global vote order with it)
   }
   if (lane < 9) flrf[9 * o + lane] = lrf[9 * q + lane];
   for (int j = lane * 4; j < D; j += 128)
@@ -332,7 +349,9 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   *F_out = 0;
   *Q_out = 0;
+  pcdb_trace_point(ctx, "features: begin");
   PCDB_TRY(stage_compact(ctx, B, P, true, has_rgb));
+  pcdb_trace_point(ctx, "features: compact");
   int totals[2] = {0, 0};
   PCDB_TRY(download(ctx, &totals[0], w.pos_pt.as<int>() + P, sizeof(int)));
   PCDB_TRY(download(ctx, &totals[1], w.pos_sf.as<int>() + P, sizeof(int)));
@@ -346,6 +365,7 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   int err[4] = {0, 0, 0, 0};
   PCDB_TRY(download(ctx, err, w.err_flag.p, sizeof(err)));
   PCDB_CUDA(cudaStreamSynchronize(st));
+  pcdb_trace_point(ctx, "features: voxel keypoints");
   if (err[0] & 1)
     return ctx->fail(PCDB_E_INVALID, "Keypoints.LeafSize too small for the cloud extent (pcl::VoxelGrid index overflow)");
   if (err[0] & 2) return ctx->fail(PCDB_E_INVALID, "Features radius too small for the cloud extent");
@@ -361,10 +381,12 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
     return PCDB_OK;
   }
   PCDB_TRY(stage_grid(ctx, B, n_surf, Q, color));
+  pcdb_trace_point(ctx, "features: grid");
   PCDB_CUDA(w.lrf.ensure(sizeof(float) * 9 * Q));
   PCDB_CUDA(w.desc.ensure(sizeof(float) * (size_t)D * Q));
   PCDB_TRY(stage_shot(ctx, n_surf, Q, color, p.lrf_radius, p.feature_radius, true, true, nullptr, w.lrf.as<float>(),
                       w.desc.as<float>()));
+  pcdb_trace_point(ctx, "features: shot");
   PCDB_CUDA(w.feat_valid.ensure(sizeof(int) * (Q + 2)));
   PCDB_CUDA(w.feat_pos.ensure(sizeof(int) * (Q + 2)));
   k_feat_valid<<<cdiv((Q + 1) * 32, 256), 256, 0, st>>>(w.lrf.as<float>(), w.desc.as<float>(), Q, D,
@@ -383,15 +405,17 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   PCDB_CUDA(w.feat_lrf.ensure(sizeof(float) * 9 * (F + 1)));
   PCDB_CUDA(w.feat_desc.ensure(sizeof(float) * (size_t)D * (F + 1)));
   PCDB_CUDA(w.feat_cloud.ensure(sizeof(int) * (F + 1)));
+  PCDB_CUDA(w.feat_kp.ensure(sizeof(int) * (F + 1)));
   k_feat_compact<<<cdiv(Q * 32, 256), 256, 0, st>>>(w.kp4.as<float4>(), w.kp_cloud.as<int>(), w.lrf.as<float>(),
                                                     w.desc.as<float>(), Q, D, w.feat_valid.as<int>(),
                                                     w.feat_pos.as<int>(), w.feat_xyz.as<float>(),
                                                     w.feat_lrf.as<float>(), w.feat_desc.as<float>(),
-                                                    w.feat_cloud.as<int>());
+                                                    w.feat_cloud.as<int>(), w.feat_kp.as<int>());
   PCDB_LAUNCH_CHECK();
   k_offsets_from_pos<<<cdiv(B + 1, 128), 128, 0, st>>>(w.kp_off.as<long long>(), B, w.feat_pos.as<int>(),
                                                         w.feat_off.as<long long>());
   PCDB_LAUNCH_CHECK();
+  pcdb_trace_point(ctx, "features: compact features");
   *F_out = F;
   return PCDB_OK;
 }
@@ -993,14 +1017,17 @@ static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, bool has
   PCDB_TRY(activate(ctx, w.feat_desc.as<float>(), F, p.knn_k, p.distance_type, PCDB_KNN_AUTO,
                     p.use_distance_ratio != 0, p.distance_ratio_threshold));
   PCDB_CUDA(cudaEventRecord(ctx->ev[2], st));
+  pcdb_trace_point(ctx, "activation");
   int64_t V = 0;
   PCDB_TRY(stage_cast_votes(ctx, w.feat_xyz.as<float>(), w.feat_lrf.as<float>(), w.feat_off.as<long long>(),
                             w.feat_cloud.as<int>(), B, F, p.knn_k, &V));
-  if (comm_keypoints_sharded(ctx)) PCDB_TRY(stage_gather_votes(ctx, B, V, &V));
+  if (comm_keypoints_sharded(ctx)) PCDB_TRY(stage_gather_votes(ctx, B, F, p.knn_k, V, &V));
   PCDB_CUDA(cudaEventRecord(ctx->ev[3], st));
+  pcdb_trace_point(ctx, "votes");
   int64_t M = 0, members = 0;
   PCDB_TRY(stage_find_maxima(ctx, B, V, &M, &members));
   PCDB_CUDA(cudaEventRecord(ctx->ev[4], st));
+  pcdb_trace_point(ctx, "maxima");
   ctx->stats.n_votes += V;
   ctx->last_V = V;
   ctx->last_M = M;

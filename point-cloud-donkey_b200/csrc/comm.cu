@@ -83,10 +83,10 @@ struct CommState {
   ncclComm_t comm = nullptr;
   int rank = 0, n = 1;
   bool shard_keypoints = false;
-  DevBuf cnt_d, q_all, send, recv, votes_all;
+  DevBuf cnt_d, q_all, send, recv, votes_all, key_local, key_all, key_sorted, ord, ord_sorted;
   std::vector<int64_t> counts;
   ~CommState() {
-    DevBuf* all[] = {&cnt_d, &q_all, &send, &recv, &votes_all};
+    DevBuf* all[] = {&cnt_d, &q_all, &send, &recv, &votes_all, &key_local, &key_all, &key_sorted, &ord, &ord_sorted};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -188,12 +188,39 @@ __global__ void k_merge_pairs(const int2* __restrict__ recv, int n, long long Q,
   cnt_out[q] = by_row ? (int)n_total : use;
 }
 
-__global__ void k_slice_offsets(long long* kp_off, int B, long long lo, long long hi) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > B) return;
-  long long v = kp_off[b];
-  v = v < lo ? lo : (v > hi ? hi : v);
-  kp_off[b] = v - lo;
+// Keypoint sharding is BLOCK-CYCLIC: blocks of KP_BLOCK consecutive keypoints (voxel order: spatial neighbours, so a
+// block still shares its staged neighbourhood) go to the ranks round-robin.  A contiguous split hands one rank the dense
+// slab of a scene (the table) and the others wait for it: measured 12 ms vs 5.8 ms of work on two GPUs.
+constexpr int KP_BLOCK = 32;
+__host__ __device__ inline long long kp_global_index(long long local, int rank, int n) {
+  return ((local / KP_BLOCK) * n + rank) * KP_BLOCK + local % KP_BLOCK;
+}
+__global__ void k_slice_cyclic(const float4* __restrict__ kp4, const int* __restrict__ kp_cloud, long long n_local,
+                               int rank, int n, float4* kp4_out, int* kp_cloud_out) {
+  long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (l >= n_local) return;
+  const long long g = kp_global_index(l, rank, n);
+  kp4_out[l] = kp4[g];
+  kp_cloud_out[l] = kp_cloud[g];
+}
+// sort key of a vote = global index of the keypoint that cast it (votes of one rank are already ascending in it)
+__global__ void k_vote_keys(const int* __restrict__ vote_feat, const int* __restrict__ feat_kp, long long V, int rank,
+                            int n, unsigned* key) {
+  long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  key[v] = (unsigned)kp_global_index(feat_kp[vote_feat[v]], rank, n);
+}
+__global__ void k_iota(int* a, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int)i;
+}
+__global__ void k_permute_votes(const pcdb_vote* __restrict__ in, const int* __restrict__ order, long long V,
+                                pcdb_vote* out) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long v = t / 5;
+  if (v >= V) return;
+  const int part = (int)(t % 5);  // an 80-byte record = five 16-byte pieces
+  reinterpret_cast<float4*>(out + v)[part] = reinterpret_cast<const float4*>(in + order[v])[part];
 }
 
 }  // namespace
@@ -274,47 +301,72 @@ int stage_knn_sharded(pcdb_ctx* ctx, const float* queries_d, int64_t Q_local, in
   return PCDB_OK;
 }
 
-// keypoint-sharded scene: keep this rank's contiguous slice of the Q keypoints (kp4 / kp_cloud / kp_off)
+// keypoint-sharded scene: keep this rank's blocks of the Q keypoints (kp4 / kp_cloud / kp_off), B == 1
 int stage_slice_keypoints(pcdb_ctx* ctx, int B, int64_t Q, int64_t* Q_local_out) {
   CommState* c = comm_of(ctx);
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
-  const int64_t base = Q / c->n, rem = Q % c->n;
-  const int64_t lo = c->rank * base + std::min<int64_t>(c->rank, rem);
-  const int64_t hi = lo + base + (c->rank < rem ? 1 : 0);
-  const int64_t n = hi - lo;
-  if (lo > 0 && n > 0) {
-    // through a scratch buffer: source and destination ranges may overlap
+  if (B != 1) return ctx->fail(PCDB_E_UNSUPPORTED, "keypoint sharding handles one scene per call");
+  const int64_t full_blocks = Q / KP_BLOCK, tail = Q % KP_BLOCK;
+  int64_t n = (full_blocks / c->n) * KP_BLOCK;                 // whole rounds
+  const int64_t left = full_blocks % c->n;                     // blocks of the last, incomplete round
+  if (c->rank < left) n += KP_BLOCK;
+  if (c->rank == left) n += tail;                              // the partial block follows the last full one
+  if (n > 0) {
     PCDB_CUDA(w.kp_in.ensure(sizeof(float4) * (size_t)(n + 1)));
-    PCDB_CUDA(cudaMemcpyAsync(w.kp_in.p, w.kp4.as<float4>() + lo, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(w.feat_valid.ensure(sizeof(int) * (size_t)(n + 2)));
+    k_slice_cyclic<<<cdiv(n, 256), 256, 0, st>>>(w.kp4.as<float4>(), w.kp_cloud.as<int>(), n, c->rank, c->n,
+                                                 w.kp_in.as<float4>(), w.feat_valid.as<int>());
+    PCDB_LAUNCH_CHECK();
     PCDB_CUDA(cudaMemcpyAsync(w.kp4.p, w.kp_in.p, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(w.kp_in.p, w.kp_cloud.as<int>() + lo, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(w.kp_cloud.p, w.kp_in.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.kp_cloud.p, w.feat_valid.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
   }
-  k_slice_offsets<<<cdiv(B + 1, 128), 128, 0, st>>>(w.kp_off.as<long long>(), B, lo, hi);
-  PCDB_LAUNCH_CHECK();
+  const long long off[2] = {0, (long long)n};
+  PCDB_CUDA(cudaMemcpyAsync(w.kp_off.p, off, sizeof(off), cudaMemcpyHostToDevice, st));
   *Q_local_out = n;
   return PCDB_OK;
 }
 
-// keypoint-sharded scene: every rank ends up with the votes of all ranks, in rank (= keypoint) order
-int stage_gather_votes(pcdb_ctx* ctx, int B, int64_t V_local, int64_t* V_out) {
+// keypoint-sharded scene: every rank ends up with the votes of all ranks in GLOBAL keypoint order — the order one GPU
+// produces — by gathering (vote, keypoint index) and a stable radix sort on the index
+int stage_gather_votes(pcdb_ctx* ctx, int B, int64_t F_local, int k, int64_t V_local, int64_t* V_out) {
   CommState* c = comm_of(ctx);
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
+  (void)F_local;
+  (void)k;
   if (B != 1) return ctx->fail(PCDB_E_UNSUPPORTED, "keypoint sharding handles one scene per call");
   PCDB_CUDA(cudaEventRecord(ctx->ev_comm[2], st));
+  PCDB_CUDA(c->key_local.ensure(sizeof(unsigned) * (size_t)(V_local + 1)));
+  if (V_local > 0) {
+    k_vote_keys<<<cdiv(V_local, 256), 256, 0, st>>>(w.vote_feat.as<int>(), w.feat_kp.as<int>(), V_local, c->rank, c->n,
+                                                    c->key_local.as<unsigned>());
+    PCDB_LAUNCH_CHECK();
+  }
   PCDB_TRY(gather_counts(ctx, V_local, c->counts));
   int64_t V = 0;
   for (int r = 0; r < c->n; ++r) V += c->counts[r];
   if (V > 0x7fffff00ll) return ctx->fail(PCDB_E_INVALID, "more than 2^31 votes");
   PCDB_CUDA(c->votes_all.ensure(sizeof(pcdb_vote) * (size_t)(V + 1)));
+  PCDB_CUDA(c->key_all.ensure(sizeof(unsigned) * (size_t)(V + 1)));
+  PCDB_CUDA(c->key_sorted.ensure(sizeof(unsigned) * (size_t)(V + 1)));
+  PCDB_CUDA(c->ord.ensure(sizeof(int) * (size_t)(V + 1)));
+  PCDB_CUDA(c->ord_sorted.ensure(sizeof(int) * (size_t)(V + 1)));
   PCDB_TRY(all_gather_v(ctx, w.votes.p, c->votes_all.p, c->counts, sizeof(pcdb_vote)));
-  std::swap(w.votes, c->votes_all);
+  PCDB_TRY(all_gather_v(ctx, c->key_local.p, c->key_all.p, c->counts, sizeof(unsigned)));
+  PCDB_CUDA(w.votes.ensure(sizeof(pcdb_vote) * (size_t)(V + 1)));
+  if (V > 0) {
+    k_iota<<<cdiv(V, 256), 256, 0, st>>>(c->ord.as<int>(), V);
+    PCDB_LAUNCH_CHECK();
+    PCDB_TRY(pcdb_cub_sort_pairs_u32(ctx, c->key_all.as<unsigned>(), c->key_sorted.as<unsigned>(), c->ord.as<int>(),
+                                     c->ord_sorted.as<int>(), V, 32));
+    k_permute_votes<<<cdiv(V * 5, 256), 256, 0, st>>>(c->votes_all.as<pcdb_vote>(), c->ord_sorted.as<int>(), V,
+                                                      w.votes.as<pcdb_vote>());
+    PCDB_LAUNCH_CHECK();
+  }
   const long long off[2] = {0, (long long)V};
   PCDB_CUDA(w.vote_off.ensure(sizeof(long long) * 2));
   PCDB_CUDA(cudaMemcpyAsync(w.vote_off.p, off, sizeof(off), cudaMemcpyHostToDevice, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));  // `off` is a stack array
   PCDB_TRY(stage_votes_unpack(ctx, B, V));
   PCDB_CUDA(cudaEventRecord(ctx->ev_comm[3], st));
   ctx->comm_events_valid = true;

@@ -96,7 +96,7 @@ struct Codebook_d {
   X(mpos) X(mseg) X(mem_cnt) X(mem_off) X(mem_idx) X(mem_w) \
   X(max_raw) X(max_sorted) X(max_kept) X(max_first) X(labels) X(nbr_cnt) \
   X(nbr_off) X(nbr_key) X(nbr_key2) X(merge_a) X(merge_b) X(nrm_pca) \
-  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len)
+  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len) X(feat_kp) X(vote_feat)
 struct Workspace {
 #define X(n) DevBuf n;
   PCDB_WS_FIELDS(X)
@@ -173,6 +173,10 @@ struct pcdb_ctx {
 constexpr int PCDB_SHOT_CHUNK = 2048;
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// PCDB_TRACE=1: wall-clock between named points of a call, each after a stream sync (diagnosis only: the syncs
+// serialise what normally overlaps).  Prints to stderr.
+void pcdb_trace_point(pcdb_ctx* ctx, const char* name);
 
 // ---- device helpers -------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -22,9 +22,15 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+// Warps per CTA: all of them share ONE staged neighbourhood, so more warps per CTA = more resident warps per byte of
+// shared memory.  SHOT: 12 warps, 2 CTAs per SM (24 resident warps; round 1 ran 8 x 2 = 16 and was latency-bound:
+// warps_active 25 %, stall_wait 2.4 per issue).  CSHOT (3 staged float4 per point, 5.4 KB histograms): 16 warps, 1 CTA.
+constexpr int kWarpsShot = 12, kWarpsCshot = 16, kWarpsMax = 16;
 constexpr int kChunk = PCDB_SHOT_CHUNK;     // staged points per work item
+// Per-warp list of in-radius staged points, filled kList entries at a time: a neighbourhood larger than one fill is
+// processed in several fills (the passes only accumulate), so the list costs 2 KB per warp instead of 2 bytes per
+// staged point (4 KB) — that difference is what lets the extra warps fit.
+constexpr int kList = 1024;
 
 constexpr double PST_RAD_45 = 0.78539816339744830961566084581988;
 constexpr double PST_RAD_90 = 1.5707963267948966192313216916398;
@@ -171,8 +177,10 @@ struct StageView {
 };
 
 template <bool COLOR>
-__global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
+__global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR ? 1 : 2) k_shot(ShotArgs a) {
   constexpr int D = COLOR ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
+  constexpr int kWarps = COLOR ? kWarpsCshot : kWarpsShot;
+  constexpr int kThreads = kWarps * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_pts = reinterpret_cast<float4*>(smem_raw);
   float4* s_nrm = s_pts + a.stage_cap;
@@ -184,11 +192,12 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
   __shared__ int s_rlen_all[kWarps][9];
   __shared__ int s_pref[10];
   __shared__ int s_item;
+  __shared__ int s_next;  // staged launch: next keypoint of the item (the warps fetch keypoints dynamically)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = *a.n_items_ptr;
   unsigned* hist = s_hist + (size_t)warp * D;
-  unsigned short* list = s_list + (size_t)warp * a.stage_cap;
+  unsigned short* list = s_list + (size_t)warp * (a.stage_cap ? kList : 0);
   const bool dense_launch = a.dense != 0;
   long long* s_rbeg = s_rbeg_all[dense_launch ? warp : 0];
   int* s_rlen = s_rlen_all[dense_launch ? warp : 0];
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
       if (item >= n_items) break;
       k0 = a.item_start[item];
       k1 = a.item_start[item + 1];
+      if (threadIdx.x == 0) s_next = k0;
       if (threadIdx.x < 9) {
         s_rbeg[threadIdx.x] = a.item_beg[(size_t)item * 9 + threadIdx.x];
         s_rlen[threadIdx.x] = a.item_len[(size_t)item * 9 + threadIdx.x];
@@ -262,34 +272,49 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
     }
     const float r2_max = fmaxf(a.do_lrf ? a.r2_lrf : 0.f, a.do_desc ? a.r2_shot : 0.f);
 
-    const int warp_off = dense_launch ? 0 : warp;
-    for (int round = k0; round < k1; round += kWarps) {
-      const bool have = round + warp_off < k1;
-      const int kidx = have ? a.kp_order[round + warp_off] : -1;
+    // Staged launch: every warp takes the next unprocessed keypoint of the item when it is free (a static round-robin
+    // left warps waiting at the item's closing barrier for the one that drew the large neighbourhoods: 1.25 barrier
+    // stalls per issue in the round-1 profile).  Dense launch: the warp's single keypoint.
+    bool first = true;
+    while (true) {
+      int kq = k0;
+      if (!dense_launch) {
+        if (lane == 0) kq = atomicAdd(&s_next, 1);
+        kq = __shfl_sync(0xffffffffu, kq, 0);
+      } else if (!first) {
+        break;
+      }
+      first = false;
+      if (kq >= k1) break;
+      const bool have = true;
+      const int kidx = a.kp_order[kq];
       float kx = 0.f, ky = 0.f, kz = 0.f;
       unsigned krgb = 0;
-      if (have) {
+      {
         float4 k4 = a.kp4[kidx];
         kx = k4.x; ky = k4.y; kz = k4.z;
         krgb = __float_as_uint(k4.w);
       }
       // Radius filter first, heavy math second: the in-radius points of the chunk are compacted into this warp's list
       // (ballot + popc, order = staging order), so the fp64 passes below run with all 32 lanes busy instead of
-      // diverging on the 30-50 % of the 27-cell neighbourhood that lies inside the sphere.
-      auto compact = [&](int cnt, float r2) -> int {
+      // diverging on the 30-50 % of the 27-cell neighbourhood that lies inside the sphere.  One fill holds at most
+      // kList entries: `from` is where the scan of the staged points resumes, the return value the number of entries.
+      auto fill = [&](int& from, int cnt, float r2) -> int {
         int n = 0;
-        if (have)
-          for (int e0 = 0; e0 < cnt; e0 += 32) {
-            const int e = e0 + lane;
-            bool in = false;
-            if (e < cnt) {
-              const float4 p = s_pts[e];
-              in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (in) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
-            n += __popc(m);
+        int e0 = from;
+        __syncwarp();  // every lane is done reading the previous fill
+        for (; e0 < cnt && n <= kList - 32; e0 += 32) {
+          const int e = e0 + lane;
+          bool in = false;
+          if (e < cnt) {
+            const float4 p = s_pts[e];
+            in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
           }
+          const unsigned m = __ballot_sync(0xffffffffu, in);
+          if (in) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
+          n += __popc(m);
+        }
+        from = e0;
         __syncwarp();
         return n;
       };
@@ -323,30 +348,34 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
       if (a.do_lrf) {
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, sw = 0;
         int valid = 0, nall = 0, n_lrf = 0;
-        {
-          n_lrf = multi ? n_g : compact(T, a.r2_lrf);
-          if (have)
-            for (int i = lane; i < n_lrf; i += 32) {
-              float4 p = pt_at(i);
-              float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-              if (!multi || d2 < a.r2_lrf) {
-                ++nall;
-                if (!(p.x == kx && p.y == ky && p.z == kz)) {
-                  double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
-                         vz = (double)__fsub_rn(p.z, kz);
-                  double wgt = a.r_lrf - sqrt((double)d2);
-                  c00 += wgt * (vx * vx);
-                  c01 += wgt * (vx * vy);
-                  c02 += wgt * (vx * vz);
-                  c11 += wgt * (vy * vy);
-                  c12 += wgt * (vy * vz);
-                  c22 += wgt * (vz * vz);
-                  sw += wgt;
-                  ++valid;
-                }
+        int from = 0, done = 0;
+        do {
+          n_lrf = multi ? n_g : fill(from, T, a.r2_lrf);
+          // lane <-> entry assignment of ONE long list, whatever the number of fills (keeps the fp64 sums' order)
+          const int start = multi ? lane : ((lane + 32 - (done & 31)) & 31);
+          for (int i = start; i < n_lrf; i += 32) {
+            float4 p = pt_at(i);
+            float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+            if (!multi || d2 < a.r2_lrf) {
+              ++nall;
+              if (!(p.x == kx && p.y == ky && p.z == kz)) {
+                double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                       vz = (double)__fsub_rn(p.z, kz);
+                double wgt = a.r_lrf - sqrt((double)d2);
+                c00 += wgt * (vx * vx);
+                c01 += wgt * (vx * vy);
+                c02 += wgt * (vx * vz);
+                c11 += wgt * (vy * vy);
+                c12 += wgt * (vy * vz);
+                c22 += wgt * (vz * vz);
+                sw += wgt;
+                ++valid;
               }
             }
-        }
+          }
+          done += n_lrf;
+        } while (!multi && from < T);
+        const bool whole = multi || done == n_lrf;  // the list still holds the complete LRF neighbourhood
         c00 = warp_sum(c00); c01 = warp_sum(c01); c02 = warp_sum(c02);
         c11 = warp_sum(c11); c12 = warp_sum(c12); c22 = warp_sum(c22);
         sw = warp_sum(sw);
@@ -365,9 +394,11 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
         }
         // pass B: sign disambiguation
         int plusX = 0, plusZ = 0;
-        {
-          if (lrf_ok)  // the list of pass A is still valid
-            for (int i = lane; i < n_lrf; i += 32) {
+        if (lrf_ok) {
+          int fromB = 0;
+          do {
+            const int nb = whole ? n_lrf : fill(fromB, T, a.r2_lrf);  // the list of pass A when it is complete
+            for (int i = lane; i < nb; i += 32) {
               float4 p = pt_at(i);
               if (multi && !(sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < a.r2_lrf)) continue;
               if (!(p.x == kx && p.y == ky && p.z == kz)) {
@@ -377,6 +408,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
                 if (vx * z[0] + vy * z[1] + vz * z[2] >= 0) ++plusZ;
               }
             }
+          } while (!whole && fromB < T);
         }
         plusX = warp_sum(plusX);
         plusZ = warp_sum(plusZ);
@@ -386,8 +418,12 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
             // Tie (about 2% of real keypoints): the reference looks at the 5 neighbours around the median of the
             // (d^2, index)-sorted valid list (shot_na_lrf.hpp:141-153).  Rank selection by bisection on the 63-bit
             // key (d^2 bits << 32 | index): 63 counting passes over the staged points + 5 successive-minimum passes.
-            auto scan = [&](auto&& f) {  // the list of passes A/B (key_of applies the LRF radius itself)
-              for (int i = lane; i < n_lrf; i += 32) f(pt_at(i), __float_as_int(nrm_at(i).w));
+            auto scan = [&](auto&& f) {  // key_of applies the LRF radius itself
+              if (whole) {           // the list of pass A
+                for (int i = lane; i < n_lrf; i += 32) f(pt_at(i), __float_as_int(nrm_at(i).w));
+              } else {               // a neighbourhood of several fills: walk the staged points
+                for (int e = lane; e < T; e += 32) f(s_pts[e], __float_as_int(s_nrm[e].w));
+              }
             };
             const unsigned long long kInvalid = ~0ull;
             auto key_of = [&](const float4& p, int idx) -> unsigned long long {
@@ -452,7 +488,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) rf[i] = a.lrf_in[(size_t)kidx * 9 + i];
       }
-      if (!a.do_desc) continue;
+      if (!a.do_desc) continue;  // next keypoint
       // Features::operator() drops keypoints whose frame is not finite (features.cpp:64-76)
       const bool frame_ok = have && isfinite(rf[0]) && isfinite(rf[3]) && isfinite(rf[6]);
       // ---------------------------------------------------------------- SHOT / CSHOT
@@ -473,7 +509,9 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
       const float inv_90f = (float)(1.0 / PST_RAD_90), inv_45f = (float)(1.0 / PST_RAD_45);
       int nshot = 0;
       if (frame_ok) {  // warp-uniform
-        const int n_in = multi ? n_g : compact(T, a.r2_shot);
+        int fromC = 0;
+        do {
+        const int n_in = multi ? n_g : fill(fromC, T, a.r2_shot);
         for (int i = lane; i < n_in; i += 32) {
           float4 p = pt_at(i);
           float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
@@ -599,6 +637,7 @@ __global__ void __launch_bounds__(kThreads) k_shot(ShotArgs a) {
           hist_add(hist, volS + stepS, wS, fix_scale);
           if (COLOR) hist_add(hist, volC + stepC, wC, fix_scale);
         }
+        } while (!multi && fromC < T);
       }
       nshot = warp_sum(nshot);
       if (have && lane == 0 && a.nbr_counts && frame_ok) atomicAdd(&a.nbr_counts[1], (unsigned long long)nshot);
@@ -660,10 +699,12 @@ __global__ void k_item_population(const int* __restrict__ item_len, const int* _
 
 }  // namespace
 
+static int shot_warps(bool color) { return color ? kWarpsCshot : kWarpsShot; }
 static size_t shot_smem_for(bool color, int stage_cap) {
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
-  return sizeof(float4) * (size_t)stage_cap * (color ? 3 : 2) + sizeof(unsigned) * (size_t)kWarps * D +
-         sizeof(unsigned short) * (size_t)kWarps * stage_cap;
+  const size_t W = (size_t)shot_warps(color);
+  return sizeof(float4) * (size_t)stage_cap * (color ? 3 : 2) + sizeof(unsigned) * W * D +
+         (stage_cap ? sizeof(unsigned short) * W * kList : 0);
 }
 size_t shot_smem_bytes(bool color) { return shot_smem_for(color, kChunk); }
 
@@ -743,8 +784,9 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   a.item_id = w.item_id.as<int>();
   a.item_head = w.item_head.as<int>();
   a.work_counter_dense = w.scalars.as<int>() + 2;
-  // dense launch: no staging arrays, so more CTAs fit; every warp takes keypoints on its own
-  const int dense_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * (color ? 2 : 3), cdiv(Q, kWarps));
+  // dense launch: no staging arrays; every warp takes keypoints on its own
+  const int kWarps = shot_warps(color), kThreads = kWarps * 32;
+  const int dense_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * (color ? 1 : 2), cdiv(Q, kWarps));
   if (h_pop > (unsigned long long)kChunk) {
     a.gcap = (long long)((h_pop + 31) & ~31ull);
     const size_t bytes = sizeof(unsigned) * (size_t)a.gcap * (size_t)dense_grid * kWarps;

@@ -55,5 +55,5 @@ bool comm_keypoints_sharded(const pcdb_ctx* ctx);  // one scene per call, keypoi
 int stage_knn_sharded(pcdb_ctx* ctx, const float* queries_d, int64_t Q_local, int k, int dist_type, int mode,
                       bool use_ratio, float ratio_thr);
 int stage_slice_keypoints(pcdb_ctx* ctx, int B, int64_t Q, int64_t* Q_local_out);
-int stage_gather_votes(pcdb_ctx* ctx, int B, int64_t V_local, int64_t* V_out);  // syncs
+int stage_gather_votes(pcdb_ctx* ctx, int B, int64_t F_local, int k, int64_t V_local, int64_t* V_out);  // syncs
 float comm_last_exchange_ms(pcdb_ctx* ctx);

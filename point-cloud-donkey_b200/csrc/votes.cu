@@ -130,7 +130,7 @@ __global__ void k_vote_count(VoteArgs a, int* cnt) {
 }
 
 __global__ void k_vote_write(VoteArgs a, const int* __restrict__ pos, const int* __restrict__ feat_cloud,
-                             pcdb_vote* votes, float4* vote_pw, int* vote_cloud) {
+                             pcdb_vote* votes, float4* vote_pw, int* vote_cloud, int* vote_feat) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= a.F * a.k) return;
   long long f = t / a.k;
@@ -180,6 +180,7 @@ __global__ void k_vote_write(VoteArgs a, const int* __restrict__ pos, const int*
     for (int i = 0; i < 5; ++i) dst[i] = src[i];
     vote_pw[o] = make_float4(out.position[0], out.position[1], out.position[2], wgt);
     vote_cloud[o] = feat_cloud[f];
+    if (vote_feat) vote_feat[o] = (int)f;
     ++o;
   }
 }
@@ -248,9 +249,12 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
   PCDB_CUDA(w.votes.ensure(sizeof(pcdb_vote) * (size_t)(V + 1)));
   PCDB_CUDA(w.vote_pw.ensure(sizeof(float4) * (size_t)(V + 1)));
   PCDB_CUDA(w.vote_cloud.ensure(sizeof(int) * (size_t)(V + 1)));
+  const bool want_feat = comm_keypoints_sharded(ctx);  // the vote -> feature map restores the global order after the gather
+  if (want_feat) PCDB_CUDA(w.vote_feat.ensure(sizeof(int) * (size_t)(V + 1)));
   if (V > 0) {
     k_vote_write<<<cdiv(T, 128), 128, 0, st>>>(a, w.vote_pos.as<int>(), feat_cloud_d, w.votes.as<pcdb_vote>(),
-                                               w.vote_pw.as<float4>(), w.vote_cloud.as<int>());
+                                               w.vote_pw.as<float4>(), w.vote_cloud.as<int>(),
+                                               want_feat ? w.vote_feat.as<int>() : nullptr);
     PCDB_LAUNCH_CHECK();
   }
   k_vote_offsets<<<cdiv(B + 1, 128), 128, 0, st>>>(feat_off_d, B, k, w.vote_pos.as<int>(), w.vote_off.as<long long>());

@@ -121,8 +121,9 @@ def _worker(rank, world, port, q):
         lab, _, _ = full.classify_batch(xa[oa[a]:oa[b]], na[oa[a]:oa[b]], ra[oa[a]:oa[b]], oa[a:b + 1] - oa[a],
                                         want_maxima=False) if b > a else (np.zeros(0, np.int32), None, None)
         ok = ok and np.array_equal(lab, lab_all[a:b])
-        # one scene, keypoints sharded contiguously over the ranks (C5): the rank-ordered concatenation of the slices'
-        # votes is the single-rank vote list, bit for bit
+        # one scene, keypoints sharded BLOCK-CYCLICALLY over the ranks (C5, comm.cu: blocks of 32 keypoints round-robin
+        # for load balance): every vote travels with the global index of its keypoint and a stable sort on that index
+        # restores the single-rank vote list, bit for bit
         sprm = synth.workload_params("c2", knn_k=2, single_object_mode=0, min_votes_threshold=3)
         sx_, sn_, sc_, _ = synth.make_scene([0, 1, 2], 5, 900, plane_points=1500, clutter_points=300)
         sx_[7] = np.nan
@@ -130,25 +131,28 @@ def _worker(rank, world, port, q):
         fin = np.isfinite(sx_).all(1)
         pts, col, nr = sx_[fin], sc_[fin], sn_[fin]
         kp, kr, _ = orc.voxel_keypoints(pts, col, [0, len(pts)], sprm.leaf_size)
-        cuts = sharded.shard_bounds(len(kp), world)
-        a, b = cuts[rank], cuts[rank + 1]
+        BS = 32
+        mine = np.array([g for g in range(len(kp)) if (g // BS) % world == rank], np.int64)
         surf = np.isfinite(nr).all(1)
         sxx, snn, scc, soff = pts[surf], nr[surf], col[surf], [0, int(surf.sum())]
-        kx, kc = kp[a:b], kr[a:b]
+        kx, kc, gidx = kp[mine], kr[mine], mine
         lrf = orc.shot_lrf(sxx, soff, kx, [0, len(kx)], sprm.lrf_radius)
         good = np.isfinite(lrf[:, 0]) & np.isfinite(lrf[:, 3]) & np.isfinite(lrf[:, 6])
-        kx, kc, lrf = kx[good], kc[good], lrf[good]
+        kx, kc, lrf, gidx = kx[good], kc[good], lrf[good], gidx[good]
         desc = orc.shot_describe(sprm.feature_type, sxx, snn, scc, soff, kx, kc, lrf, [0, len(kx)], sprm.feature_radius)
         good = ~np.isnan(desc).any(1)
-        kx, lrf, desc = kx[good], lrf[good], desc[good]
+        kx, lrf, desc, gidx = kx[good], lrf[good], desc[good], gidx[good]
         i1, d1, c1 = sm.knn(desc, k=2)
-        v_mine, _ = sm.cast_votes(kx, lrf, [0, len(kx)], i1, d1, c1)
+        v_mine, per_feat = sm.cast_votes(kx, lrf, np.arange(len(kx) + 1), i1, d1, c1)   # one "cloud" per feature
+        keys = np.repeat(gidx, np.diff(per_feat))
         parts = _gather_np(v_mine, dist, torch)
-        sv = np.concatenate(parts)
+        kparts = _gather_np(keys, dist, torch)
+        allv, allk = np.concatenate(parts), np.concatenate(kparts)
+        sv = allv[np.argsort(allk, kind="stable")]
         fx1, fl1, fd1, fo1 = orc.compute_features(sprm, sx_, sn_, sc_, [0, len(sx_)])
         i1, d1, c1 = sm.knn(fd1, k=2)
         rv, rvo = sm.cast_votes(fx1, fl1, fo1, i1, d1, c1)
-        ok = ok and sv.tobytes() == rv.tobytes() and len(sv) > 0
+        ok = ok and sv.tobytes() == rv.tobytes() and len(sv) > 0 and len(kp) > 2 * BS
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
