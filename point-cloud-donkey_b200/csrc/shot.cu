@@ -303,16 +303,25 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
         int n = 0;
         int e0 = from;
         __syncwarp();  // every lane is done reading the previous fill
-        for (; e0 < cnt && n <= kList - 32; e0 += 32) {
-          const int e = e0 + lane;
-          bool in = false;
-          if (e < cnt) {
-            const float4 p = s_pts[e];
-            in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
+        // 64 staged points per iteration (two independent loads / distance chains per lane): the compaction is a fifth
+        // of the kernel's instructions, and half of those were loop overhead and latency waits at 32 per iteration
+        for (; e0 < cnt && n <= kList - 64; e0 += 64) {
+          const int ea = e0 + lane, eb = ea + 32;
+          bool ina = false, inb = false;
+          if (ea < cnt) {
+            const float4 p = s_pts[ea];
+            ina = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
           }
-          const unsigned m = __ballot_sync(0xffffffffu, in);
-          if (in) list[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)e;
-          n += __popc(m);
+          if (eb < cnt) {
+            const float4 p = s_pts[eb];
+            inb = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2;
+          }
+          const unsigned ma = __ballot_sync(0xffffffffu, ina), mb = __ballot_sync(0xffffffffu, inb);
+          const unsigned below = (1u << lane) - 1u;
+          if (ina) list[n + __popc(ma & below)] = (unsigned short)ea;
+          n += __popc(ma);
+          if (inb) list[n + __popc(mb & below)] = (unsigned short)eb;
+          n += __popc(mb);
         }
         from = e0;
         __syncwarp();
