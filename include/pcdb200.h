@@ -47,6 +47,10 @@ enum { PCDB_KERNEL_GAUSSIAN = 0, PCDB_KERNEL_UNIFORM = 1 };       /* voting_mean
 enum { PCDB_SUPPRESS_AVERAGE = 0, PCDB_SUPPRESS_SUPPRESS = 1 };   /* voting_mean_shift.cpp:98-122 */
 enum { PCDB_MAXFILTER_NONE = 0, PCDB_MAXFILTER_SIMPLE = 1, PCDB_MAXFILTER_MERGE = 2 }; /* maxima_handler.cpp:272-383 */
 enum { PCDB_KNN_AUTO = 0, PCDB_KNN_SCAN = 1, PCDB_KNN_GEMM = 2 }; /* which exact-kNN kernel family */
+/* Voting.BinOrBandwidthType (maxima_handler.cpp:509-521): Config|Fixed, FirstDim|ObjectRadius, SecondDim|BoundingBoxMedian */
+enum { PCDB_RADIUS_CONFIG = 0, PCDB_RADIUS_FIRST_DIM = 1, PCDB_RADIUS_SECOND_DIM = 2 };
+/* Voting.SingleObjectMaxType (maxima_handler.h:42-58): Default|None, BandwidthVotes, VotingSpaceVotes, ModelRadiusVotes */
+enum { PCDB_SOMAX_DEFAULT = 0, PCDB_SOMAX_BANDWIDTH = 1, PCDB_SOMAX_VOTING_SPACE = 2, PCDB_SOMAX_MODEL_RADIUS = 3 };
 
 #define PCDB_SHOT_DIM 352
 #define PCDB_CSHOT_DIM 1344
@@ -86,6 +90,15 @@ typedef struct pcdb_params {
                                         centroid, 2 inverted SHOT-LRF z axis (the code default) */
   /* Cross-class maxima filtering when !single_object_mode (voting.cpp:265-268, maxima_handler.cpp:272-383) */
   int32_t max_filter_type;           /* PCDB_MAXFILTER_*; Voting.MaxFilterType */
+  /* Per-class search distance (maxima_handler.cpp:509-521, voting_mean_shift.cpp:47-49): Config = Voting.Bandwidth for
+   * every class, else the class' learned object radius / median bounding-box dimension (pcdb_set_class_dimensions)
+   * times radius_factor */
+  int32_t radius_type;               /* PCDB_RADIUS_*; Voting.BinOrBandwidthType */
+  float radius_factor;               /* Voting.BinOrBandwidthFactor */
+  /* Single-object mode without mean shift (voting_mean_shift.cpp:124-155): one maximum per class at the cloud's
+   * centroid, votes collected within the bandwidth / the model radius / the whole voting space.  Only consulted when
+   * single_object_mode != 0; needs the cloud, so the fused entries support it and pcdb_find_maxima does not */
+  int32_t single_object_max_type;    /* PCDB_SOMAX_*; Voting.SingleObjectMaxType */
 } pcdb_params;
 
 /* One Hough vote — ism3d::Vote, voting/voting_maximum.h:25-42 (80 bytes). */
@@ -142,6 +155,11 @@ int pcdb_set_codebook(pcdb_ctx* ctx, const float* words, int64_t N, int32_t D,
                       const float* vote_bbox /* V x 7 */, const float* vote_class_weight /* V or NULL */,
                       const float* kp_train, const int32_t* codeword_ids, const float* codeword_weight,
                       const float* class_sigma2, int32_t n_classes, int64_t row_base);
+
+/* Learned per-class dimensions — Voting::forwardBoxesAndRadii / iLoadData (voting/voting.cpp:497-557,619-650), the
+ * table behind BinOrBandwidthType != Config: first[c] = mean object radius, second[c] = mean median bounding-box side of
+ * class c's training models.  Classes without an entry: pass 0 (the reference's map::at would throw). */
+int pcdb_set_class_dimensions(pcdb_ctx* ctx, const float* first_dim, const float* second_dim, int32_t n_classes);
 
 /* ---- stage-level entry points (one per reference hook) ---------------- */
 /* KeypointsVoxelGrid::iComputeKeypoints (keypoints/keypoints_voxel_grid.cpp:30-46 -> pcl::VoxelGrid).

@@ -210,6 +210,11 @@ class Model:
         self.prm = prm.copy()
         lib().orc_model_set_params(self.h, C.byref(self.prm))
 
+    def set_class_dimensions(self, first_dim, second_dim):
+        """Voting::m_dimensions_map: per class (mean object radius, mean median bounding-box side)."""
+        a, b = f32(first_dim), f32(second_dim)
+        lib().orc_model_set_class_dimensions(self.h, ptr(a, F), ptr(b, F), len(a))
+
     def close(self):
         if self.h:
             lib().orc_model_destroy(self.h)

@@ -1160,6 +1160,7 @@ struct Model {
   std::vector<float> kp_train, codeword_weight;
   std::vector<int32_t> codeword_ids;
   std::vector<float> sigma2;
+  std::vector<float> dim_first, dim_second; /* Voting::m_dimensions_map (voting.cpp:497-557,619-650), by class id */
   std::shared_ptr<KdForest> forest; /* set: activation runs FLANN-style approximate search (cost stand-in only) */
   double forest_build_ms = 0;
 };
@@ -1269,9 +1270,33 @@ float ms_density(const pcdb_params& P, float h, ClassVotes& cv, const float* pos
   return density;
 }
 
-void ms_find_maxima(const pcdb_params& P, ClassVotes& cv, std::vector<Vec3>& maxima,
+/* MaximaHandler::getSearchDistForClass (maxima_handler.cpp:509-521); m_radius = the value MaximaHandler::setRadius saw */
+float search_dist_for_class(const pcdb_params& P, const std::vector<float>& dim_first,
+                            const std::vector<float>& dim_second, unsigned class_id, float m_radius) {
+  if (P.radius_type == PCDB_RADIUS_FIRST_DIM)
+    return (class_id < dim_first.size() ? dim_first[class_id] : 0.f) * P.radius_factor;
+  if (P.radius_type == PCDB_RADIUS_SECOND_DIM)
+    return (class_id < dim_second.size() ? dim_second[class_id] : 0.f) * P.radius_factor;
+  return m_radius;
+}
+
+/* single-object mode with a non-default max type (voting_mean_shift.cpp:124-155,161-176): no mean shift, one maximum at
+ * `centre`, votes collected (and re-weighted) within h */
+void ms_single_maximum(const pcdb_params& P, float h, ClassVotes& cv, const float* centre, std::vector<Vec3>& maxima,
+                       std::vector<std::vector<int>>& members, std::vector<std::vector<float>>& member_w) {
+  maxima.assign(1, Vec3{{centre[0], centre[1], centre[2]}});
+  members.clear();
+  member_w.clear();
+  std::vector<int> mem;
+  ms_density(P, h, cv, centre, mem, true);
+  members.push_back(mem);
+  std::vector<float> w;
+  for (int i : mem) w.push_back(cv.w[i]);
+  member_w.push_back(w);
+}
+
+void ms_find_maxima(const pcdb_params& P, float h, ClassVotes& cv, std::vector<Vec3>& maxima,
                     std::vector<std::vector<int>>& members, std::vector<std::vector<float>>& member_w) {
-  const float h = P.bandwidth; /* BinOrBandwidthType "Config": maxima_handler.cpp:509-513 */
   const float r2 = radius_sq(double(h));
   const int n = int(cv.w.size());
   /* createSeeds :431-481 */
@@ -1460,7 +1485,15 @@ void quat_average(const std::vector<Quat>& qs, const std::vector<float>& ws, Qua
 }
 
 /* Voting::findMaxima (voting/voting.cpp:79-328) for one cloud */
-void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv, std::vector<pcdb_maximum>& out,
+struct ClassDims {
+  const std::vector<float>* first;
+  const std::vector<float>* second;
+};
+
+/* surf / n_surf: the cloud handed to Voting::findMaxima (pointsWithoutNaN, implicit_shape_model.cpp:689) — only the
+ * single-object max types read it (centroid, model radius); may be null otherwise. */
+void find_maxima_cloud(const pcdb_params& P, const ClassDims& dims, const float* surf, int64_t n_surf,
+                       const pcdb_vote* votes, int64_t nv, std::vector<pcdb_maximum>& out,
                        std::vector<int64_t>& member_idx, std::vector<float>& member_w) {
   out.clear();
   member_idx.clear();
@@ -1478,12 +1511,51 @@ void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv,
     std::vector<float> w;
   };
   std::vector<Tmp> all;
+  static const std::vector<float> kNoDims;
+  const std::vector<float>& d1 = dims.first ? *dims.first : kNoDims;
+  const std::vector<float>& d2 = dims.second ? *dims.second : kNoDims;
+  /* VotingMeanShift::m_bandwidth / MaximaHandler::m_radius as iFindMaxima updates them class after class
+   * (voting_mean_shift.cpp:47-49).  The reference keeps m_bandwidth across detect() calls; here every cloud starts from
+   * the configured Voting.Bandwidth (what a freshly loaded model does). */
+  float m_bandwidth = P.bandwidth, m_radius = P.bandwidth;
+  const bool single_max = P.single_object_mode && P.single_object_max_type != PCDB_SOMAX_DEFAULT;
+  float centre[3] = {0, 0, 0};
+  if (single_max) { /* pcl::compute3DCentroid into an Eigen::Vector4f: sequential float sums, one division */
+    for (int64_t i = 0; i < n_surf; ++i)
+      for (int a = 0; a < 3; ++a) centre[a] += surf[3 * i + a];
+    for (int a = 0; a < 3; ++a) centre[a] /= static_cast<float>(n_surf);
+  }
   for (auto& kv : by_class) {
     ClassVotes& cv = kv.second;
     std::vector<Vec3> maxima;
     std::vector<std::vector<int>> members;
     std::vector<std::vector<float>> mw;
-    ms_find_maxima(P, cv, maxima, members, mw);
+    m_radius = m_bandwidth;
+    m_bandwidth = search_dist_for_class(P, d1, d2, kv.first, m_radius);
+    if (!single_max) {
+      ms_find_maxima(P, m_bandwidth, cv, maxima, members, mw);
+    } else {
+      if (P.single_object_max_type == PCDB_SOMAX_BANDWIDTH)
+        m_bandwidth = search_dist_for_class(P, d1, d2, kv.first, m_radius);
+      if (P.single_object_max_type == PCDB_SOMAX_MODEL_RADIUS) { /* SingleObjectHelper::getModelRadius */
+        float r = 0;
+        for (int64_t i = 0; i < n_surf; ++i) {
+          float d = norm3(surf + 3 * i, centre);
+          if (d > r) r = d;
+        }
+        m_bandwidth = r;
+      }
+      if (P.single_object_max_type == PCDB_SOMAX_VOTING_SPACE) { /* SingleObjectHelper::getVotingSpaceSize */
+        float mx = 0;
+        for (size_t i = 0; i < cv.w.size(); ++i) {
+          float dx = cv.pos[3 * i] - centre[0], dy = cv.pos[3 * i + 1] - centre[1], dz = cv.pos[3 * i + 2] - centre[2];
+          float d = dx * dx + dy * dy + dz * dz;
+          mx = mx > d ? mx : d;
+        }
+        m_bandwidth = std::sqrt(mx);
+      }
+      ms_single_maximum(P, m_bandwidth, cv, centre, maxima, members, mw);
+    }
     for (size_t i = 0; i < maxima.size(); ++i) {
       const std::vector<int>& mem = members[i];
       if ((int)mem.size() < P.min_votes_threshold || mem.empty()) continue;
@@ -1561,10 +1633,92 @@ void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv,
       for (size_t i = 0; i < all.size(); ++i) {
         const float* q = all[i].m.position;
         float dx = c[0] - q[0], dy = c[1] - q[1], dz = c[2] - q[2];
-        if (std::sqrt(dx * dx + dy * dy + dz * dz) < P.bandwidth) work[i] = -1.f;
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) < m_radius) work[i] = -1.f;
       }
     }
     all = std::move(kept_max);
+  }
+  if (!P.single_object_mode && P.max_filter_type == PCDB_MAXFILTER_MERGE) {
+    /* MaximaHandler::mergeAndFilterMaxima(maxima, true) + mergeMaxima (maxima_handler.cpp:296-383,386-443): a maximum
+     * subsumes later maxima closer than its class' search distance whose own search distance is not larger; the group
+     * (neighbours first, the maximum itself last) is merged per class (std::map: ascending class id) by running
+     * weighted averages, and the heaviest merged maximum survives. */
+    auto dist_for = [&](unsigned cls) { return search_dist_for_class(P, d1, d2, cls, m_radius); };
+    std::vector<Tmp> filtered;
+    std::vector<bool> dirty(all.size(), false);
+    for (size_t i = 0; i < all.size(); ++i) {
+      if (dirty[i]) continue;
+      const float sd = dist_for(all[i].m.class_id);
+      std::vector<size_t> close;
+      for (size_t j = i + 1; j < all.size(); ++j) {
+        if (dirty[j]) continue;
+        const float dist = norm3(all[j].m.position, all[i].m.position);
+        const float od = dist_for(all[j].m.class_id);
+        if (dist < sd && od <= sd) {
+          close.push_back(j);
+          dirty[j] = true;
+        }
+      }
+      if (close.empty()) {
+        filtered.push_back(all[i]);
+        continue;
+      }
+      close.push_back(i);
+      std::map<unsigned, std::vector<size_t>> same;
+      for (size_t c : close) same[all[c].m.class_id].push_back(c);
+      Tmp best;
+      std::memset(&best.m, 0, sizeof(best.m)); /* VotingMaximum(): weight 0, class -1, instance max, identity quat */
+      best.m.class_id = 0xffffffffu;
+      best.m.instance_id = 0xffffffffu;
+      best.m.bbox_quat[0] = 1;
+      for (auto& kv : same) {
+        Tmp r;
+        std::memset(&r.m, 0, sizeof(r.m));
+        r.m.bbox_quat[0] = 1;
+        std::map<unsigned, float> inst_w;
+        for (size_t c : kv.second) {
+          const pcdb_maximum& m = all[c].m;
+          const float rw = r.m.weight, mw_ = m.weight;
+          for (int a = 0; a < 3; ++a) {
+            r.m.position[a] = r.m.position[a] * rw + m.position[a] * mw_;
+            r.m.position[a] /= (rw + mw_);
+            r.m.bbox_size[a] = r.m.bbox_size[a] * rw + m.bbox_size[a] * mw_;
+            r.m.bbox_size[a] /= (rw + mw_);
+          }
+          Quat q;
+          quat_average({Quat{r.m.bbox_quat[0], r.m.bbox_quat[1], r.m.bbox_quat[2], r.m.bbox_quat[3]},
+                        Quat{m.bbox_quat[0], m.bbox_quat[1], m.bbox_quat[2], m.bbox_quat[3]}},
+                       {rw, mw_}, q);
+          r.m.bbox_quat[0] = q.a;
+          r.m.bbox_quat[1] = q.b;
+          r.m.bbox_quat[2] = q.c;
+          r.m.bbox_quat[3] = q.d;
+          r.m.class_id = m.class_id;
+          r.m.weight += m.weight;
+          r.idx.insert(r.idx.end(), all[c].idx.begin(), all[c].idx.end());
+          r.w.insert(r.w.end(), all[c].w.begin(), all[c].w.end());
+          auto it = inst_w.find(m.instance_id);
+          if (it != inst_w.end())
+            it->second += m.instance_weight;
+          else
+            inst_w.insert({m.instance_id, m.instance_weight});
+          unsigned max_id = 0; /* uninitialised in the reference when no weight > 0 */
+          float best_weight = 0;
+          for (auto& iw : inst_w)
+            if (iw.second > best_weight) {
+              best_weight = iw.second;
+              max_id = iw.first;
+            }
+          r.m.instance_id = max_id;
+          r.m.instance_weight = inst_w[max_id];
+        }
+        r.m.raw_weight = r.m.weight;
+        r.m.n_votes = int(r.idx.size());
+        if (r.m.weight > best.m.weight) best = r;
+      }
+      filtered.push_back(best);
+    }
+    all = std::move(filtered);
   }
   std::stable_sort(all.begin(), all.end(), [](const Tmp& a, const Tmp& b) { return a.m.weight > b.m.weight; });
   float sum = 0, sum_inst = 0; /* normalizeWeights :441-462 */
@@ -1599,6 +1753,7 @@ void find_maxima_cloud(const pcdb_params& P, const pcdb_vote* votes, int64_t nv,
 /* ------------------------------------------------------------------------------------------- */
 struct CloudFeatures {
   std::vector<float> xyz, lrf, desc;
+  std::vector<float> surf; /* pointsWithoutNaN: finite points with finite normals (what Voting::findMaxima is handed) */
   int64_t n_kp = 0, n_lrf_nb = 0, n_shot_nb = 0;
 };
 
@@ -1639,6 +1794,7 @@ void compute_features_cloud(const pcdb_params& P, const float* xyz, const float*
   const int Q = int(kps.rgb.size());
   const int ns = int(srgb.size());
   out.n_kp = Q;
+  out.surf = sxyz;
   CloudGrid g_lrf, g_shot;
   g_lrf.build(sxyz.data(), ns, P.lrf_radius);
   g_shot.build(sxyz.data(), ns, P.feature_radius);
@@ -1770,6 +1926,9 @@ void orc_default_params(pcdb_params* p) {
   p->normal_radius = 0.05f;
   p->consistent_normals_method = 2;
   p->max_filter_type = PCDB_MAXFILTER_NONE;
+  p->radius_type = PCDB_RADIUS_CONFIG;
+  p->radius_factor = 1.0f;
+  p->single_object_max_type = PCDB_SOMAX_DEFAULT;
 }
 
 int orc_voxel_keypoints(const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B, float leaf,
@@ -1978,6 +2137,11 @@ double orc_model_set_approximate(void* model, int32_t trees, int32_t checks, uin
   return m->forest_build_ms;
 }
 void orc_model_set_params(void* model, const pcdb_params* prm) { static_cast<Model*>(model)->prm = *prm; }
+void orc_model_set_class_dimensions(void* model, const float* first_dim, const float* second_dim, int32_t n_classes) {
+  Model* m = static_cast<Model*>(model);
+  m->dim_first.assign(first_dim, first_dim + n_classes);
+  m->dim_second.assign(second_dim, second_dim + n_classes);
+}
 void orc_model_destroy(void* model) { delete static_cast<Model*>(model); }
 
 int orc_knn(void* model, const float* queries, int64_t Q, int32_t k, int32_t dist_type, int32_t /*mode*/,
@@ -2030,7 +2194,12 @@ int orc_find_maxima(void* model, const pcdb_vote* votes, const int64_t* vote_off
     std::vector<pcdb_maximum> mx;
     std::vector<int64_t> mi;
     std::vector<float> mw;
-    find_maxima_cloud(m.prm, votes + vote_off[b], vote_off[b + 1] - vote_off[b], mx, mi, mw);
+    if (m.prm.single_object_mode && m.prm.single_object_max_type != PCDB_SOMAX_DEFAULT) {
+      g_err = "SingleObjectMaxType other than Default needs the cloud: use the fused classify entry";
+      return PCDB_E_UNSUPPORTED;
+    }
+    find_maxima_cloud(m.prm, ClassDims{&m.dim_first, &m.dim_second}, nullptr, 0, votes + vote_off[b],
+                      vote_off[b + 1] - vote_off[b], mx, mi, mw);
     if (total + (int64_t)mx.size() > maxima_capacity) {
       g_err = "maxima_capacity too small";
       return PCDB_E_CAPACITY;
@@ -2101,7 +2270,8 @@ int orc_classify_batch(void* model, const float* xyz, const float* normals, cons
     std::vector<pcdb_maximum> mx;
     std::vector<int64_t> mi;
     std::vector<float> mw;
-    find_maxima_cloud(P, votes.data(), (int64_t)votes.size(), mx, mi, mw);
+    find_maxima_cloud(P, ClassDims{&m.dim_first, &m.dim_second}, f.surf.data(), (int64_t)f.surf.size() / 3,
+                      votes.data(), (int64_t)votes.size(), mx, mi, mw);
     auto t3 = std::chrono::steady_clock::now();
     t_max += std::chrono::duration<double, std::milli>(t3 - t2).count();
     label_out[b] = mx.empty() ? -1 : int32_t(mx[0].class_id); /* eval_classification.cpp:412-417 */

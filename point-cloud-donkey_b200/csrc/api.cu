@@ -62,6 +62,14 @@ int check_params(pcdb_ctx* ctx, const pcdb_params& p) {
   if (p.maxima_suppression != PCDB_SUPPRESS_AVERAGE && p.maxima_suppression != PCDB_SUPPRESS_SUPPRESS)
     return ctx->fail(PCDB_E_INVALID, "invalid Voting.MaximaSuppression %d", p.maxima_suppression);
   if (!(p.bandwidth > 0)) return ctx->fail(PCDB_E_INVALID, "Voting.Bandwidth must be positive");
+  if (p.radius_type < PCDB_RADIUS_CONFIG || p.radius_type > PCDB_RADIUS_SECOND_DIM)
+    return ctx->fail(PCDB_E_INVALID, "invalid Voting.BinOrBandwidthType %d", p.radius_type);
+  if (p.radius_type != PCDB_RADIUS_CONFIG && !(p.radius_factor > 0))
+    return ctx->fail(PCDB_E_INVALID, "Voting.BinOrBandwidthFactor must be positive");
+  if (p.single_object_max_type < PCDB_SOMAX_DEFAULT || p.single_object_max_type > PCDB_SOMAX_MODEL_RADIUS)
+    return ctx->fail(PCDB_E_INVALID, "invalid Voting.SingleObjectMaxType %d", p.single_object_max_type);
+  if (p.max_filter_type < PCDB_MAXFILTER_NONE || p.max_filter_type > PCDB_MAXFILTER_MERGE)
+    return ctx->fail(PCDB_E_INVALID, "invalid Voting.MaxFilterType %d", p.max_filter_type);
   return PCDB_OK;
 }
 
@@ -555,6 +563,9 @@ void pcdb_default_params(pcdb_params* p) {
   p->normal_radius = 0.05f;
   p->consistent_normals_method = 2;
   p->max_filter_type = PCDB_MAXFILTER_NONE;
+  p->radius_type = PCDB_RADIUS_CONFIG;
+  p->radius_factor = 1.0f;
+  p->single_object_max_type = PCDB_SOMAX_DEFAULT;
 }
 
 int pcdb_create(pcdb_ctx** out, int device) {
@@ -665,6 +676,15 @@ int pcdb_set_codebook_sharded(pcdb_ctx* ctx, const float* words, int64_t row_lo,
   return set_codebook_impl(ctx, words, row_hi - row_lo, N_total, row_lo, D, vote_off, vote_xyz, vote_weight, vote_class,
                            vote_instance, vote_bbox, vote_class_weight, kp_train, codeword_ids, codeword_weight,
                            class_sigma2, n_classes, 0);
+}
+
+int pcdb_set_class_dimensions(pcdb_ctx* ctx, const float* first_dim, const float* second_dim, int32_t n_classes) {
+  if (!ctx) return PCDB_E_INVALID;
+  if (n_classes < 0 || (n_classes > 0 && (!first_dim || !second_dim)))
+    return ctx->fail(PCDB_E_INVALID, "bad class dimension arguments");
+  ctx->class_dim_first.assign(first_dim, first_dim + n_classes);
+  ctx->class_dim_second.assign(second_dim, second_dim + n_classes);
+  return PCDB_OK;
 }
 
 int pcdb_voxel_keypoints(pcdb_ctx* ctx, const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B,
@@ -941,7 +961,7 @@ int pcdb_find_maxima(pcdb_ctx* ctx, const pcdb_vote* votes, const int64_t* vote_
   PCDB_TRY(upload(ctx, w.vote_off, vote_off, sizeof(int64_t) * (B + 1)));
   PCDB_TRY(stage_votes_unpack(ctx, B, V));
   int64_t M = 0, members = 0;
-  PCDB_TRY(stage_find_maxima(ctx, B, V, &M, &members));
+  PCDB_TRY(stage_find_maxima(ctx, B, V, false, &M, &members));
   ctx->last_V = V;
   ctx->last_M = M;
   ctx->last_members = members;
@@ -1025,7 +1045,7 @@ static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, bool has
   PCDB_CUDA(cudaEventRecord(ctx->ev[3], st));
   pcdb_trace_point(ctx, "votes");
   int64_t M = 0, members = 0;
-  PCDB_TRY(stage_find_maxima(ctx, B, V, &M, &members));
+  PCDB_TRY(stage_find_maxima(ctx, B, V, true, &M, &members));
   PCDB_CUDA(cudaEventRecord(ctx->ev[4], st));
   pcdb_trace_point(ctx, "maxima");
   ctx->stats.n_votes += V;

@@ -96,7 +96,8 @@ struct Codebook_d {
   X(mpos) X(mseg) X(mem_cnt) X(mem_off) X(mem_idx) X(mem_w) \
   X(max_raw) X(max_sorted) X(max_kept) X(max_first) X(labels) X(nbr_cnt) \
   X(nbr_off) X(nbr_key) X(nbr_key2) X(merge_a) X(merge_b) X(nrm_pca) \
-  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len) X(feat_kp) X(vote_feat)
+  X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len) X(feat_kp) X(vote_feat) \
+  X(ms_grp) X(ms_close) X(ms_src_dst) X(ms_cls_h) X(ms_cloud_cm) X(mem_idx2) X(mem_w2)
 struct Workspace {
 #define X(n) DevBuf n;
   PCDB_WS_FIELDS(X)
@@ -129,6 +130,7 @@ struct pcdb_ctx {
   bool comm_events_valid = false;
   float* lab_lut_d = nullptr;  // 256 + 4000 floats, built on the host with powf (features_cshot.cpp:52-71)
   // host mirrors of the last batch (for pcdb_get_votes / pcdb_get_maximum_votes)
+  std::vector<float> class_dim_first, class_dim_second;  // Voting::m_dimensions_map by class id (pcdb_set_class_dimensions)
   int64_t last_V = 0, last_M = 0, last_members = 0;
   int last_B = 0;
   std::vector<int64_t> h_off_a, h_off_b;

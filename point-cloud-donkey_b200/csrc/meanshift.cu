@@ -11,17 +11,30 @@
 // sort of the bin keys, every seed iterates in its own warp over the group's votes (16 B per vote, L1/L2 resident),
 // and the small order-dependent tails (average / suppress / cumulative re-weighting) run one warp or block per
 // group exactly in the reference's order.  Membership tests are the kd-tree's float test d^2 < float(h*h).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "stages.h"
 
 namespace {
 
 struct MsP {
-  float h, r2, hh, bin, thr;
+  float h_cfg, thr;        // Voting.Bandwidth, Voting.Threshold
   int max_iter, kernel, suppression, min_votes, best_k, average_rotation, n_classes;
   float min_threshold;
   int cross_class_filter;  // PCDB_MAXFILTER_* applied per cloud when !single_object_mode
+  int radius_type;         // PCDB_RADIUS_*
+  int single_max;          // PCDB_SOMAX_* when single_object_mode, else 0 (mean shift)
+  // (h, r2 = float(double h * h), hh = float h * h, bin = 2 h / sqrt 2) of every (cloud, class) vote group: the search
+  // distance is per class (BinOrBandwidthType) or even per group (single-object max types), k_group_params fills it
+  const float4* grp;
+  const float* cls_h;      // [n_classes] MaximaHandler::getSearchDistForClass for the cross-class filters
 };
+
+__device__ __forceinline__ float4 make_hp(float h) {
+  return make_float4(h, (float)((double)h * (double)h), __fmul_rn(h, h), __fdiv_rn(__fmul_rn(h, 2.0f), sqrtf(2.f)));
+}
 
 __device__ __forceinline__ float ms_profile(int kernel, float u) {
   // kernelGaussian: float profile = exp(-0.5 * x) evaluated in double (voting_mean_shift.cpp:396-400)
@@ -59,16 +72,18 @@ __global__ void k_vote_keys(const pcdb_vote* __restrict__ votes, const int* __re
 }
 
 __global__ void k_gather_pw(const int* __restrict__ ord, long long V, const float4* __restrict__ pw, MsP P,
-                            float4* pwS, float* wwork, unsigned long long* seedkey, int* ident) {
+                            const int* __restrict__ seg_id, const int* __restrict__ seg_head, float4* pwS,
+                            float* wwork, unsigned long long* seedkey, int* ident) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= V) return;
   float4 p = pw[ord[t]];
   pwS[t] = p;
   wwork[t] = p.w;
+  const float bin = P.grp[seg_id[t] + seg_head[t] - 1].w;
   // createSeeds: key = (int)floor(pos / binSize + 0.5)  (float division, double add/floor)  (:431-449)
-  long long kx = (long long)floor((double)__fdiv_rn(p.x, P.bin) + 0.5);
-  long long ky = (long long)floor((double)__fdiv_rn(p.y, P.bin) + 0.5);
-  long long kz = (long long)floor((double)__fdiv_rn(p.z, P.bin) + 0.5);
+  long long kx = (long long)floor((double)__fdiv_rn(p.x, bin) + 0.5);
+  long long ky = (long long)floor((double)__fdiv_rn(p.y, bin) + 0.5);
+  long long kz = (long long)floor((double)__fdiv_rn(p.z, bin) + 0.5);
   const long long lim = (1ll << 20) - 1;
   kx = max(-lim, min(lim, kx)) + (1ll << 20);
   ky = max(-lim, min(lim, ky)) + (1ll << 20);
@@ -142,6 +157,79 @@ __global__ void k_seed_list(const int* __restrict__ head, const int* __restrict_
   }
 }
 
+// ---- per-group search distance (voting_mean_shift.cpp:47-49,124-155; maxima_handler.cpp:509-521) -------------------
+// One warp per (cloud, class) group.  Mean-shift mode: h = the class' search distance.  Single-object max types (no
+// mean shift): BandwidthVotes = the same, ModelRadiusVotes = the cloud's model radius, VotingSpaceVotes = the distance
+// of the farthest vote of the group from the cloud's centroid; the group's single maximum sits at that centroid.
+__global__ void k_group_params(const int* __restrict__ nseg_ptr, const unsigned* __restrict__ seg_key,
+                               const int* __restrict__ seg_start, const float4* __restrict__ pw,
+                               const int* __restrict__ ord, MsP P, const float4* __restrict__ cloud_cm, float4* grp,
+                               int* seed_first, float4* max_pos, int* n_max) {
+  const int seg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  const int nseg = *nseg_ptr;
+  if (seg > nseg) return;
+  if (seg == nseg) {
+    if (lane == 0 && P.single_max) seed_first[seg] = seg;
+    return;
+  }
+  const unsigned cls = seg_key[seg] % (unsigned)P.n_classes, cloud = seg_key[seg] / (unsigned)P.n_classes;
+  float h = P.cls_h[cls];
+  if (P.single_max) {
+    const float4 cm = cloud_cm[cloud];  // centroid xyz, model radius
+    if (P.single_max == PCDB_SOMAX_MODEL_RADIUS) h = cm.w;
+    if (P.single_max == PCDB_SOMAX_VOTING_SPACE) {  // SingleObjectHelper::getVotingSpaceSize: sqrt(max squaredNorm)
+      float mx = 0.f;
+      for (int t = seg_start[seg] + lane; t < seg_start[seg + 1]; t += 32) {
+        const float4 p = pw[ord[t]];
+        mx = fmaxf(mx, sqdist3_rn(p.x, p.y, p.z, cm.x, cm.y, cm.z));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      h = __fsqrt_rn(mx);
+    }
+    if (lane == 0) {
+      seed_first[seg] = seg;  // slot of the group's single maximum
+      max_pos[seg] = make_float4(cm.x, cm.y, cm.z, 1.f);
+      n_max[seg] = 1;
+    }
+  }
+  if (lane == 0) grp[seg] = make_hp(h);
+}
+
+// pcl::compute3DCentroid of the cloud Voting::findMaxima is handed (the surface points: finite points with finite
+// normals) — sequential float sums and one division, as the Eigen::Vector4f accumulation does — and
+// SingleObjectHelper::getModelRadius (farthest point from it).  One warp per cloud; lane 0 owns the ordered sums.
+__global__ void k_cloud_centroid(const float4* __restrict__ surf, const long long* __restrict__ surf_off, int B,
+                                 float4* cloud_cm) {
+  const int b = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const long long s0 = surf_off[b], s1 = surf_off[b + 1];
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  if (lane == 0) {
+    for (long long i = s0; i < s1; ++i) {
+      const float4 p = surf[i];
+      cx = __fadd_rn(cx, p.x);
+      cy = __fadd_rn(cy, p.y);
+      cz = __fadd_rn(cz, p.z);
+    }
+    const float n = (float)(s1 - s0);
+    cx = __fdiv_rn(cx, n);
+    cy = __fdiv_rn(cy, n);
+    cz = __fdiv_rn(cz, n);
+  }
+  cx = __shfl_sync(0xffffffffu, cx, 0);
+  cy = __shfl_sync(0xffffffffu, cy, 0);
+  cz = __shfl_sync(0xffffffffu, cz, 0);
+  float r = 0.f;
+  for (long long i = s0 + lane; i < s1; i += 32) {
+    const float4 p = surf[i];
+    r = fmaxf(r, norm3_rn(p.x, p.y, p.z, cx, cy, cz));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if (lane == 0) cloud_cm[b] = make_float4(cx, cy, cz, r);
+}
+
 // ---- iDoMeanShift / computeMeanShift: one warp per seed -------------------------------------------------------
 __global__ void __launch_bounds__(128) k_meanshift(const int* __restrict__ n_seeds_ptr,
                                                    const unsigned long long* __restrict__ seed_key,
@@ -153,10 +241,11 @@ __global__ void __launch_bounds__(128) k_meanshift(const int* __restrict__ n_see
   const unsigned long long key = seed_key[warp];
   const int seg = seed_seg[warp];
   const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+  const float4 hp = P.grp[seg];
   // seed position = key * binSize (int -> float, float multiply)  (:466-470)
-  float cx = __fmul_rn((float)((long long)(key & 0x1fffff) - (1ll << 20)), P.bin);
-  float cy = __fmul_rn((float)((long long)((key >> 21) & 0x1fffff) - (1ll << 20)), P.bin);
-  float cz = __fmul_rn((float)((long long)((key >> 42) & 0x1fffff) - (1ll << 20)), P.bin);
+  float cx = __fmul_rn((float)((long long)(key & 0x1fffff) - (1ll << 20)), hp.w);
+  float cy = __fmul_rn((float)((long long)((key >> 21) & 0x1fffff) - (1ll << 20)), hp.w);
+  float cz = __fmul_rn((float)((long long)((key >> 42) & 0x1fffff) - (1ll << 20)), hp.w);
   int iter = 0;
   float diff = 0.f;
   bool skip = false;
@@ -167,8 +256,8 @@ __global__ void __launch_bounds__(128) k_meanshift(const int* __restrict__ n_see
     for (int t = s0 + lane; t < s1; t += 32) {
       float4 p = pwS[t];
       float d2 = sqdist3_rn(cx, cy, cz, p.x, p.y, p.z);
-      if (d2 < P.r2) {
-        float u = __fdiv_rn(d2, P.hh);
+      if (d2 < hp.y) {
+        float u = __fdiv_rn(d2, hp.z);
         float g = ms_g(P.kernel, u, p.w);
         sx = __fadd_rn(sx, __fmul_rn(g, p.x));
         sy = __fadd_rn(sy, __fmul_rn(g, p.y));
@@ -203,12 +292,12 @@ __global__ void __launch_bounds__(128) k_meanshift(const int* __restrict__ n_see
 
 // density of one position over a vote group, warp-cooperative (estimateDensity :247-285)
 __device__ float group_density(const float4* __restrict__ pwS, const float* __restrict__ w, int s0, int s1, float x,
-                               float y, float z, const MsP& P, int lane) {
+                               float y, float z, const MsP& P, const float4 hp, int lane) {
   float dens = 0.f;
   for (int t = s0 + lane; t < s1; t += 32) {
     float4 p = pwS[t];
     float d2 = sqdist3_rn(x, y, z, p.x, p.y, p.z);
-    if (d2 < P.r2) dens = __fadd_rn(dens, __fmul_rn(ms_profile(P.kernel, __fdiv_rn(d2, P.hh)), w[t]));
+    if (d2 < hp.y) dens = __fadd_rn(dens, __fmul_rn(ms_profile(P.kernel, __fdiv_rn(d2, hp.z)), w[t]));
   }
   return warp_sum(dens);
 }
@@ -223,6 +312,7 @@ __global__ void __launch_bounds__(32) k_ms_tail(const int* __restrict__ nseg_ptr
   if (seg >= *nseg_ptr) return;
   const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
   const int f0 = seed_first[seg], f1 = seed_first[seg + 1];
+  const float4 hp = P.grp[seg];
   float4* C = cen + f0;
   float4* C2 = cen2 + f0;
   float* Dn = dens + f0;
@@ -240,7 +330,7 @@ __global__ void __launch_bounds__(32) k_ms_tail(const int* __restrict__ nseg_ptr
   __syncwarp();
   for (int i = 0; i < M; ++i) {
     float4 c = C[i];
-    float d = group_density(pwS, w0, s0, s1, c.x, c.y, c.z, P, lane);
+    float d = group_density(pwS, w0, s0, s1, c.x, c.y, c.z, P, hp, lane);
     if (lane == 0) Dn[i] = d;
   }
   __syncwarp();
@@ -271,7 +361,7 @@ __global__ void __launch_bounds__(32) k_ms_tail(const int* __restrict__ nseg_ptr
         float4 b = make_float4(0, 0, 0, 0);
         if (j < M && !Fl[j]) {
           b = C[j];
-          hit = norm3_rn(a.x, a.y, a.z, b.x, b.y, b.z) < P.h;
+          hit = norm3_rn(a.x, a.y, a.z, b.x, b.y, b.z) < hp.x;
         }
         unsigned m = __ballot_sync(0xffffffffu, hit);
         if (hit) Fl[j] = 1;
@@ -303,7 +393,7 @@ __global__ void __launch_bounds__(32) k_ms_tail(const int* __restrict__ nseg_ptr
     __syncwarp();
     for (int i = 0; i < M; ++i) {
       float4 c = C[i];
-      float d = group_density(pwS, w0, s0, s1, c.x, c.y, c.z, P, lane);
+      float d = group_density(pwS, w0, s0, s1, c.x, c.y, c.z, P, hp, lane);
       if (lane == 0) Dn[i] = d;
     }
     __syncwarp();
@@ -335,7 +425,7 @@ __global__ void __launch_bounds__(32) k_ms_tail(const int* __restrict__ nseg_ptr
     ++nm;
     for (int i = lane; i < M; i += 32) {
       float4 b = C[i];
-      if (i == bi || norm3_rn(c.x, c.y, c.z, b.x, b.y, b.z) < P.h) Dn[i] = -1.f;
+      if (i == bi || norm3_rn(c.x, c.y, c.z, b.x, b.y, b.z) < hp.x) Dn[i] = -1.f;
     }
     __syncwarp();
   }
@@ -367,10 +457,11 @@ __global__ void k_member_count(const int* __restrict__ M_ptr, const float4* __re
   }
   float4 c = mpos[m];
   int seg = mseg[m];
+  const float r2 = P.grp[seg].y;
   int cnt = 0;
   for (int t = seg_start[seg] + lane; t < seg_start[seg + 1]; t += 32) {
     float4 p = pwS[t];
-    if (sqdist3_rn(c.x, c.y, c.z, p.x, p.y, p.z) < P.r2) ++cnt;
+    if (sqdist3_rn(c.x, c.y, c.z, p.x, p.y, p.z) < r2) ++cnt;
   }
   cnt = warp_sum(cnt);
   if (lane == 0) mem_cnt[m] = cnt;
@@ -386,6 +477,7 @@ __global__ void __launch_bounds__(32) k_ms_reweight(const int* __restrict__ nseg
   const int seg = blockIdx.x, lane = threadIdx.x;
   if (seg >= *nseg_ptr) return;
   const int s0 = seg_start[seg], s1 = seg_start[seg + 1];
+  const float4 hp = P.grp[seg];
   for (int m = max_off[seg]; m < max_off[seg] + n_max[seg]; ++m) {
     float4 c = mpos[m];
     int o = mem_off[m];
@@ -396,9 +488,9 @@ __global__ void __launch_bounds__(32) k_ms_reweight(const int* __restrict__ nseg
       if (t < s1) {
         float4 p = pwS[t];
         float d2 = sqdist3_rn(c.x, c.y, c.z, p.x, p.y, p.z);
-        if (d2 < P.r2) {
+        if (d2 < hp.y) {
           in = true;
-          nw = __fmul_rn(ms_profile(P.kernel, __fdiv_rn(d2, P.hh)), wwork[t]);
+          nw = __fmul_rn(ms_profile(P.kernel, __fdiv_rn(d2, hp.z)), wwork[t]);
           wwork[t] = nw;
         }
       }
@@ -562,8 +654,9 @@ __global__ void k_max_reduce(const int* __restrict__ M_ptr, const float4* __rest
 
 // ---- per-cloud sort / normalise / threshold / best-K / label (voting.cpp:272-323), one warp per cloud ----------
 __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const unsigned* __restrict__ seg_key,
-                                 const int* __restrict__ max_off, pcdb_maximum* raw, MsP P, int* flag,
-                                 pcdb_maximum* sorted, int* kept, int* first, int* label) {
+                                 const int* __restrict__ max_off, const int* __restrict__ mem_off, pcdb_maximum* raw,
+                                 MsP P, int* flag, int* close_list, int* src_dst, pcdb_maximum* sorted, int* kept,
+                                 int* first, int* label) {
   const int b = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const int nseg = *nseg_ptr;
@@ -583,9 +676,12 @@ __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const 
   int g1 = lo;
   const int m0 = max_off[g0], m1 = max_off[g1];
   if (P.cross_class_filter == PCDB_MAXFILTER_SIMPLE) {
-    // MaximaHandler::suppressNeighborMaxima2 (maxima_handler.cpp:227-268), radius = Voting.Bandwidth: keep the heaviest
-    // pending maximum (the first of equal ones), drop every maximum of any class closer than the radius, repeat.  The
-    // list is short and the loop order dependent: one lane.  Dropped maxima get n_votes = 0 and fall out below.
+    // MaximaHandler::suppressNeighborMaxima2 (maxima_handler.cpp:227-268): keep the heaviest pending maximum (the first
+    // of equal ones), drop every maximum of any class closer than the radius, repeat.  The radius is
+    // MaximaHandler::m_radius as iFindMaxima left it (voting_mean_shift.cpp:47-49): Voting.Bandwidth for
+    // BinOrBandwidthType "Config", else the search distance of the class processed BEFORE the last one.  The list is
+    // short and the loop order dependent: one lane.  Dropped maxima get n_votes = 0 and fall out below.
+    const float radius = (P.radius_type != PCDB_RADIUS_CONFIG && g1 - g0 >= 2) ? P.grp[g1 - 2].x : P.h_cfg;
     if (lane == 0) {
       for (int i = m0; i < m1; ++i) flag[i] = (raw[i].n_votes >= P.min_votes && raw[i].n_votes > 0) ? 0 : 2;
       for (;;) {
@@ -597,11 +693,143 @@ __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const 
         const float cx = raw[best].position[0], cy = raw[best].position[1], cz = raw[best].position[2];
         for (int i = m0; i < m1; ++i)
           if (flag[i] == 0 &&
-              norm3_rn(cx, cy, cz, raw[i].position[0], raw[i].position[1], raw[i].position[2]) < P.h)
+              norm3_rn(cx, cy, cz, raw[i].position[0], raw[i].position[1], raw[i].position[2]) < radius)
             flag[i] = 2;
       }
       for (int i = m0; i < m1; ++i)
         if (flag[i] == 2) raw[i].n_votes = 0;
+    }
+    __syncwarp();
+  }
+  if (P.cross_class_filter == PCDB_MAXFILTER_MERGE) {
+    // MaximaHandler::mergeAndFilterMaxima(maxima, true) + mergeMaxima (maxima_handler.cpp:296-383,386-443), order
+    // dependent: one lane.  flag: 0 pending, 1 subsumed (dirty), 2 below MinVotesThreshold.  `sorted` serves as the
+    // output list until the ranking below re-reads `raw`; src_dst[s] = where source maximum s's member votes go in the
+    // re-packed member arrays (-1: dropped), the cloud's members keep their range [mem_off[m0], mem_off[m1]).
+    if (lane == 0) {
+      int n_out = 0, new_off = mem_off[m0];
+      for (int i = m0; i < m1; ++i) {
+        flag[i] = (raw[i].n_votes >= P.min_votes && raw[i].n_votes > 0) ? 0 : 2;
+        src_dst[i] = -1;
+      }
+      for (int i = m0; i < m1; ++i) {
+        if (flag[i] != 0) continue;
+        const float sd = P.cls_h[raw[i].class_id];
+        int n_close = 0;
+        for (int j = i + 1; j < m1; ++j) {
+          if (flag[j] != 0) continue;
+          const float dist = norm3_rn(raw[j].position[0], raw[j].position[1], raw[j].position[2], raw[i].position[0],
+                                      raw[i].position[1], raw[i].position[2]);
+          if (dist < sd && P.cls_h[raw[j].class_id] <= sd) {
+            close_list[m0 + n_close++] = j;
+            flag[j] = 1;
+          }
+        }
+        if (n_close == 0) {
+          pcdb_maximum r = raw[i];
+          src_dst[i] = new_off;
+          r.vote_begin = new_off;
+          new_off += r.n_votes;
+          sorted[m0 + n_out++] = r;
+          continue;
+        }
+        close_list[m0 + n_close++] = i;  // the maximum itself comes last
+        // classes of the group in ascending order (std::map), each merged in list order; the heaviest merged one stays
+        pcdb_maximum best;
+        best.weight = 0.f;
+        best.n_votes = 0;
+        unsigned best_cls = 0xffffffffu;
+        long long prev_cls = -1;
+        for (;;) {
+          long long cls = -1;
+          for (int c = 0; c < n_close; ++c) {
+            const long long k = (long long)raw[close_list[m0 + c]].class_id;
+            if (k > prev_cls && (cls < 0 || k < cls)) cls = k;
+          }
+          if (cls < 0) break;
+          prev_cls = cls;
+          pcdb_maximum r;
+          r.position[0] = r.position[1] = r.position[2] = 0.f;
+          r.bbox_size[0] = r.bbox_size[1] = r.bbox_size[2] = 0.f;
+          r.bbox_quat[0] = 1.f;
+          r.bbox_quat[1] = r.bbox_quat[2] = r.bbox_quat[3] = 0.f;
+          r.weight = 0.f;
+          r.n_votes = 0;
+          r.class_id = (unsigned)cls;
+          r.instance_id = 0;
+          r.instance_weight = 0.f;
+          for (int c = 0; c < n_close; ++c) {
+            const pcdb_maximum& mx = raw[close_list[m0 + c]];
+            if ((long long)mx.class_id != cls) continue;
+            const float rw = r.weight, mw = mx.weight, den = __fadd_rn(rw, mw);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              r.position[a] = __fdiv_rn(__fadd_rn(__fmul_rn(r.position[a], rw), __fmul_rn(mx.position[a], mw)), den);
+              r.bbox_size[a] = __fdiv_rn(__fadd_rn(__fmul_rn(r.bbox_size[a], rw), __fmul_rn(mx.bbox_size[a], mw)), den);
+            }
+            float S[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b2 = 0; b2 < 4; ++b2)
+                S[a][b2] = __fadd_rn(__fadd_rn(0.f, __fmul_rn(__fmul_rn(rw, r.bbox_quat[a]), r.bbox_quat[b2])),
+                                     __fmul_rn(__fmul_rn(mw, mx.bbox_quat[a]), mx.bbox_quat[b2]));
+            quat_avg_eig(S, r.bbox_quat);
+            r.weight = __fadd_rn(r.weight, mx.weight);
+            r.n_votes += mx.n_votes;
+            // instance weights summed per id over the merged maxima so far; largest wins, ascending id on ties (std::map)
+            float bw = 0.f;
+            unsigned bid = 0;
+            float w_id0 = 0.f;
+            bool any = false;
+            for (int d = 0; d <= c; ++d) {
+              const pcdb_maximum& md = raw[close_list[m0 + d]];
+              if ((long long)md.class_id != cls) continue;
+              bool first_of_id = true;
+              for (int e = 0; e < d; ++e) {
+                const pcdb_maximum& me = raw[close_list[m0 + e]];
+                if ((long long)me.class_id == cls && me.instance_id == md.instance_id) first_of_id = false;
+              }
+              if (!first_of_id) continue;
+              float tot = 0.f;
+              for (int e = d; e <= c; ++e) {
+                const pcdb_maximum& me = raw[close_list[m0 + e]];
+                if ((long long)me.class_id == cls && me.instance_id == md.instance_id)
+                  tot = __fadd_rn(tot, me.instance_weight);
+              }
+              if (md.instance_id == 0) w_id0 = tot;
+              if (tot > bw || (tot == bw && tot > 0.f && any && md.instance_id < bid)) {
+                bw = tot;
+                bid = md.instance_id;
+                any = true;
+              }
+            }
+            if (!any) {  // no instance weight > 0: the reference leaves the id uninitialised; defined as 0
+              bid = 0;
+              bw = w_id0;
+            }
+            r.instance_id = bid;
+            r.instance_weight = bw;
+          }
+          r.raw_weight = r.weight;
+          if (r.weight > best.weight) {
+            best = r;
+            best_cls = (unsigned)cls;
+          }
+        }
+        if (best_cls != 0xffffffffu) {
+          best.vote_begin = new_off;
+          for (int c = 0; c < n_close; ++c) {
+            const int s = close_list[m0 + c];
+            if (raw[s].class_id != best_cls) continue;
+            src_dst[s] = new_off;
+            new_off += raw[s].n_votes;
+          }
+          sorted[m0 + n_out++] = best;
+        }
+      }
+      for (int i = 0; i < n_out; ++i) raw[m0 + i] = sorted[m0 + i];
+      for (int i = m0 + n_out; i < m1; ++i) raw[i].n_votes = 0;
     }
     __syncwarp();
   }
@@ -647,6 +875,19 @@ __global__ void k_cloud_finalize(int B, const int* __restrict__ nseg_ptr, const 
   }
 }
 
+// "Merge" filter: member votes of the surviving maxima, re-packed in merge order; one warp per source maximum
+__global__ void k_repack_members(const int* __restrict__ M_ptr, const int* __restrict__ mem_off,
+                                 const int* __restrict__ src_dst, const long long* __restrict__ mem_idx,
+                                 const float* __restrict__ mem_w, long long* mem_idx2, float* mem_w2) {
+  const int m = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (m >= *M_ptr || src_dst[m] < 0) return;
+  const int o0 = mem_off[m], n = mem_off[m + 1] - o0, d0 = src_dst[m];
+  for (int i = lane; i < n; i += 32) {
+    mem_idx2[d0 + i] = mem_idx[o0 + i];
+    mem_w2[d0 + i] = mem_w[o0 + i];
+  }
+}
+
 __global__ void k_fill_labels(int B, int* kept, int* first, int* label) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -659,7 +900,7 @@ __global__ void k_fill_labels(int B, int* kept, int* first, int* label) {
 
 // votes (device, V records), vote_pw, vote_cloud already in the workspace.  Leaves per-cloud sorted maxima in
 // ws.max_sorted (+ ws.max_kept / ws.max_first), labels in ws.labels and member lists in ws.mem_idx / ws.mem_w.
-int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* members_out) {
+int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, bool have_cloud, int64_t* M_out, int64_t* members_out) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const pcdb_params& p = ctx->prm;
@@ -676,10 +917,7 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   }
   if ((int64_t)B * C > 0xffffffffll) return ctx->fail(PCDB_E_INVALID, "B * n_classes overflows the 32-bit group key");
   MsP P;
-  P.h = p.bandwidth;
-  P.r2 = (float)((double)p.bandwidth * (double)p.bandwidth);  // pcl radiusSearch(double) -> float(r*r)
-  P.hh = p.bandwidth * p.bandwidth;                           // float h*h of the kernels (:271,:313,:356)
-  P.bin = (p.bandwidth * 2.0f) / sqrtf(2);                    // iGetSeedsRange (:33-37)
+  P.h_cfg = p.bandwidth;
   P.thr = p.ms_threshold;
   P.max_iter = p.ms_max_iter;
   P.kernel = p.ms_kernel;
@@ -690,9 +928,26 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   P.n_classes = C;
   P.min_threshold = p.min_threshold;
   P.cross_class_filter = p.single_object_mode ? PCDB_MAXFILTER_NONE : p.max_filter_type;
-  if (P.cross_class_filter == PCDB_MAXFILTER_MERGE)
-    return ctx->fail(PCDB_E_UNSUPPORTED, "Voting.MaxFilterType \"Merge\" is not built (SURVEY 8f-4); use None or Simple");
-  if (!(P.bin > 0.f)) return ctx->fail(PCDB_E_INVALID, "Voting.Bandwidth must be positive");
+  P.radius_type = p.radius_type;
+  P.single_max = p.single_object_mode ? p.single_object_max_type : PCDB_SOMAX_DEFAULT;
+  if (!(p.bandwidth > 0.f)) return ctx->fail(PCDB_E_INVALID, "Voting.Bandwidth must be positive");
+  if (P.single_max != PCDB_SOMAX_DEFAULT && !have_cloud)
+    return ctx->fail(PCDB_E_UNSUPPORTED,
+                     "Voting.SingleObjectMaxType other than Default needs the cloud (centroid, model radius): use "
+                     "pcdb_classify_batch");
+  // MaximaHandler::getSearchDistForClass per class (maxima_handler.cpp:509-521)
+  std::vector<float> cls_h((size_t)C, p.bandwidth);
+  if (p.radius_type != PCDB_RADIUS_CONFIG) {
+    const std::vector<float>& dims = p.radius_type == PCDB_RADIUS_FIRST_DIM ? ctx->class_dim_first : ctx->class_dim_second;
+    if ((int)dims.size() < C)
+      return ctx->fail(PCDB_E_STATE, "Voting.BinOrBandwidthType needs the learned class dimensions: call "
+                                     "pcdb_set_class_dimensions for all %d classes", C);
+    for (int c = 0; c < C; ++c) cls_h[c] = dims[c] * p.radius_factor;
+  }
+  PCDB_CUDA(w.ms_cls_h.ensure(sizeof(float) * (size_t)C));
+  PCDB_CUDA(cudaMemcpyAsync(w.ms_cls_h.p, cls_h.data(), sizeof(float) * (size_t)C, cudaMemcpyHostToDevice, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));  // cls_h is a local
+  P.cls_h = w.ms_cls_h.as<float>();
 
   const size_t n = (size_t)V + 2;
   PCDB_CUDA(w.vote_key.ensure(sizeof(unsigned) * n));
@@ -735,6 +990,10 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   PCDB_CUDA(w.max_raw.ensure(sizeof(pcdb_maximum) * n));
   PCDB_CUDA(w.max_sorted.ensure(sizeof(pcdb_maximum) * n));
   PCDB_CUDA(w.max_flag.ensure(sizeof(int) * n));
+  PCDB_CUDA(w.ms_grp.ensure(sizeof(float4) * n));
+  PCDB_CUDA(w.ms_close.ensure(sizeof(int) * n));
+  PCDB_CUDA(w.ms_src_dst.ensure(sizeof(int) * n));
+  P.grp = w.ms_grp.as<float4>();
 
   const unsigned gV = cdiv(V, 256), gV1 = cdiv(V + 1, 256);
   const pcdb_vote* votes = w.votes.as<pcdb_vote>();
@@ -745,10 +1004,6 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
   while ((1ll << bits) < (int64_t)B * C && bits < 32) ++bits;
   PCDB_TRY(pcdb_cub_sort_pairs_u32(ctx, w.vote_key.as<unsigned>(), w.vote_key2.as<unsigned>(), w.vote_ord.as<int>(),
                                    w.vote_ord2.as<int>(), V, bits));
-  k_gather_pw<<<gV, 256, 0, st>>>(w.vote_ord2.as<int>(), V, w.vote_pw.as<float4>(), P, w.vote_pwS.as<float4>(),
-                                  w.vote_w_work.as<float>(), w.seed_k0.as<unsigned long long>(), w.seed_i0.as<int>());
-  PCDB_LAUNCH_CHECK();
-  PCDB_CUDA(cudaMemcpyAsync(w.vote_w0.p, w.vote_w_work.p, sizeof(float) * V, cudaMemcpyDeviceToDevice, st));
   k_heads_u32<<<gV1, 256, 0, st>>>(w.vote_key2.as<unsigned>(), V, w.seg2_head.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.seg2_head.as<int>(), w.seg2_id.as<int>(), V + 1));
@@ -756,39 +1011,57 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
                                   w.seg2_start.as<int>(), w.seg2_key.as<unsigned>());
   PCDB_LAUNCH_CHECK();
   const int* nseg_ptr = w.seg2_id.as<int>() + V;
-  // seeds: sort bin keys, then stable by group
-  PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.seed_k0.as<unsigned long long>(), w.seed_k1.as<unsigned long long>(),
-                                   w.seed_i0.as<int>(), w.seed_i1.as<int>(), V, 63));
-  k_gather_segkey<<<gV, 256, 0, st>>>(w.seed_i1.as<int>(), w.seg2_id.as<int>(), w.seg2_head.as<int>(), V,
-                                      w.seed_s0.as<unsigned>(),
-                                      w.seed_i2.as<int>());
-  PCDB_LAUNCH_CHECK();
-  int sbits = 1;
-  while ((1ll << sbits) < V + 1 && sbits < 32) ++sbits;
-  PCDB_TRY(pcdb_cub_sort_pairs_u32(ctx, w.seed_s0.as<unsigned>(), w.seed_s1.as<unsigned>(), w.seed_i2.as<int>(),
-                                   w.seed_i3.as<int>(), V, sbits));
-  k_seed_heads<<<gV1, 256, 0, st>>>(w.seed_s1.as<unsigned>(), w.seed_i3.as<int>(),
-                                    w.seed_k1.as<unsigned long long>(), V, w.seed_kS.as<unsigned long long>(),
-                                    w.seed_head.as<int>());
-  PCDB_LAUNCH_CHECK();
-  PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.seed_head.as<int>(), w.seed_id.as<int>(), V + 1));
-  k_seed_list<<<gV1, 256, 0, st>>>(w.seed_head.as<int>(), w.seed_id.as<int>(), w.seed_kS.as<unsigned long long>(),
-                                   w.seed_s1.as<unsigned>(), V, nseg_ptr, w.seed_key.as<unsigned long long>(),
-                                   w.seed_seg.as<int>(), w.seed_first.as<int>());
-  PCDB_LAUNCH_CHECK();
-  const int* nseeds_ptr = w.seed_id.as<int>() + V;
-  // mean shift: one warp per seed (at most V seeds)
-  k_meanshift<<<cdiv(V * 32, 128), 128, 0, st>>>(nseeds_ptr, w.seed_key.as<unsigned long long>(), w.seed_seg.as<int>(),
-                                                 w.seg2_start.as<int>(), w.vote_pwS.as<float4>(), P,
-                                                 w.centers.as<float4>());
-  PCDB_LAUNCH_CHECK();
   const unsigned gseg = (unsigned)std::min<int64_t>(V, (int64_t)B * C);
   PCDB_CUDA(cudaMemsetAsync(w.max_n.p, 0, sizeof(int) * n, st));
-  k_ms_tail<<<gseg, 32, 0, st>>>(nseg_ptr, w.seg2_start.as<int>(), w.seed_first.as<int>(), w.centers.as<float4>(),
-                                 w.vote_pwS.as<float4>(), w.vote_w0.as<float>(), P, w.ms_cen.as<float4>(),
-                                 w.ms_cen2.as<float4>(), w.ms_dens.as<float>(), w.ms_flag.as<int>(),
-                                 w.max_pos.as<float4>(), w.max_n.as<int>());
+  if (P.single_max != PCDB_SOMAX_DEFAULT) {  // centroid + model radius of the cloud handed to Voting::findMaxima
+    PCDB_CUDA(w.ms_cloud_cm.ensure(sizeof(float4) * (size_t)(B + 1)));
+    k_cloud_centroid<<<cdiv((int64_t)B * 32, 128), 128, 0, st>>>(w.surf4.as<float4>(), w.surf_off.as<long long>(), B,
+                                                                 w.ms_cloud_cm.as<float4>());
+    PCDB_LAUNCH_CHECK();
+  }
+  // search distance of every (cloud, class) group; in the single-object max types also the group's one maximum
+  k_group_params<<<cdiv(((int64_t)gseg + 1) * 32, 128), 128, 0, st>>>(
+      nseg_ptr, w.seg2_key.as<unsigned>(), w.seg2_start.as<int>(), w.vote_pw.as<float4>(), w.vote_ord2.as<int>(), P,
+      w.ms_cloud_cm.as<float4>(), w.ms_grp.as<float4>(), w.seed_first.as<int>(), w.max_pos.as<float4>(),
+      w.max_n.as<int>());
   PCDB_LAUNCH_CHECK();
+  k_gather_pw<<<gV, 256, 0, st>>>(w.vote_ord2.as<int>(), V, w.vote_pw.as<float4>(), P, w.seg2_id.as<int>(),
+                                  w.seg2_head.as<int>(), w.vote_pwS.as<float4>(), w.vote_w_work.as<float>(),
+                                  w.seed_k0.as<unsigned long long>(), w.seed_i0.as<int>());
+  PCDB_LAUNCH_CHECK();
+  PCDB_CUDA(cudaMemcpyAsync(w.vote_w0.p, w.vote_w_work.p, sizeof(float) * V, cudaMemcpyDeviceToDevice, st));
+  if (P.single_max == PCDB_SOMAX_DEFAULT) {
+    // seeds: sort bin keys, then stable by group
+    PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.seed_k0.as<unsigned long long>(), w.seed_k1.as<unsigned long long>(),
+                                     w.seed_i0.as<int>(), w.seed_i1.as<int>(), V, 63));
+    k_gather_segkey<<<gV, 256, 0, st>>>(w.seed_i1.as<int>(), w.seg2_id.as<int>(), w.seg2_head.as<int>(), V,
+                                        w.seed_s0.as<unsigned>(), w.seed_i2.as<int>());
+    PCDB_LAUNCH_CHECK();
+    int sbits = 1;
+    while ((1ll << sbits) < V + 1 && sbits < 32) ++sbits;
+    PCDB_TRY(pcdb_cub_sort_pairs_u32(ctx, w.seed_s0.as<unsigned>(), w.seed_s1.as<unsigned>(), w.seed_i2.as<int>(),
+                                     w.seed_i3.as<int>(), V, sbits));
+    k_seed_heads<<<gV1, 256, 0, st>>>(w.seed_s1.as<unsigned>(), w.seed_i3.as<int>(),
+                                      w.seed_k1.as<unsigned long long>(), V, w.seed_kS.as<unsigned long long>(),
+                                      w.seed_head.as<int>());
+    PCDB_LAUNCH_CHECK();
+    PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.seed_head.as<int>(), w.seed_id.as<int>(), V + 1));
+    k_seed_list<<<gV1, 256, 0, st>>>(w.seed_head.as<int>(), w.seed_id.as<int>(), w.seed_kS.as<unsigned long long>(),
+                                     w.seed_s1.as<unsigned>(), V, nseg_ptr, w.seed_key.as<unsigned long long>(),
+                                     w.seed_seg.as<int>(), w.seed_first.as<int>());
+    PCDB_LAUNCH_CHECK();
+    const int* nseeds_ptr = w.seed_id.as<int>() + V;
+    // mean shift: one warp per seed (at most V seeds)
+    k_meanshift<<<cdiv(V * 32, 128), 128, 0, st>>>(nseeds_ptr, w.seed_key.as<unsigned long long>(),
+                                                   w.seed_seg.as<int>(), w.seg2_start.as<int>(),
+                                                   w.vote_pwS.as<float4>(), P, w.centers.as<float4>());
+    PCDB_LAUNCH_CHECK();
+    k_ms_tail<<<gseg, 32, 0, st>>>(nseg_ptr, w.seg2_start.as<int>(), w.seed_first.as<int>(), w.centers.as<float4>(),
+                                   w.vote_pwS.as<float4>(), w.vote_w0.as<float>(), P, w.ms_cen.as<float4>(),
+                                   w.ms_cen2.as<float4>(), w.ms_dens.as<float>(), w.ms_flag.as<int>(),
+                                   w.max_pos.as<float4>(), w.max_n.as<int>());
+    PCDB_LAUNCH_CHECK();
+  }
   // maxima offsets per group (entries past nseg are zero), total M
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.max_n.as<int>(), w.max_off.as<int>(), (int64_t)gseg + 1));
   const int* M_ptr = w.max_off.as<int>() + gseg;
@@ -822,11 +1095,21 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* 
                                                               w.max_raw.as<pcdb_maximum>());
     PCDB_LAUNCH_CHECK();
   }
-  k_cloud_finalize<<<cdiv((int64_t)B * 32, 128), 128, 0, st>>>(B, nseg_ptr, w.seg2_key.as<unsigned>(),
-                                                               w.max_off.as<int>(), w.max_raw.as<pcdb_maximum>(), P,
-                                                               w.max_flag.as<int>(), w.max_sorted.as<pcdb_maximum>(), w.max_kept.as<int>(),
-                                                               w.max_first.as<int>(), w.labels.as<int>());
+  k_cloud_finalize<<<cdiv((int64_t)B * 32, 128), 128, 0, st>>>(
+      B, nseg_ptr, w.seg2_key.as<unsigned>(), w.max_off.as<int>(), w.mem_off.as<int>(), w.max_raw.as<pcdb_maximum>(), P,
+      w.max_flag.as<int>(), w.ms_close.as<int>(), w.ms_src_dst.as<int>(), w.max_sorted.as<pcdb_maximum>(),
+      w.max_kept.as<int>(), w.max_first.as<int>(), w.labels.as<int>());
   PCDB_LAUNCH_CHECK();
+  if (P.cross_class_filter == PCDB_MAXFILTER_MERGE && hM > 0) {  // member votes of merged maxima, in merge order
+    PCDB_CUDA(w.mem_idx2.ensure(sizeof(long long) * ((size_t)hMem + 1)));
+    PCDB_CUDA(w.mem_w2.ensure(sizeof(float) * ((size_t)hMem + 1)));
+    k_repack_members<<<cdiv((int64_t)hM * 32, 128), 128, 0, st>>>(M_ptr, w.mem_off.as<int>(), w.ms_src_dst.as<int>(),
+                                                                  w.mem_idx.as<long long>(), w.mem_w.as<float>(),
+                                                                  w.mem_idx2.as<long long>(), w.mem_w2.as<float>());
+    PCDB_LAUNCH_CHECK();
+    std::swap(w.mem_idx, w.mem_idx2);
+    std::swap(w.mem_w, w.mem_w2);
+  }
   *M_out = hM;
   *members_out = hMem;
   return PCDB_OK;

@@ -42,7 +42,8 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
 
 // meanshift.cu
 int stage_votes_unpack(pcdb_ctx* ctx, int B, int64_t V);
-int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, int64_t* M_out, int64_t* members_out);  // syncs
+// have_cloud: ws.surf4 / ws.surf_off hold the clouds the votes came from (fused path) — the single-object max types need it
+int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, bool have_cloud, int64_t* M_out, int64_t* members_out);  // syncs
 
 // api.cu: exact kNN of device-resident queries against this context's descriptor rows (GEMM or scan by `mode`)
 int pcdb_run_knn(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,

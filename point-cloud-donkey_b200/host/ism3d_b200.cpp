@@ -263,15 +263,35 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   P.best_k = (int)vr.num("BestK", -1);
   P.average_rotation = vr.boolean("AverageRotation", false);
   P.single_object_mode = vr.boolean("SingleObjectMode", false);
+  // MaximaHandler::getSearchDistForClass (maxima_handler.cpp:509-521); an unknown type logs an error and uses the config value
   const std::string rtype = vr.str("BinOrBandwidthType", "Config");
-  if (rtype != "Config" && rtype != "Fixed") throw BadParamException("BinOrBandwidthType \"" + rtype + "\" is a 'next' row (SURVEY 8f)");
+  if (rtype == "Config" || rtype == "Fixed") P.radius_type = PCDB_RADIUS_CONFIG;
+  else if (rtype == "FirstDim" || rtype == "ObjectRadius") P.radius_type = PCDB_RADIUS_FIRST_DIM;
+  else if (rtype == "SecondDim" || rtype == "BoundingBoxMedian") P.radius_type = PCDB_RADIUS_SECOND_DIM;
+  else {
+    log("ERROR", "Invalid radius type: " + rtype + "! Using config value instead.");
+    P.radius_type = PCDB_RADIUS_CONFIG;
+  }
+  P.radius_factor = (float)vr.num("BinOrBandwidthFactor", 1.0);
+  // MaximaHandler::setSingleObjectMaxType (maxima_handler.h:42-58)
   const std::string mtype = vr.str("SingleObjectMaxType", "Default");
-  if (P.single_object_mode && mtype != "None" && mtype != "Default")
-    throw BadParamException("SingleObjectMaxType \"" + mtype + "\" is a 'next' row (SURVEY 8f)");
+  if (mtype == "None" || mtype == "Default") P.single_object_max_type = PCDB_SOMAX_DEFAULT;
+  else if (mtype == "BandwidthVotes") P.single_object_max_type = PCDB_SOMAX_BANDWIDTH;
+  else if (mtype == "VotingSpaceVotes") P.single_object_max_type = PCDB_SOMAX_VOTING_SPACE;
+  else if (mtype == "ModelRadiusVotes") P.single_object_max_type = PCDB_SOMAX_MODEL_RADIUS;
+  else {
+    log("WARN", "Invalid single object maximum type: " + mtype + "! Using default instead.");
+    P.single_object_max_type = PCDB_SOMAX_DEFAULT;
+  }
+  // MaximaHandler::filterMaxima (maxima_handler.cpp:272-295): an unknown type logs an error and filters nothing
   const std::string ftr = vr.str("MaxFilterType", "None");
   if (ftr == "None") P.max_filter_type = PCDB_MAXFILTER_NONE;
   else if (ftr == "Simple") P.max_filter_type = PCDB_MAXFILTER_SIMPLE;
-  else if (!P.single_object_mode) throw BadParamException("MaxFilterType \"" + ftr + "\" is not built (SURVEY 8f-4); use None or Simple");
+  else if (ftr == "Merge") P.max_filter_type = PCDB_MAXFILTER_MERGE;
+  else {
+    log("ERROR", "Invalid maxima filter type specified: " + ftr + "! No filtering is performed!");
+    P.max_filter_type = PCDB_MAXFILTER_NONE;
+  }
   if (vr.boolean("UseGlobalFeatures", false)) throw BadParamException("UseGlobalFeatures=true is outside the built hot path");
   if (vo["Parameters"].isMember("RansacVoteFiltering") && vr.boolean("RansacVoteFiltering", false))
     throw BadParamException("RansacVoteFiltering=true is outside the built hot path");
@@ -516,6 +536,14 @@ void ImplicitShapeModel::uploadCodebook() {
                           c.vote_weight.data(), c.vote_class.data(), c.vote_instance.data(), c.vote_bbox.data(),
                           c.vote_class_weight.data(), c.keypoints.data(), c.ids.data(), c.weights.data(), sigma.data(),
                           n_classes, 0));
+  // Voting::iLoadData -> MaximaHandler::setBoundingBoxMaps (voting.cpp:619-650): the table behind BinOrBandwidthType
+  std::vector<float> d1((size_t)n_classes, 0.f), d2((size_t)n_classes, 0.f);
+  for (const auto& it : m_voting.m_dimensions_map)
+    if ((int)it.first < n_classes) {
+      d1[it.first] = it.second.first;
+      d2[it.first] = it.second.second;
+    }
+  check(pcdb_set_class_dimensions(m_ctx, d1.data(), d2.data(), n_classes));
   m_codebook_uploaded = true;
 }
 

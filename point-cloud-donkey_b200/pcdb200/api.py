@@ -23,7 +23,7 @@ SYMBOLS = [
     "pcdb_shot_describe", "pcdb_compute_normals", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
     "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
     "pcdb_get_stats", "pcdb_reset_stats", "pcdb_comm_unique_id", "pcdb_comm_init", "pcdb_comm_destroy", "pcdb_comm_info",
-    "pcdb_set_codebook_sharded", "pcdb_comm_shard_keypoints",
+    "pcdb_set_codebook_sharded", "pcdb_comm_shard_keypoints", "pcdb_set_class_dimensions",
 ]
 COMM_ID_BYTES = 128
 
@@ -89,6 +89,11 @@ class Context:
     def set_params(self, prm):
         self.prm = prm.copy()
         self._check(lib().pcdb_set_params(self.h, C.byref(self.prm)))
+
+    def set_class_dimensions(self, first_dim, second_dim):
+        """Voting::m_dimensions_map: per class (mean object radius, mean median bounding-box side)."""
+        a, b = f32(first_dim), f32(second_dim)
+        self._check(lib().pcdb_set_class_dimensions(self.h, ptr(a, F), ptr(b, F), len(a)))
 
     def set_stream(self, cuda_stream_ptr):
         self._check(lib().pcdb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

@@ -9,6 +9,8 @@ KERNEL_GAUSSIAN, KERNEL_UNIFORM = 0, 1
 SUPPRESS_AVERAGE, SUPPRESS_SUPPRESS = 0, 1
 MAXFILTER_NONE, MAXFILTER_SIMPLE, MAXFILTER_MERGE = 0, 1, 2
 KNN_AUTO, KNN_SCAN, KNN_GEMM = 0, 1, 2
+RADIUS_CONFIG, RADIUS_FIRST_DIM, RADIUS_SECOND_DIM = 0, 1, 2
+SOMAX_DEFAULT, SOMAX_BANDWIDTH, SOMAX_VOTING_SPACE, SOMAX_MODEL_RADIUS = 0, 1, 2, 3
 SHOT_DIM, CSHOT_DIM, MAX_K = 352, 1344, 16
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_STATE, E_UNSUPPORTED, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
@@ -44,6 +46,9 @@ class Params(C.Structure):
         ("normal_radius", C.c_float),
         ("consistent_normals_method", C.c_int32),
         ("max_filter_type", C.c_int32),
+        ("radius_type", C.c_int32),
+        ("radius_factor", C.c_float),
+        ("single_object_max_type", C.c_int32),
     ]
 
     @property
@@ -80,6 +85,9 @@ def default_params(**kw):
     p.normal_radius = 0.05
     p.consistent_normals_method = 2
     p.max_filter_type = MAXFILTER_NONE
+    p.radius_type = RADIUS_CONFIG
+    p.radius_factor = 1.0
+    p.single_object_max_type = SOMAX_DEFAULT
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)

@@ -610,6 +610,75 @@ def test_find_maxima_parity_blobs(api, orc, suppression, kernel):
     c.close()
 
 
+def _merge_scene(rng, b):
+    """Votes whose maxima need the cross-class filters: a wide class-0 object with two class-1 maxima and a class-2
+    maximum inside its search distance, plus far-away singles."""
+    parts = [_blob_votes([(0, 0, 0)], 150, 0.03, rng, cls=0, inst=b % 3),
+             _blob_votes([(0.22, 0.02, 0), (-0.2, 0.05, 0.02)], 60, 0.02, rng, cls=1, inst=4),
+             _blob_votes([(0.05, 0.25, 0)], 40, 0.02, rng, cls=2, inst=1),
+             _blob_votes([(3, 3, 3)], 50, 0.02, rng, cls=1, inst=5),
+             _blob_votes([(3.1, 3, 3)], 30 + 40 * (b % 2), 0.02, rng, cls=2, inst=2),
+             _blob_votes([(-4, 0, 1)], 25, 0.02, rng, cls=3, inst=0)]
+    v = np.concatenate(parts)
+    v["instance_id"][::7] = 9  # several instances inside one maximum
+    rng.shuffle(v)
+    return v
+
+
+@pytest.mark.parametrize("radius_type", [0, 1, 2])
+@pytest.mark.parametrize("flt", [0, 1, 2])
+def test_find_maxima_radius_types_and_cross_class_filters(api, orc, radius_type, flt):
+    """BinOrBandwidthType Config / FirstDim / SecondDim (per-class mean-shift bandwidth, maxima_handler.cpp:509-521) x
+    MaxFilterType None / Simple / Merge (maxima_handler.cpp:227-383 incl. mergeMaxima :386-443)."""
+    rng = np.random.default_rng(100 + 3 * radius_type + flt)
+    clouds = [_merge_scene(rng, b) for b in range(4)]
+    clouds.insert(1, clouds[0][:0])
+    votes = np.concatenate(clouds)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64)
+    prm = default_params(bandwidth=0.3, max_filter_type=flt, radius_type=radius_type, radius_factor=1.1,
+                         average_rotation=1, single_object_mode=0)
+    first, second = [0.45, 0.12, 0.2, 0.3], [0.35, 0.15, 0.1, 0.25]
+    cb = _dummy_codebook(np.zeros((4, 352), np.float32), n_classes=4)
+    c = api.Context(prm, cb)
+    c.set_class_dimensions(first, second)
+    m = orc.Model(prm, cb)
+    m.set_class_dimensions(first, second)
+    a, b = c.find_maxima(votes, off), m.find_maxima(votes, off)
+    _compare_maxima(a, b)
+    qa, qb = a[0]["bbox_quat"], b[0]["bbox_quat"]
+    assert np.allclose(np.abs((qa * qb).sum(1)), 1.0, atol=2e-3)
+    if flt == 2 and radius_type == 1:
+        # class 0 (search distance 0.495) subsumes the two class-1 maxima (0.132) and the class-2 one (0.22) around it:
+        # the two class-1 maxima are merged into one candidate, and the heaviest candidate of the group survives
+        n0 = [int(((a[0]["class_id"][a[1][i]:a[1][i + 1]]) == 1).sum()) for i in (0, 2, 3, 4)]
+        assert all(n <= 1 for n in n0)
+    c.close()
+
+
+@pytest.mark.parametrize("max_type", [1, 2, 3])
+def test_classify_single_object_max_types(api, orc, small_world, max_type):
+    """SingleObjectMode with SingleObjectMaxType BandwidthVotes / VotingSpaceVotes / ModelRadiusVotes
+    (voting_mean_shift.cpp:124-155): no mean shift, one maximum per voted class at the cloud's centroid."""
+    prm = small_world["prm"].copy()
+    prm.single_object_mode, prm.single_object_max_type = 1, max_type
+    cb = small_world["cb"]
+    xt, nt, rt, ot, _ = small_world["test"]
+    xt = xt.copy()
+    xt[5] = np.nan
+    c = api.Context(prm, cb)
+    m = orc.Model(prm, cb)
+    la, ma, oa = c.classify_batch(xt, nt, rt, ot)
+    lb, mb, ob = m.classify_batch(xt, nt, rt, ot)
+    assert np.array_equal(la, lb) and np.array_equal(oa, ob)
+    assert np.array_equal(ma["class_id"], mb["class_id"]) and np.array_equal(ma["n_votes"], mb["n_votes"])
+    assert np.allclose(ma["position"], mb["position"], atol=1e-5) and np.allclose(ma["weight"], mb["weight"], rtol=1e-4)
+    for b in range(len(ot) - 1):  # every maximum of a cloud sits at the cloud's centroid
+        assert np.allclose(ma["position"][oa[b]:oa[b + 1]], ma["position"][oa[b]], atol=0)
+    with pytest.raises(api.PcdbError):  # the stage-level entry has no cloud to take the centroid of
+        c.find_maxima(np.zeros(1, VOTE_DTYPE), [0, 1])
+    c.close()
+
+
 def test_find_maxima_thresholds_parity(api, orc):
     rng = np.random.default_rng(19)
     votes = np.concatenate([_blob_votes([(0, 0, 0)], 100, 0.02, rng, cls=0),

@@ -518,3 +518,74 @@ def test_pruned_exact_search_equals_the_linear_scan(orc, small_world):
     lab = orc.classify_batch_pruned(m, xt, nt, rt, ot)
     ref, _, _ = m.classify_batch(xt, nt, rt, ot, want_maxima=False)
     assert np.array_equal(lab, ref)
+
+
+def _votes(centres, n_per, cls, rng, sigma=0.01, inst=0):
+    from pcdb200.structs import VOTE_DTYPE
+    v = np.zeros(len(centres) * n_per, VOTE_DTYPE)
+    for i, c in enumerate(centres):
+        v["position"][i * n_per:(i + 1) * n_per] = (np.asarray(c) + rng.normal(scale=sigma, size=(n_per, 3))).astype(np.float32)
+    v["weight"] = 1.0
+    v["class_id"] = cls
+    v["instance_id"] = inst
+    v["bbox_quat"][:, 0] = 1.0
+    v["bbox_size"] = 1.0
+    return v
+
+
+def test_cross_class_merge_filter_known_answer(orc):
+    """MaxFilterType "Merge" (maxima_handler.cpp:296-383): a class with a large search distance subsumes the maxima of
+    classes with smaller ones around it; same-class maxima inside the group are merged by weighted averaging
+    (mergeMaxima :386-443) and only the heaviest candidate of the group survives."""
+    from pcdb200.structs import Codebook, default_params
+    rng = np.random.default_rng(3)
+    votes = np.concatenate([_votes([(0, 0, 0)], 50, 0, rng),                      # class 0: search distance 0.5
+                            _votes([(0.2, 0, 0), (-0.2, 0, 0)], 40, 1, rng),      # class 1: 0.1 -> two maxima, 80 votes
+                            _votes([(5, 5, 5)], 10, 1, rng)])                     # far away: untouched
+    off = np.array([0, len(votes)], np.int64)
+    W = np.zeros((2, 352), np.float32)
+    cb = Codebook(W, np.arange(3), np.zeros((2, 3)), np.ones(2), np.zeros(2), np.zeros(2), np.zeros((2, 7)), np.ones(2),
+                  np.zeros((2, 3)), np.arange(2), np.ones(2))
+    prm = default_params(bandwidth=0.3, radius_type=1, radius_factor=1.0, max_filter_type=2, single_object_mode=0,
+                         ms_kernel=1)
+    m = orc.Model(prm, cb)
+    m.set_class_dimensions([0.5, 0.1], [0.5, 0.1])
+    mx, moff, mi, mw = m.find_maxima(votes, off)
+    assert len(mx) == 2
+    # the merged class-1 candidate (80 votes) outweighs the class-0 maximum (50 votes) and sits between its two parts
+    assert mx["class_id"].tolist() == [1, 1] and mx["n_votes"].tolist() == [80, 10]
+    assert np.allclose(mx["position"][0], [0, 0, 0], atol=0.01) and np.allclose(mx["position"][1], [5, 5, 5], atol=0.01)
+    assert np.isclose(mx["weight"].sum(), 1.0)
+    assert sorted(mi[mx["vote_begin"][0]:mx["vote_begin"][0] + 80].tolist()) == list(range(50, 130))
+    # without the filter: three class-1 maxima and the class-0 one
+    prm.max_filter_type = 0
+    m.set_params(prm)
+    assert sorted(m.find_maxima(votes, off)[0]["n_votes"].tolist()) == [10, 40, 40, 50]
+    # "Simple" with a per-class radius type uses the search distance of the class processed before the last (here
+    # class 0's 0.5: MaximaHandler::m_radius as iFindMaxima left it): the class-0 maximum suppresses both neighbours
+    prm.max_filter_type = 1
+    m.set_params(prm)
+    mx = m.find_maxima(votes, off)[0]
+    assert sorted(zip(mx["class_id"].tolist(), mx["n_votes"].tolist())) == [(0, 50), (1, 10)]
+
+
+def test_single_object_max_types_known_answer(orc, small_world):
+    """SingleObjectMaxType VotingSpaceVotes collects every vote of a class at the centroid; ModelRadiusVotes those
+    within the farthest point's distance; BandwidthVotes those within Voting.Bandwidth."""
+    prm = small_world["prm"].copy()
+    cb = small_world["cb"]
+    xt, nt, rt, ot, _ = small_world["test"]
+    x, n, r, o = xt[ot[0]:ot[1]], nt[ot[0]:ot[1]], rt[ot[0]:ot[1]], np.array([0, ot[1] - ot[0]], np.int64)
+    counts = {}
+    for mt in (0, 1, 2, 3):
+        prm.single_object_mode, prm.single_object_max_type = 1, mt
+        m = orc.Model(prm, cb)
+        _, mx, moff = m.classify_batch(x, n, r, o)
+        counts[mt] = mx
+    centroid = x.astype(np.float32).sum(0, dtype=np.float32) / np.float32(len(x))
+    for mt in (1, 2, 3):
+        assert np.allclose(counts[mt]["position"], centroid, atol=1e-5)
+        assert len(set(counts[mt]["class_id"].tolist())) == len(counts[mt])  # one maximum per voted class
+    # (the farthest vote itself fails the strict d^2 < h^2 test of the radius search: VotingSpaceVotes misses it)
+    assert counts[3]["n_votes"].sum() >= counts[1]["n_votes"].sum() > 0
+    assert counts[2]["n_votes"].sum() >= counts[3]["n_votes"].sum() - len(counts[2])
