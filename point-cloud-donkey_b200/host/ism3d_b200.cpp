@@ -124,7 +124,20 @@ ImplicitShapeModel::ImplicitShapeModel(int device) {
   m_processing_times = {{"complete", 0}, {"features", 0}, {"keypoints", 0}, {"normals", 0},
                         {"flann", 0},    {"voting", 0},   {"maxima", 0}};  // implicit_shape_model.cpp:160
 }
-ImplicitShapeModel::~ImplicitShapeModel() { pcdb_destroy(m_ctx); }
+ImplicitShapeModel::ImplicitShapeModel(NoDevice) { pcdb_default_params(&m_params); }
+ImplicitShapeModel::~ImplicitShapeModel() {
+  if (m_ctx) pcdb_destroy(m_ctx);
+}
+
+pcdb_params ImplicitShapeModel::paramsOfConfigFile(const std::string& file, std::string* bounding_box_type) {
+  ImplicitShapeModel m{NoDevice{}};
+  m.setLogging(false);
+  jsonmin::Value cfg = jsonmin::parse_file(file);
+  if (!cfg.isObject() || !cfg.isMember("ObjectConfig")) throw RuntimeException("no ObjectConfig in " + file);
+  m.configFromJson(cfg["ObjectConfig"]);
+  if (bounding_box_type) *bounding_box_type = m.m_bb_type;
+  return m.m_params;
+}
 
 void ImplicitShapeModel::check(int rc) const {
   if (rc == PCDB_OK) return;
@@ -204,9 +217,10 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   if (!top.boolean("FLANNExactMatch", false))
     log("INFO", "FLANNExactMatch=false: this implementation always runs the exact search (the approximate kd-forest "
                 "is not reproducible; SURVEY.md section 0-4)");
+  // options outside the built hot path are collected and reported together
+  std::vector<std::string> outside;
   for (const char* k : {"UseSmoothing", "UseStatisticalOutlierRemoval", "UseRadiusOutlierRemoval", "UseVoxelFiltering", "UseSvmTraining"})
-    if (oc["Parameters"].isMember(k) && top.boolean(k, false))
-      throw BadParamException(std::string(k) + "=true is outside the built hot path");
+    if (oc["Parameters"].isMember(k) && top.boolean(k, false)) outside.push_back(std::string("Parameters.") + k + "=true");
 
   const jsonmin::Value& ch = oc["Children"];
   // Features
@@ -292,12 +306,19 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
     log("ERROR", "Invalid maxima filter type specified: " + ftr + "! No filtering is performed!");
     P.max_filter_type = PCDB_MAXFILTER_NONE;
   }
-  if (vr.boolean("UseGlobalFeatures", false)) throw BadParamException("UseGlobalFeatures=true is outside the built hot path");
+  if (vr.boolean("UseGlobalFeatures", false))
+    outside.push_back("Voting.UseGlobalFeatures=true (global-descriptor classifiers: GlobalFeatures child, SVM / KNN merge of "
+                      "global and local hypotheses, voting.cpp:217-300)");
   if (vo["Parameters"].isMember("RansacVoteFiltering") && vr.boolean("RansacVoteFiltering", false))
-    throw BadParamException("RansacVoteFiltering=true is outside the built hot path");
+    outside.push_back("Voting.RansacVoteFiltering=true (PCL's CorrespondenceRejectorSampleConsensus, voting.cpp:356-433)");
+  if (!outside.empty()) {
+    std::string msg = "this configuration asks for parts of the reference outside the built hot path; set them to false: ";
+    for (size_t i = 0; i < outside.size(); ++i) msg += (i ? "; " : "") + outside[i];
+    throw BadParamException(msg);
+  }
   for (const std::string& w : warn) log("WARN", w);
   m_params = P;
-  check(pcdb_set_params(m_ctx, &m_params));
+  if (m_ctx) check(pcdb_set_params(m_ctx, &m_params));
 }
 
 std::map<unsigned, float> ImplicitShapeModel::getDetectionThreshold() const {
@@ -560,8 +581,21 @@ void ImplicitShapeModel::train() {
   m_codebook_uploaded = false;
   if (m_training_objects_filenames.empty()) { log("WARN", "no training models found"); return; }
   if (m_bb_type != "AABB" && m_bb_type != "MVBB") throw BadParamException("invalid bounding box type: " + m_bb_type);
-  if (m_bb_type == "MVBB")
-    log("WARN", "BoundingBoxType MVBB (libgdiam) is outside the built path: axis-aligned boxes are used for training");
+  if (m_bb_type == "MVBB") {
+    // Utils::computeMVBB (utils/utils.cpp:242-293) is libgdiam's approximate minimum-volume box, a training-side
+    // dependency that is not built.  Decision: train with the axis-aligned box (the reference's other BoundingBoxType),
+    // say so, and record "AABB" in the model that is written, so that the saved .ism describes what its votes were
+    // computed from.  Labels are unaffected in practice (votes still point at a box centre); vote vectors and stored
+    // box sizes differ from an MVBB-trained model.
+    log("WARN", "BoundingBoxType MVBB (libgdiam approximate minimum-volume box) is not built: training uses AABB and the "
+                "written model records BoundingBoxType = AABB");
+    m_bb_type = "AABB";
+    if (m_config.isObject() && m_config.isMember("Parameters")) {
+      jsonmin::Value params = m_config["Parameters"];
+      params.set("BoundingBoxType", jsonmin::Value::of(std::string("AABB")));
+      m_config.set("Parameters", params);
+    }
+  }
   const int D = m_params.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   // per class (std::map order), per model: features through the GPU path
   std::vector<float> fxyz, flrf, fdesc;

@@ -90,6 +90,9 @@ class ImplicitShapeModel {
  public:
   explicit ImplicitShapeModel(int device = 0);
   ~ImplicitShapeModel();
+  // What readObject(file, training = true) makes of a configuration file, WITHOUT creating a device context (host-only:
+  // config checks and tests run where there is no GPU).  Throws what readObject throws for options outside the built path.
+  static pcdb_params paramsOfConfigFile(const std::string& file, std::string* bounding_box_type = nullptr);
   ImplicitShapeModel(const ImplicitShapeModel&) = delete;
 
   // JSONObject (utils/json_object.h:49-66)
@@ -126,6 +129,8 @@ class ImplicitShapeModel {
   pcdb_ctx* context() { return m_ctx; }
 
  private:
+  struct NoDevice {};
+  explicit ImplicitShapeModel(NoDevice);
   void configFromJson(const jsonmin::Value& objectConfig);
   void saveData(std::ostream& os) const;
   void loadData(std::istream& is);

@@ -155,3 +155,71 @@ def test_lzf_reader_against_the_references_own_encoder(tmp_path):
         mine = pcd.lzf_compress(raw[:20000])
         out = C.create_string_buffer(20000)
         assert lz.lzf_decompress(mine, len(mine), out, 20000) == 20000 and out.raw == raw[:20000]
+
+
+# ---- the reference's shipped configurations through the shim's own config reader (host-only: no device context) ------
+CONFIG_PARAMS = os.path.join(HOST, "config_params")
+
+
+def _params_of(path):
+    if not os.path.exists(CONFIG_PARAMS):
+        subprocess.check_call(["make", "-C", HOST, "-s", "config_params"])
+    r = subprocess.run([CONFIG_PARAMS, path], capture_output=True, text=True)
+    return r.returncode, r.stdout.strip(), r.stderr
+
+
+@pytest.mark.parametrize("name,restated", [("qs_input_config.ism", "QS_INPUT_CONFIG"),
+                                           ("default_config_kinect.ism", "DEFAULT_CONFIG_KINECT")])
+def test_shipped_configs_read_like_their_restatement(tmp_path, name, restated):
+    """ImplicitShapeModel::readObject on the reference's real file and on tests/ref_configs.py's restatement of it (what
+    the GPU tests use, where /root/reference does not exist) must yield the same parameters."""
+    import ref_configs
+    rc, mine, err = _params_of(ref_configs.write(getattr(ref_configs, restated), str(tmp_path / name)))
+    assert rc == 0, err
+    assert "distance_type=1" in mine and "single_object_mode=1" in mine  # chi^2, single-object mode: as shipped
+    real = os.path.join("/root/reference/config", name)
+    if not os.path.exists(real):
+        pytest.skip("reference not mounted")
+    rc, theirs, err = _params_of(real)
+    assert rc == 0, err
+    assert mine == theirs
+
+
+def test_default_ism_is_rejected_like_the_reference_rejects_it():
+    """config/default.ism has no FeatureWeighting child: the reference's own loader refuses it
+    (implicit_shape_model.cpp:1095-1103 "could not find necessary json entries") and so does the shim."""
+    real = "/root/reference/config/default.ism"
+    if not os.path.exists(real):
+        pytest.skip("reference not mounted")
+    rc, out, err = _params_of(real)
+    assert rc == 2 and "FeatureWeighting" in err
+
+
+def test_options_outside_the_path_are_named(tmp_path):
+    import copy
+    import ref_configs
+    cfg = copy.deepcopy(ref_configs.DEFAULT_CONFIG_KINECT)
+    cfg["ObjectConfig"]["Children"]["Voting"]["Parameters"]["UseGlobalFeatures"] = True
+    cfg["ObjectConfig"]["Parameters"]["UseSvmTraining"] = True
+    rc, out, err = _params_of(ref_configs.write(cfg, str(tmp_path / "g.ism")))
+    assert rc == 2 and "UseGlobalFeatures" in err and "UseSvmTraining" in err
+    cfg = copy.deepcopy(ref_configs.QS_INPUT_CONFIG)
+    v = cfg["ObjectConfig"]["Children"]["Voting"]["Parameters"]
+    v["BinOrBandwidthType"], v["BinOrBandwidthFactor"], v["MaxFilterType"], v["SingleObjectMaxType"] = \
+        "BoundingBoxMedian", 0.5, "Merge", "ModelRadiusVotes"
+    rc, out, err = _params_of(ref_configs.write(cfg, str(tmp_path / "h.ism")))
+    assert rc == 0, err
+    assert "radius_type=2 radius_factor=0.5 single_object_max_type=3" in out and "max_filter_type=2" in out
+
+
+def test_detection_metrics_known_answers(tmp_path):
+    """host/eval_detection.h (eval_tool_detection's metrics): greedy matching, per-class AP, dataset sweep, parsers."""
+    tool = os.path.join(HOST, "eval_detection_selftest")
+    if not os.path.exists(tool):
+        subprocess.check_call(["make", "-C", HOST, "-s", "eval_detection_selftest"])
+    ann = tmp_path / "scene1.txt"
+    ann.write_text("chair (0.25) 1.0 2.0 3.0\n\ntable (0.0) 0.5 0.5 3.5 1 1 1 1 0 0 0\nbook (0.1) 0 0 0\n")
+    lst = tmp_path / "list.txt"
+    lst.write_text("# test detection\nscene1.pcd scene1.txt\n#skipped.pcd skipped.txt\nscene2.pcd scene2.txt\n")
+    out = subprocess.check_output([tool, str(ann), str(lst)]).decode()
+    assert "selftest ok" in out
