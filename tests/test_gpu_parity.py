@@ -878,8 +878,15 @@ def test_scene_cross_class_filter_simple(api, orc):
     pos = mxa["position"].astype(np.float64)
     d = np.linalg.norm(pos[:, None] - pos[None], axis=2) + np.eye(len(pos)) * 1e9
     assert d.min() >= filt.bandwidth - 3e-3  # no two survivors closer than the radius
-    with pytest.raises(api.PcdbError):
-        api.Context(synth.workload_params("c2", single_object_mode=0, max_filter_type=2), cb).classify_batch(x, n, col, off)
+    # "Merge" on the same scene: same maxima as the oracle's mergeAndFilterMaxima
+    mrg = synth.workload_params("c2", single_object_mode=0, max_filter_type=2, min_votes_threshold=filt.min_votes_threshold)
+    cm = api.Context(mrg, cb)
+    lm, mxm, offm = cm.classify_batch(x, n, col, off)
+    lo, mxo, offo = orc.Model(mrg, cb).classify_batch(x, n, col, off)
+    assert np.array_equal(lm, lo) and np.array_equal(offm, offo)
+    assert np.array_equal(mxm["class_id"], mxo["class_id"]) and np.array_equal(mxm["n_votes"], mxo["n_votes"])
+    assert np.allclose(mxm["weight"], mxo["weight"], rtol=2e-3, atol=1e-6)
+    cm.close()
     c.close()
 
 
