@@ -225,7 +225,7 @@ __global__ void k_heads_u64(const unsigned long long* __restrict__ keys, long lo
 // surface fits the kernel's shared-memory stage (small objects: a cell holds 2-3 keypoints, a cloud a few hundred; one
 // staging then serves them all and every warp of the CTA has a keypoint in every round).
 __global__ void k_item_heads(const unsigned long long* __restrict__ keys, long long n,
-                             const long long* __restrict__ surf_off, int* head) {
+                             const long long* __restrict__ surf_off, int item_kp, int* head) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int h = 1;
@@ -238,10 +238,15 @@ __global__ void k_item_heads(const unsigned long long* __restrict__ keys, long l
     } else if ((a >> 48) != (b >> 48)) {
       h = 1;
     } else {
-      // a cloud's keypoints are cut into items of 64 (8 rounds of the 8 warps): fine enough to balance the persistent
-      // CTAs at the end of the launch, coarse enough to amortise the staging of the cloud
+      // a cloud's keypoints are cut into items of item_kp: the warps of a CTA fetch keypoints dynamically and meet at a
+      // barrier when the item is exhausted, so an item should hold many keypoints per warp (the wait for the last warp
+      // is one keypoint long: 64-keypoint items on 12 warps cost 11 % in barrier stalls) — unless the batch is so
+      // small that only finer items keep every SM busy (the host sizes item_kp from the keypoint count)
       const long long first = lower_bound_u64(keys, 0, n, (unsigned long long)cloud << 48);
-      h = ((i - first) % 64) == 0;
+      const long long last = lower_bound_u64(keys, first, n, (unsigned long long)(cloud + 1) << 48);
+      const long long n_items = (last - first + item_kp - 1) / item_kp;       // equal-sized items inside a cloud
+      const long long size = (last - first + n_items - 1) / n_items;
+      h = ((i - first) % size) == 0;
     }
   }
   head[i] = h;
@@ -474,7 +479,9 @@ int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color) {
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.kkeys.as<unsigned long long>(), w.kkeys2.as<unsigned long long>(),
                                    w.kvals.as<int>(), w.kvals2.as<int>(), Q, 48 + ceil_log2(B + 1)));
-  k_item_heads<<<cdiv(Q, 256), 256, 0, st>>>(w.kkeys2.as<unsigned long long>(), Q, w.surf_off.as<long long>(),
+  // whole-cloud items: about four items per resident CTA of the descriptor kernel, at least two keypoints per warp
+  const int item_kp = (int)std::max<int64_t>(24, std::min<int64_t>(4096, Q / (4 * 2 * (int64_t)ctx->sm_count)));
+  k_item_heads<<<cdiv(Q, 256), 256, 0, st>>>(w.kkeys2.as<unsigned long long>(), Q, w.surf_off.as<long long>(), item_kp,
                                              w.item_head.as<int>());
   PCDB_LAUNCH_CHECK();
   PCDB_CUDA(cudaMemsetAsync(w.item_head.as<int>() + Q, 0, sizeof(int), st));
