@@ -25,6 +25,29 @@ void pcdb_trace_point(pcdb_ctx* ctx, const char* name) {
   last = now;
 }
 
+int pcdb_read_small(pcdb_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+  if (bytes == 0) return PCDB_OK;
+  const size_t need = (bytes + 15) & ~(size_t)15;
+  if (!ctx->pinned || ctx->pinned_used + need > ctx->pinned_cap) {  // no room: plain (blocking) copy
+    PCDB_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PCDB_OK;
+  }
+  PCDB_CUDA(cudaMemcpyAsync(static_cast<char*>(ctx->pinned) + ctx->pinned_used, dev_src, bytes, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  ctx->pending_reads.push_back({host_dst, ctx->pinned_used, bytes});
+  ctx->pinned_used += need;
+  return PCDB_OK;
+}
+
+int pcdb_sync_reads(pcdb_ctx* ctx) {
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  for (const auto& r : ctx->pending_reads) std::memcpy(r.dst, static_cast<char*>(ctx->pinned) + r.off, r.bytes);
+  ctx->pending_reads.clear();
+  ctx->pinned_used = 0;
+  if (e != cudaSuccess) return ctx->fail(PCDB_E_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+  return PCDB_OK;
+}
+
 namespace {
 
 thread_local std::string g_create_err;
@@ -361,9 +384,9 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   PCDB_TRY(stage_compact(ctx, B, P, true, has_rgb));
   pcdb_trace_point(ctx, "features: compact");
   int totals[2] = {0, 0};
-  PCDB_TRY(download(ctx, &totals[0], w.pos_pt.as<int>() + P, sizeof(int)));
-  PCDB_TRY(download(ctx, &totals[1], w.pos_sf.as<int>() + P, sizeof(int)));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &totals[0], w.pos_pt.as<int>() + P, sizeof(int)));
+  PCDB_TRY(pcdb_read_small(ctx, &totals[1], w.pos_sf.as<int>() + P, sizeof(int)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   const int64_t n_pts = totals[0], n_surf = totals[1];
   ctx->stats.n_points += n_pts;
   PCDB_TRY(stage_cloud_setup(ctx, B, n_pts, nullptr, nullptr, 0, p.leaf_size,
@@ -371,8 +394,8 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   int64_t Q = 0;
   PCDB_TRY(stage_voxel_keypoints(ctx, B, n_pts, p.leaf_size, &Q));
   int err[4] = {0, 0, 0, 0};
-  PCDB_TRY(download(ctx, err, w.err_flag.p, sizeof(err)));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, err, w.err_flag.p, sizeof(err)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   pcdb_trace_point(ctx, "features: voxel keypoints");
   if (err[0] & 1)
     return ctx->fail(PCDB_E_INVALID, "Keypoints.LeafSize too small for the cloud extent (pcl::VoxelGrid index overflow)");
@@ -402,10 +425,10 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.feat_valid.as<int>(), w.feat_pos.as<int>(), Q + 1));
   int F = 0;
-  PCDB_TRY(download(ctx, &F, w.feat_pos.as<int>() + Q, sizeof(int)));
+  PCDB_TRY(pcdb_read_small(ctx, &F, w.feat_pos.as<int>() + Q, sizeof(int)));
   unsigned long long nb[2] = {0, 0};
-  PCDB_TRY(download(ctx, nb, w.scalars.as<char>() + 16, sizeof(nb)));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, nb, w.scalars.as<char>() + 16, sizeof(nb)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   ctx->stats.n_neighbours_lrf += (int64_t)nb[0];
   ctx->stats.n_neighbours_shot += (int64_t)nb[1];
   ctx->stats.n_features += F;
@@ -433,12 +456,12 @@ int fetch_maxima(pcdb_ctx* ctx, int B, int64_t M, pcdb_maximum* maxima_out, int6
                  int64_t maxima_capacity, int32_t* label_out) {
   Workspace& w = ctx->ws;
   std::vector<int> kept(B), first(B), labels(B);
-  PCDB_TRY(download(ctx, kept.data(), w.max_kept.p, sizeof(int) * B));
-  PCDB_TRY(download(ctx, first.data(), w.max_first.p, sizeof(int) * B));
-  PCDB_TRY(download(ctx, labels.data(), w.labels.p, sizeof(int) * B));
+  PCDB_TRY(pcdb_read_small(ctx, kept.data(), w.max_kept.p, sizeof(int) * B));
+  PCDB_TRY(pcdb_read_small(ctx, first.data(), w.max_first.p, sizeof(int) * B));
+  PCDB_TRY(pcdb_read_small(ctx, labels.data(), w.labels.p, sizeof(int) * B));
   std::vector<pcdb_maximum> all((size_t)std::max<int64_t>(M, 1));
-  if (maxima_out && M > 0) PCDB_TRY(download(ctx, all.data(), w.max_sorted.p, sizeof(pcdb_maximum) * M));
-  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (maxima_out && M > 0) PCDB_TRY(pcdb_read_small(ctx, all.data(), w.max_sorted.p, sizeof(pcdb_maximum) * M));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   int64_t total = 0;
   if (maxima_off_out) maxima_off_out[0] = 0;
   for (int b = 0; b < B; ++b) {
@@ -602,6 +625,7 @@ int pcdb_create(pcdb_ctx** out, int device) {
     return PCDB_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (cudaMallocHost(&ctx->pinned, 1 << 16) == cudaSuccess) ctx->pinned_cap = 1 << 16;  // else: plain copies
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   // CIELab look-up tables, built on the host with powf exactly as the reference does (features_cshot.cpp:52-71)
   std::vector<float> lut(256 + 4000);
@@ -633,6 +657,7 @@ void pcdb_destroy(pcdb_ctx* ctx) {
   pcdb_comm_destroy(ctx);
   if (ctx->gemm_state && ctx->gemm_state_free) ctx->gemm_state_free(ctx->gemm_state);
   if (ctx->lab_lut_d) cudaFree(ctx->lab_lut_d);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -97,7 +97,7 @@ struct Codebook_d {
   X(max_raw) X(max_sorted) X(max_kept) X(max_first) X(labels) X(nbr_cnt) \
   X(nbr_off) X(nbr_key) X(nbr_key2) X(merge_a) X(merge_b) X(nrm_pca) \
   X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len) X(feat_kp) X(vote_feat) \
-  X(ms_grp) X(ms_close) X(ms_src_dst) X(ms_cls_h) X(ms_cloud_cm) X(mem_idx2) X(mem_w2)
+  X(item_next) X(ms_grp) X(ms_close) X(ms_src_dst) X(ms_cls_h) X(ms_cloud_cm) X(mem_idx2) X(mem_w2)
 struct Workspace {
 #define X(n) DevBuf n;
   PCDB_WS_FIELDS(X)
@@ -134,8 +134,12 @@ struct pcdb_ctx {
   int64_t last_V = 0, last_M = 0, last_members = 0;
   int last_B = 0;
   std::vector<int64_t> h_off_a, h_off_b;
-  void* pinned = nullptr;  // small pinned staging area
-  size_t pinned_cap = 0;
+  // Small device->host reads (counts, flags) land in a pinned area and are handed to their destinations at the next
+  // pcdb_sync_reads: a pageable destination makes every cudaMemcpyAsync a blocking ~20 us round trip of its own.
+  void* pinned = nullptr;
+  size_t pinned_cap = 0, pinned_used = 0;
+  struct PendingRead { void* dst; size_t off, bytes; };
+  std::vector<PendingRead> pending_reads;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   int fail(int code, const char* fmt, ...) {
@@ -242,6 +246,10 @@ __device__ __forceinline__ long long lower_bound_u64(const unsigned long long* k
   return lo;
 }
 #endif
+
+// api.cu: enqueue a small device->host read / wait for the stream and deliver every pending read
+int pcdb_read_small(pcdb_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+int pcdb_sync_reads(pcdb_ctx* ctx);
 
 // ---- stage functions implemented across the .cu files (all asynchronous on ctx->stream unless noted) -----
 int pcdb_cub_exclusive_sum_i32(pcdb_ctx* ctx, const int* in, int* out, int64_t n);  // out has n+1 entries (total last)

@@ -926,7 +926,22 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   // (the streaming-query variant for D = 1344 re-reads its query tile with every codebook tile and sits on the L2->SM
   // limit either way; it keeps the query-major sweep, whose L2 hit rate measured 99 %)
   int S = a_res ? (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20) : 1;
-  if (g.n_mpairs < max_pairs) S = std::max(S, max_pairs / g.n_mpairs);
+  if (g.n_mpairs < max_pairs) {
+    // Few queries (one cloud): every (slice, query pair) unit runs at the same time, the kernel takes as long as the
+    // CTA pair with the most tiles.  Units are dealt round-robin, so pick the slice count that minimises
+    // rounds x tiles per slice — 2 query pairs on 74 CTA pairs want 37 slices (one round), not 38 (two).
+    const int pairs = gs->max_clusters[a_res ? 1 : 0] > 0 ? gs->max_clusters[a_res ? 1 : 0] : max_pairs;
+    long long best = -1;
+    int best_s = S;
+    for (int s = 1; s <= std::min(g.n_ntiles, 4 * pairs); ++s) {
+      const long long cost = (long long)cdiv((int64_t)g.n_mpairs * s, pairs) * (long long)cdiv(g.n_ntiles, s);
+      if (best < 0 || cost < best) {
+        best = cost;
+        best_s = s;
+      }
+    }
+    S = best_s;
+  }
   S = std::max(1, std::min(S, g.n_ntiles));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
@@ -1008,8 +1023,8 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
         PCDB_TRY((launch_gemm<true, 1, true>(ctx, map_a, op.map_b, g2, grid)));
       else
         PCDB_TRY((launch_gemm<false, 1, true>(ctx, map_a, op.map_b, g2, grid)));
-      PCDB_CUDA(cudaMemcpyAsync(&total, pool_count, 8, cudaMemcpyDeviceToHost, st));
-      PCDB_CUDA(cudaStreamSynchronize(st));
+      PCDB_TRY(pcdb_read_small(ctx, &total, pool_count, 8));
+      PCDB_TRY(pcdb_sync_reads(ctx));
       if ((int64_t)total <= gs->pool_cap) break;
       if (attempt >= 2 || total > 0x7fff0000ull)
         return ctx->fail(PCDB_E_CAPACITY, "chi^2 candidate pool: %llu entries for %lld queries", total, (long long)Q);
@@ -1027,9 +1042,9 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   // overflow fallback: exact scan of the affected queries (still on the GPU)
   int n_fb = 0;
   unsigned long long n_eval = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&n_fb, gs->fb_pos.as<int>() + Q, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaMemcpyAsync(&n_eval, w.scalars.as<char>() + 64, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &n_fb, gs->fb_pos.as<int>() + Q, sizeof(int)));
+  PCDB_TRY(pcdb_read_small(ctx, &n_eval, w.scalars.as<char>() + 64, sizeof(n_eval)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   if (!chi) ctx->stats.knn_candidates += (int64_t)n_eval;
   ctx->stats.knn_fallback_queries += n_fb;
   if (n_fb > 0) {

@@ -1075,12 +1075,12 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, bool have_cloud, int64_t*
   // mem_cnt has M+1 valid entries; scan over V+1 upper bound needs zeros beyond: cleared by the count kernel only up
   // to M, so read M first.
   int hM = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&hM, M_ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &hM, M_ptr, sizeof(int)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.mem_cnt.as<int>(), w.mem_off.as<int>(), (int64_t)hM + 1));
   int hMem = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&hMem, w.mem_off.as<int>() + hM, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &hMem, w.mem_off.as<int>() + hM, sizeof(int)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   PCDB_CUDA(w.mem_idx.ensure(sizeof(long long) * ((size_t)hMem + 1)));
   PCDB_CUDA(w.mem_w.ensure(sizeof(float) * ((size_t)hMem + 1)));
   k_ms_reweight<<<gseg, 32, 0, st>>>(nseg_ptr, w.max_n.as<int>(), w.max_off.as<int>(), w.seg2_start.as<int>(),

@@ -431,8 +431,8 @@ int stage_voxel_keypoints(pcdb_ctx* ctx, int B, int64_t n_pts, float leaf, int64
                                                          B, 32, w.kp_off.as<long long>());
   PCDB_LAUNCH_CHECK();
   int Q = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&Q, w.seg_id.as<int>() + n_pts, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &Q, w.seg_id.as<int>() + n_pts, sizeof(int)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   if (Q > 0) {
     k_centroids<<<cdiv(Q, 128), 128, 0, st>>>(w.pts4.as<float4>(), w.vvals2.as<int>(), w.seg_start.as<int>(), Q,
                                                w.pts_cloud.as<int>(), w.kp4.as<float4>(), w.kp_cloud.as<int>());
@@ -479,8 +479,9 @@ int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color) {
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_sort_pairs_u64(ctx, w.kkeys.as<unsigned long long>(), w.kkeys2.as<unsigned long long>(),
                                    w.kvals.as<int>(), w.kvals2.as<int>(), Q, 48 + ceil_log2(B + 1)));
-  // whole-cloud items: about four items per resident CTA of the descriptor kernel, at least two keypoints per warp
-  const int item_kp = (int)std::max<int64_t>(24, std::min<int64_t>(4096, Q / (4 * 2 * (int64_t)ctx->sm_count)));
+  // whole-cloud items are not cut any more: CTAs that run out of items help with the ones still in progress (k_shot
+  // draws keypoints from a global per-item counter), so one staging serves a whole cloud and the launch has no item tail
+  const int item_kp = 1 << 30;
   k_item_heads<<<cdiv(Q, 256), 256, 0, st>>>(w.kkeys2.as<unsigned long long>(), Q, w.surf_off.as<long long>(), item_kp,
                                              w.item_head.as<int>());
   PCDB_LAUNCH_CHECK();

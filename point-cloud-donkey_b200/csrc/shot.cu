@@ -16,6 +16,7 @@
 // accumulated in 32-bit fixed point in shared memory (native integer atomics => bit-reproducible across runs).
 // Geometry follows the reference's float/double choices; membership d^2 < r^2 is bit-exact.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "stages.h"
@@ -23,9 +24,11 @@
 namespace {
 
 // Warps per CTA: all of them share ONE staged neighbourhood, so more warps per CTA = more resident warps per byte of
-// shared memory.  SHOT: 12 warps, 2 CTAs per SM (24 resident warps; round 1 ran 8 x 2 = 16 and was latency-bound:
-// warps_active 25 %, stall_wait 2.4 per issue).  CSHOT (3 staged float4 per point, 5.4 KB histograms): 16 warps, 1 CTA.
-constexpr int kWarpsShot = 12, kWarpsCshot = 16, kWarpsMax = 16;
+// shared memory.  SHOT: 16 warps, 2 CTAs per SM = 32 resident warps at 64 registers (round 1 ran 8 x 2 = 16 and was
+// latency-bound: warps_active 25 %, stall_wait 2.4 per issue; 12 x 2 measured 36 %).  The stage is 28 B per point (the
+// normal as three float arrays, the point's index in the unused w of its position) so that two such CTAs fit the SM.
+// CSHOT (44 B per staged point, 5.4 KB histograms): 16 warps, 1 CTA.
+constexpr int kWarpsShot = 16, kWarpsCshot = 16, kWarpsMax = 16;
 constexpr int kChunk = PCDB_SHOT_CHUNK;     // staged points per work item
 // Per-warp list of in-radius staged points, filled kList entries at a time: a neighbourhood larger than one fill is
 // processed in several fills (the passes only accumulate), so the list costs 2 KB per warp instead of 2 bytes per
@@ -66,6 +69,8 @@ struct ShotArgs {
   const int* item_id;    // exclusive scan of the item heads over the sorted keypoints
   const int* item_head;
   int* work_counter_dense;
+  int* item_next;    // staged launch: keypoints drawn so far from every item (global, so that helper CTAs share an item)
+  int blocked;       // pass C: lane-blocked (1) or lane-strided (0) walk of the in-radius list
   unsigned* glist;   // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of in-radius points
   long long gcap;    // entries per warp (>= the largest 27-cell population of the batch)
 };
@@ -169,51 +174,118 @@ __device__ __forceinline__ void hist_add(unsigned* hist, int bin, float v, float
   atomicAdd(hist + bin, __float2uint_rn(__fmul_rn(v, scale)));
 }
 
-struct StageView {
-  const float4* pts;
-  const float4* nrm;
-  const float4* lab;
-  int cnt;
-};
+// ---- fast fp32 helpers for the CONTINUOUS interpolation weights (never for a discrete decision) -------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// acos on [-1, 1]: sqrt(1 - |x|) * P7(|x|) (Abramowitz & Stegun 4.4.46), |error| <= 5e-7 rad in fp32
+__device__ __forceinline__ float acos_fast(float x) {
+  const float ax = fabsf(x);
+  float p = -0.0012624911f;
+  p = fmaf(p, ax, 0.0066700901f);
+  p = fmaf(p, ax, -0.0170881256f);
+  p = fmaf(p, ax, 0.0308918810f);
+  p = fmaf(p, ax, -0.0501743046f);
+  p = fmaf(p, ax, 0.0889789874f);
+  p = fmaf(p, ax, -0.2145988016f);
+  p = fmaf(p, ax, 1.5707963050f);
+  const float r = sqrt_approx(1.0f - ax) * p;
+  return x < 0.f ? 3.14159265358979f - r : r;
+}
+// atan2 for (y, x) != (0, 0): odd minimax polynomial of degree 15 on the reduced argument, |error| <= 3e-7 rad in fp32
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float t = mn * rcp_approx(mx);
+  const float s = t * t;
+  float p = -0.004054560326039791f;
+  p = fmaf(p, s, 0.021862933412194252f);
+  p = fmaf(p, s, -0.05591229349374771f);
+  p = fmaf(p, s, 0.09642194956541061f);
+  p = fmaf(p, s, -0.1390862911939621f);
+  p = fmaf(p, s, 0.19946566224098206f);
+  p = fmaf(p, s, -0.33329859375953674f);
+  p = fmaf(p, s, 0.9999993443489075f);
+  float r = p * t;
+  if (ay > ax) r = 1.57079632679490f - r;
+  if (x < 0.f) r = 3.14159265358979f - r;
+  return copysignf(r, y);
+}
 
-template <bool COLOR>
+// Work distribution of the staged launch.  Pass 0 hands every item (a whole small cloud, or one search-grid cell of a
+// large one) to one CTA.  A CTA that finds no pass-0 item left becomes a HELPER: it walks the last items in reverse
+// order (those are the ones still being worked on), stages the same neighbourhood and draws keypoints from the item's
+// global counter.  The launch therefore ends about one keypoint after the last keypoint was drawn, instead of one
+// item after the last item was drawn (round 2 measured sm__issue_active min/max over the SMs = 51 / 68 %: the item tail).
+template <bool COLOR, bool DENSE>
 __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR ? 1 : 2) k_shot(ShotArgs a) {
   constexpr int D = COLOR ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   constexpr int kWarps = COLOR ? kWarpsCshot : kWarpsShot;
   constexpr int kThreads = kWarps * 32;
+  constexpr int kStage = DENSE ? 0 : kChunk;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // staged neighbourhood: float4 (x, y, z, surface index bits), the normal as three float arrays, float4 Lab (CSHOT)
   float4* s_pts = reinterpret_cast<float4*>(smem_raw);
-  float4* s_nrm = s_pts + a.stage_cap;
-  float4* s_lab = s_nrm + a.stage_cap;  // only touched when COLOR
-  unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + sizeof(float4) * a.stage_cap * (COLOR ? 3 : 2));
-  // per-warp compacted list of the staged points inside the current search radius (positions in the chunk)
+  float* s_nx = reinterpret_cast<float*>(s_pts + kStage);
+  float* s_ny = s_nx + kStage;
+  float* s_nz = s_ny + kStage;
+  float4* s_lab = reinterpret_cast<float4*>(s_nz + kStage);  // only touched when COLOR
+  unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + (size_t)kStage * (COLOR ? 44 : 28));
+  // per-warp compacted list of the staged points inside the current search radius (positions in the stage)
   unsigned short* s_list = reinterpret_cast<unsigned short*>(s_hist + (size_t)kWarps * D);
-  __shared__ long long s_rbeg_all[kWarps][9];  // staged launch: row 0 is the CTA's item; dense launch: one row per warp
-  __shared__ int s_rlen_all[kWarps][9];
+  __shared__ long long s_rbeg_all[DENSE ? kWarps : 1][9];  // dense launch: one row per warp
+  __shared__ int s_rlen_all[DENSE ? kWarps : 1][9];
   __shared__ int s_pref[10];
   __shared__ int s_item;
-  __shared__ int s_next;  // staged launch: next keypoint of the item (the warps fetch keypoints dynamically)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = *a.n_items_ptr;
   unsigned* hist = s_hist + (size_t)warp * D;
-  unsigned short* list = s_list + (size_t)warp * (a.stage_cap ? kList : 0);
-  const bool dense_launch = a.dense != 0;
-  long long* s_rbeg = s_rbeg_all[dense_launch ? warp : 0];
-  int* s_rlen = s_rlen_all[dense_launch ? warp : 0];
-  unsigned* glist = a.glist ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
+  unsigned short* list = s_list + (size_t)warp * (DENSE ? 0 : kList);
+  long long* s_rbeg = s_rbeg_all[DENSE ? warp : 0];
+  int* s_rlen = s_rlen_all[DENSE ? warp : 0];
+  unsigned* glist = DENSE ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
+  // helper passes over the last n_tail items (see above); few items (a single cloud) => many CTAs share each of them
+  const int n_tail = min(n_items, (int)gridDim.x);
+  const int n_pass = DENSE ? 0 : (n_items >= (int)gridDim.x ? 4 : min(64, max(4, 2 * (int)gridDim.x / max(1, n_items))));
+  const long long n_units = (long long)n_items + (long long)(n_pass - 1) * n_tail;
 
   while (true) {
-    int k0, k1, T;
-    if (!dense_launch) {
+    int k0, k1, T, item = 0;
+    if (!DENSE) {
       __syncthreads();
-      if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1);
+      if (threadIdx.x == 0) {
+        const long long u = (long long)atomicAdd(a.work_counter, 1);
+        int it = -1;
+        if (u < n_units) {
+          if (u < n_items) {
+            it = (int)u;
+          } else {  // helper unit: skip an item whose keypoints have all been drawn
+            it = n_items - 1 - (int)((u - n_items) % n_tail);
+            const int drawn = *reinterpret_cast<volatile int*>(a.item_next + it);
+            if (a.item_start[it] + drawn >= a.item_start[it + 1]) it = -2;
+          }
+        }
+        s_item = it;
+      }
       __syncthreads();
-      const int item = s_item;
-      if (item >= n_items) break;
+      item = s_item;
+      if (item == -1) break;
+      if (item == -2) continue;
       k0 = a.item_start[item];
       k1 = a.item_start[item + 1];
-      if (threadIdx.x == 0) s_next = k0;
       if (threadIdx.x < 9) {
         s_rbeg[threadIdx.x] = a.item_beg[(size_t)item * 9 + threadIdx.x];
         s_rlen[threadIdx.x] = a.item_len[(size_t)item * 9 + threadIdx.x];
@@ -229,18 +301,31 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
       }
       __syncthreads();
       T = s_pref[9];
-      if (T > kChunk && a.glist) continue;  // dense neighbourhood: left to the dense launch (block-uniform)
+      if (T > kChunk) continue;  // dense neighbourhood: left to the dense launch (block-uniform)
+      for (int e = threadIdx.x; e < T; e += kThreads) {
+        int r = 0;
+        while (e >= s_pref[r + 1]) ++r;
+        const long long src = s_rbeg[r] + (e - s_pref[r]);
+        const float4 p = a.surfS[src], nq = a.snrmS[src];
+        s_pts[e] = make_float4(p.x, p.y, p.z, nq.w);
+        s_nx[e] = nq.x;
+        s_ny[e] = nq.y;
+        s_nz[e] = nq.z;
+        if (COLOR) s_lab[e] = a.slabS[src];
+      }
+      __syncthreads();
     } else {
       // Dense launch: nothing is shared between the warps of a CTA, so every warp walks the sorted keypoints on its own
-      // (a cell of a dense cloud holds 2-3 keypoints: tying 8 warps to it left most of them waiting at a barrier)
+      // (a cell of a dense cloud holds 2-3 keypoints: tying the warps of a CTA to it left most of them waiting at a barrier)
       int p = 0;
       if (lane == 0) p = atomicAdd(a.work_counter_dense, 1);
       p = __shfl_sync(0xffffffffu, p, 0);
       if (p >= a.n_kp) break;
-      const int item = a.item_id[p] + a.item_head[p] - 1;
+      const int it = a.item_id[p] + a.item_head[p] - 1;
+      __syncwarp();
       if (lane < 9) {
-        s_rbeg[lane] = a.item_beg[(size_t)item * 9 + lane];
-        s_rlen[lane] = a.item_len[(size_t)item * 9 + lane];
+        s_rbeg[lane] = a.item_beg[(size_t)it * 9 + lane];
+        s_rlen[lane] = a.item_len[(size_t)it * 9 + lane];
       }
       __syncwarp();
       T = 0;
@@ -251,61 +336,38 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
     }
     const float fix_scale = exp2f(floorf(log2f(4294967296.0f / (4.0f * (float)T + 4.0f))));
     const float fix_inv = 1.0f / fix_scale;
-    const bool multi = T > kChunk;  // dense neighbourhood: no staging, per-warp global lists (see below)
-
-    auto stage = [&](int chunk) {
-      const int base = chunk * kChunk;
-      const int cnt = min(kChunk, T - base);
-      for (int e = threadIdx.x; e < cnt; e += kThreads) {
-        int g = base + e;
-        int r = 0;
-        while (g >= s_pref[r + 1]) ++r;
-        long long src = s_rbeg[r] + (g - s_pref[r]);
-        s_pts[e] = a.surfS[src];
-        s_nrm[e] = a.snrmS[src];
-        if (COLOR) s_lab[e] = a.slabS[src];
-      }
-    };
-    if (!dense_launch) {
-      if (!multi && T > 0) stage(0);
-      __syncthreads();
-    }
     const float r2_max = fmaxf(a.do_lrf ? a.r2_lrf : 0.f, a.do_desc ? a.r2_shot : 0.f);
 
-    // Staged launch: every warp takes the next unprocessed keypoint of the item when it is free (a static round-robin
-    // left warps waiting at the item's closing barrier for the one that drew the large neighbourhoods: 1.25 barrier
-    // stalls per issue in the round-1 profile).  Dense launch: the warp's single keypoint.
+    // Staged launch: every warp draws the next keypoint of the item when it is free (the counter is global so that
+    // helper CTAs draw from the same item).  Dense launch: the warp's single keypoint.
     bool first = true;
     while (true) {
       int kq = k0;
-      if (!dense_launch) {
-        if (lane == 0) kq = atomicAdd(&s_next, 1);
+      if (!DENSE) {
+        if (lane == 0) kq = k0 + atomicAdd(a.item_next + item, 1);
         kq = __shfl_sync(0xffffffffu, kq, 0);
       } else if (!first) {
         break;
       }
       first = false;
       if (kq >= k1) break;
-      const bool have = true;
       const int kidx = a.kp_order[kq];
-      float kx = 0.f, ky = 0.f, kz = 0.f;
-      unsigned krgb = 0;
+      float kx, ky, kz;
+      unsigned krgb;
       {
-        float4 k4 = a.kp4[kidx];
+        const float4 k4 = a.kp4[kidx];
         kx = k4.x; ky = k4.y; kz = k4.z;
         krgb = __float_as_uint(k4.w);
       }
-      // Radius filter first, heavy math second: the in-radius points of the chunk are compacted into this warp's list
-      // (ballot + popc, order = staging order), so the fp64 passes below run with all 32 lanes busy instead of
-      // diverging on the 30-50 % of the 27-cell neighbourhood that lies inside the sphere.  One fill holds at most
-      // kList entries: `from` is where the scan of the staged points resumes, the return value the number of entries.
+      // Radius filter first, heavy math second: the in-radius points of the stage are compacted into this warp's list
+      // (ballot + popc, order = staging order), so the passes below run with all 32 lanes busy instead of diverging on
+      // the 30-50 % of the staged neighbourhood that lies inside the sphere.  One fill holds at most kList entries:
+      // `from` is where the scan of the staged points resumes, the return value the number of entries.
       auto fill = [&](int& from, int cnt, float r2) -> int {
         int n = 0;
         int e0 = from;
         __syncwarp();  // every lane is done reading the previous fill
-        // 64 staged points per iteration (two independent loads / distance chains per lane): the compaction is a fifth
-        // of the kernel's instructions, and half of those were loop overhead and latency waits at 32 per iteration
-        for (; e0 < cnt && n <= kList - 64; e0 += 64) {
+        for (; e0 < cnt && n <= kList - 64; e0 += 64) {  // two independent loads / distance chains per lane
           const int ea = e0 + lane, eb = ea + 32;
           bool ina = false, inb = false;
           if (ea < cnt) {
@@ -331,7 +393,7 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
       // the points inside the larger of the two radii; the passes below then touch only those (typically < 10 % of the
       // 27-cell population) and apply their own radius inline.  No block-wide barrier in this mode.
       int n_g = 0;
-      if (multi && have) {
+      if (DENSE) {
         for (int r = 0; r < 9; ++r) {
           const long long rb = s_rbeg[r];
           const int rl = s_rlen[r];
@@ -349,28 +411,32 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
         }
         __syncwarp();
       }
-      auto pt_at = [&](int i) -> float4 { return multi ? a.surfS[glist[i]] : s_pts[list[i]]; };
-      auto nrm_at = [&](int i) -> float4 { return multi ? a.snrmS[glist[i]] : s_nrm[list[i]]; };
+      auto pt_at = [&](int i) -> float4 {  // .w: rgb bits (dense) / surface index bits (staged) — neither is used as xyz
+        if constexpr (DENSE) return a.surfS[glist[i]]; else return s_pts[list[i]];
+      };
+      auto idx_at = [&](int i) -> int {  // index of the point inside its cloud (tie-break key of the sorted kd-tree result)
+        if constexpr (DENSE) return __float_as_int(a.snrmS[glist[i]].w); else return __float_as_int(s_pts[list[i]].w);
+      };
       float rf[9];
-      bool lrf_ok = have;
+      bool lrf_ok = true;
       // ---------------------------------------------------------------- LRF
       if (a.do_lrf) {
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, sw = 0;
         int valid = 0, nall = 0, n_lrf = 0;
         int from = 0, done = 0;
         do {
-          n_lrf = multi ? n_g : fill(from, T, a.r2_lrf);
+          n_lrf = DENSE ? n_g : fill(from, T, a.r2_lrf);
           // lane <-> entry assignment of ONE long list, whatever the number of fills (keeps the fp64 sums' order)
-          const int start = multi ? lane : ((lane + 32 - (done & 31)) & 31);
+          const int start = DENSE ? lane : ((lane + 32 - (done & 31)) & 31);
           for (int i = start; i < n_lrf; i += 32) {
-            float4 p = pt_at(i);
-            float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-            if (!multi || d2 < a.r2_lrf) {
+            const float4 p = pt_at(i);
+            const float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+            if (!DENSE || d2 < a.r2_lrf) {
               ++nall;
               if (!(p.x == kx && p.y == ky && p.z == kz)) {
-                double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
-                       vz = (double)__fsub_rn(p.z, kz);
-                double wgt = a.r_lrf - sqrt((double)d2);
+                const double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                             vz = (double)__fsub_rn(p.z, kz);
+                const double wgt = a.r_lrf - sqrt((double)d2);
                 c00 += wgt * (vx * vx);
                 c01 += wgt * (vx * vy);
                 c02 += wgt * (vx * vz);
@@ -383,16 +449,16 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
             }
           }
           done += n_lrf;
-        } while (!multi && from < T);
-        const bool whole = multi || done == n_lrf;  // the list still holds the complete LRF neighbourhood
+        } while (!DENSE && from < T);
+        const bool whole = DENSE || done == n_lrf;  // the list still holds the complete LRF neighbourhood
         c00 = warp_sum(c00); c01 = warp_sum(c01); c02 = warp_sum(c02);
         c11 = warp_sum(c11); c12 = warp_sum(c12); c22 = warp_sum(c22);
         sw = warp_sum(sw);
         valid = warp_sum(valid);
         nall = warp_sum(nall);
-        if (have && lane == 0 && a.nbr_counts) atomicAdd(&a.nbr_counts[0], (unsigned long long)nall);
+        if (lane == 0 && a.nbr_counts) atomicAdd(&a.nbr_counts[0], (unsigned long long)nall);
         double x[3] = {0, 0, 0}, z[3] = {0, 0, 0};
-        lrf_ok = have && valid >= 5;
+        lrf_ok = valid >= 5;
         if (lrf_ok) {
           double cov[6] = {c00 / sw, c01 / sw, c02 / sw, c11 / sw, c12 / sw, c22 / sw};
           double ev[3], V[3][3];
@@ -408,11 +474,11 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
           do {
             const int nb = whole ? n_lrf : fill(fromB, T, a.r2_lrf);  // the list of pass A when it is complete
             for (int i = lane; i < nb; i += 32) {
-              float4 p = pt_at(i);
-              if (multi && !(sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < a.r2_lrf)) continue;
+              const float4 p = pt_at(i);
+              if (DENSE && !(sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < a.r2_lrf)) continue;
               if (!(p.x == kx && p.y == ky && p.z == kz)) {
-                double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
-                       vz = (double)__fsub_rn(p.z, kz);
+                const double vx = (double)__fsub_rn(p.x, kx), vy = (double)__fsub_rn(p.y, ky),
+                             vz = (double)__fsub_rn(p.z, kz);
                 if (vx * x[0] + vy * x[1] + vz * x[2] >= 0) ++plusX;
                 if (vx * z[0] + vy * z[1] + vz * z[2] >= 0) ++plusZ;
               }
@@ -429,9 +495,9 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
             // key (d^2 bits << 32 | index): 63 counting passes over the staged points + 5 successive-minimum passes.
             auto scan = [&](auto&& f) {  // key_of applies the LRF radius itself
               if (whole) {           // the list of pass A
-                for (int i = lane; i < n_lrf; i += 32) f(pt_at(i), __float_as_int(nrm_at(i).w));
+                for (int i = lane; i < n_lrf; i += 32) f(pt_at(i), idx_at(i));
               } else {               // a neighbourhood of several fills: walk the staged points
-                for (int e = lane; e < T; e += 32) f(s_pts[e], __float_as_int(s_nrm[e].w));
+                for (int e = lane; e < T; e += 32) f(s_pts[e], __float_as_int(s_pts[e].w));
               }
             };
             const unsigned long long kInvalid = ~0ull;
@@ -486,20 +552,20 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
 #pragma unroll
           for (int i = 0; i < 9; ++i) rf[i] = __int_as_float(0x7fc00000);
         }
-        if (have && a.lrf_out && lane < 9) {
+        if (a.lrf_out && lane < 9) {
           float v = rf[0];
 #pragma unroll
           for (int i = 1; i < 9; ++i)
             if (lane == i) v = rf[i];
           a.lrf_out[(size_t)kidx * 9 + lane] = v;
         }
-      } else if (have) {
+      } else {
 #pragma unroll
         for (int i = 0; i < 9; ++i) rf[i] = a.lrf_in[(size_t)kidx * 9 + i];
       }
       if (!a.do_desc) continue;  // next keypoint
       // Features::operator() drops keypoints whose frame is not finite (features.cpp:64-76)
-      const bool frame_ok = have && isfinite(rf[0]) && isfinite(rf[3]) && isfinite(rf[6]);
+      const bool frame_ok = isfinite(rf[0]) && isfinite(rf[3]) && isfinite(rf[6]);
       // ---------------------------------------------------------------- SHOT / CSHOT
       for (int j = lane; j < D; j += 32) hist[j] = 0;
       __syncwarp();
@@ -509,10 +575,12 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
         LRef = l.x; aRef = l.y; bRef = l.z;
       }
       // Discrete decisions (volume index, histogram bin, which neighbour bin) are taken exactly as the reference takes
-      // them: on float-exact quantities, on fp64 bdS/bdC, and on the radial shells through float thresholds on d^2
-      // that are equivalent to the reference's fp64 "sqrt(d^2) > r/2" tests (computed on the host, stage_shot).  The
-      // CONTINUOUS interpolation weights (radial, inclination, azimuth) are evaluated in fp32: their error (~1e-7) is
-      // far inside the 1e-4 descriptor bar and saves the software fp64 sqrt / acos / atan2 that dominated this loop.
+      // them: on float-exact quantities, on the fp64 bin position (through an fp32 evaluation that falls back to the
+      // fp64 one whenever it lands within 1e-4 of a rounding boundary: the two differ by < 5e-6), and on the radial
+      // shells through float thresholds on d^2 that are equivalent to the reference's fp64 "sqrt(d^2) > r/2" tests
+      // (computed on the host, stage_shot).  The CONTINUOUS interpolation weights (cosine / colour bin fraction, radial,
+      // inclination, azimuth) are evaluated in fp32 with hardware approximations and short polynomials: their error
+      // (< 1e-6) is far inside the 1e-4 descriptor bar and removes the software fp64 / libm code that dominated this loop.
       const float r34f = (float)((a.r_shot * 3) / 4), r14f = (float)(a.r_shot / 4);
       const float inv_r12f = (float)(1.0 / (a.r_shot / 2));
       const float inv_90f = (float)(1.0 / PST_RAD_90), inv_45f = (float)(1.0 / PST_RAD_45);
@@ -520,20 +588,52 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
       if (frame_ok) {  // warp-uniform
         int fromC = 0;
         do {
-        const int n_in = multi ? n_g : fill(fromC, T, a.r2_shot);
-        for (int i = lane; i < n_in; i += 32) {
-          float4 p = pt_at(i);
-          float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
-          if (multi && !(d2 < a.r2_shot)) continue;
+        const int n_in = DENSE ? n_g : fill(fromC, T, a.r2_shot);
+        // lane L takes the contiguous entries [L m, (L + 1) m): the list is in staging (= cell) order, so the 32 points
+        // a warp accumulates at the same time are far apart and rarely hit the same histogram bin (same-address shared
+        // atomics serialise); m is odd, which keeps the 16-bit list reads of the 32 lanes on different banks
+        const int m_blk = a.blocked ? (((n_in + 31) >> 5) | 1) : ((n_in + 31) >> 5);
+        const int i_base = a.blocked ? lane * m_blk : lane, i_step = a.blocked ? 1 : 32;
+        for (int j = 0; j < m_blk; ++j) {
+          const int i = i_base + j * i_step;
+          if (i >= n_in) continue;
+          unsigned gi = 0;
+          int li = 0;
+          if (DENSE) gi = glist[i]; else li = list[i];
+          const float4 p = DENSE ? a.surfS[gi] : s_pts[li];
+          const float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
+          if (DENSE && !(d2 < a.r2_shot)) continue;
           ++nshot;
-          float4 nr = nrm_at(i);
-          if (!finite3(nr.x, nr.y, nr.z)) continue;
-          double cosineDesc = (double)dot3_rn(nr.x, nr.y, nr.z, rf[6], rf[7], rf[8]);
-          cosineDesc = fmin(1.0, fmax(-1.0, cosineDesc));
-          double bdS = ((1.0 + cosineDesc) * 10) / 2;
+          float nrx, nry, nrz;
+          if (DENSE) {
+            const float4 nr = a.snrmS[gi];
+            nrx = nr.x; nry = nr.y; nrz = nr.z;
+          } else {
+            nrx = s_nx[li]; nry = s_ny[li]; nrz = s_nz[li];
+          }
+          if (!finite3(nrx, nry, nrz)) continue;
+          const float cosf_ = fminf(1.0f, fmaxf(-1.0f, dot3_rn(nrx, nry, nrz, rf[6], rf[7], rf[8])));
           if (d2 < 1E-30f) continue;  // reference: fabs(sqrt(d2)) < 1e-15
-          const float distance = __fsqrt_rn(d2);
-          float dx = __fsub_rn(p.x, kx), dy = __fsub_rn(p.y, ky), dz = __fsub_rn(p.z, kz);
+          // bin position bdS = ((1 + cos) * 10) / 2, stepS = floor(bdS + 0.5), fraction bdS - stepS
+          int stepS;
+          float fracS;
+          {
+            const float bd = fmaf(cosf_, 5.0f, 5.0f);
+            const float t = bd + 0.5f, st = floorf(t), fr = t - st;
+            if (fr < 1e-4f || fr > 0.9999f) {  // near a rounding boundary: the reference's fp64 evaluation decides
+              double bdS = ((1.0 + (double)cosf_) * 10) / 2;
+              const int s = (int)floor(bdS + 0.5);
+              bdS -= s;
+              stepS = s;
+              fracS = (float)bdS;
+            } else {
+              stepS = (int)st;
+              fracS = bd - st;
+            }
+          }
+          const float inv_d = rsqrt_approx(d2);
+          const float distance = d2 * inv_d;
+          const float dx = __fsub_rn(p.x, kx), dy = __fsub_rn(p.y, ky), dz = __fsub_rn(p.z, kz);
           float xIn = dot3_rn(dx, dy, dz, rf[0], rf[1], rf[2]);
           float yIn = dot3_rn(dx, dy, dz, rf[3], rf[4], rf[5]);
           float zIn = dot3_rn(dx, dy, dz, rf[6], rf[7], rf[8]);
@@ -552,32 +652,43 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
           const bool outer = d2 >= a.t2_gt_r12;  // sqrt((double)d2) > r/2
           di += outer ? 2 : 0;
 
-          int stepS = (int)floor(bdS + 0.5);
           const int volS = di * 11;
-          bdS -= stepS;
-          float wS = (float)(1 - fabs(bdS));
-          if (bdS > 0)
-            hist_add(hist, volS + ((stepS + 1) % 10), (float)bdS, fix_scale);
+          float wS = 1.0f - fabsf(fracS);
+          if (fracS > 0.f)
+            hist_add(hist, volS + ((stepS + 1) % 10), fracS, fix_scale);
           else
-            hist_add(hist, volS + ((stepS - 1 + 10) % 10), (float)-bdS, fix_scale);
+            hist_add(hist, volS + ((stepS - 1 + 10) % 10), -fracS, fix_scale);
           int stepC = 0, volC = 0;
           float wC = 0.f;
           if (COLOR) {
-            float4 lb = multi ? a.slabS[glist[i]] : s_lab[list[i]];
-            float cdist = __fdiv_rn(
+            float4 lb;
+            if (DENSE) lb = a.slabS[gi]; else lb = s_lab[li];
+            const float cdist = __fdiv_rn(
                 __fadd_rn(fabsf(__fsub_rn(LRef, lb.x)),
                           __fdiv_rn(__fadd_rn(fabsf(__fsub_rn(aRef, lb.y)), fabsf(__fsub_rn(bRef, lb.z))), 2.0f)),
                 3.0f);
-            double cd = fmin(1.0, fmax(0.0, (double)cdist));
-            double bdC = cd * 30;
-            stepC = (int)floor(bdC + 0.5);
+            const float cd = fminf(1.0f, fmaxf(0.0f, cdist));
+            float fracC;
+            {
+              const float bd = cd * 30.0f;
+              const float t = bd + 0.5f, st = floorf(t), fr = t - st;
+              if (fr < 1e-4f || fr > 0.9999f) {
+                double bdC = (double)cd * 30;
+                const int s = (int)floor(bdC + 0.5);
+                bdC -= s;
+                stepC = s;
+                fracC = (float)bdC;
+              } else {
+                stepC = (int)st;
+                fracC = bd - st;
+              }
+            }
             volC = 352 + di * 31;
-            bdC -= stepC;
-            wC = (float)(1 - fabs(bdC));
-            if (bdC > 0)
-              hist_add(hist, volC + ((stepC + 1) % 30), (float)bdC, fix_scale);
+            wC = 1.0f - fabsf(fracC);
+            if (fracC > 0.f)
+              hist_add(hist, volC + ((stepC + 1) % 30), fracC, fix_scale);
             else
-              hist_add(hist, volC + ((stepC - 1 + 30) % 30), (float)-bdC, fix_scale);
+              hist_add(hist, volC + ((stepC - 1 + 30) % 30), -fracC, fix_scale);
           }
 #define SHOT_NEIGHBOUR(DI, VAL)                                           \
   do {                                                                    \
@@ -586,7 +697,7 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
   } while (0)
           float wAdd = 0.f;
           if (outer) {
-            float rd = (distance - r34f) * inv_r12f;
+            const float rd = (distance - r34f) * inv_r12f;
             if (d2 >= a.t2_gt_r34)  // sqrt((double)d2) > 3r/4
               wAdd += 1.f - rd;
             else {
@@ -594,7 +705,7 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
               SHOT_NEIGHBOUR(di - 2, -rd);
             }
           } else {
-            float rd = (distance - r14f) * inv_r12f;
+            const float rd = (distance - r14f) * inv_r12f;
             if (d2 < a.t2_ge_r14)  // sqrt((double)d2) < r/4
               wAdd += 1.f + rd;
             else {
@@ -602,56 +713,48 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
               SHOT_NEIGHBOUR(di + 2, rd);
             }
           }
-          wS += wAdd;
-          wC += wAdd;
           // the reference branches on acos(z/d) > 90 deg (ties: z <= 0), which is z <= 0 for every representable input
-          const float incl = acosf(fminf(1.f, fmaxf(-1.f, __fdiv_rn(zIn, distance))));
+          const float incl = acos_fast(fminf(1.f, fmaxf(-1.f, zIn * inv_d)));
           if (zIn <= 0.f) {
-            float id = (incl - (float)PST_RAD_135) * inv_90f;
+            const float id = (incl - (float)PST_RAD_135) * inv_90f;
             if (id > 0.f) {
-              wS += 1.f - id;
-              wC += 1.f - id;
+              wAdd += 1.f - id;
             } else {
-              wS += 1.f + id;
-              wC += 1.f + id;
+              wAdd += 1.f + id;
               SHOT_NEIGHBOUR(di + 1, -id);
             }
           } else {
-            float id = (incl - (float)PST_RAD_45) * inv_90f;
+            const float id = (incl - (float)PST_RAD_45) * inv_90f;
             if (id < 0.f) {
-              wS += 1.f + id;
-              wC += 1.f + id;
+              wAdd += 1.f + id;
             } else {
-              wS += 1.f - id;
-              wC += 1.f - id;
+              wAdd += 1.f - id;
               SHOT_NEIGHBOUR(di - 1, id);
             }
           }
           if (yIn != 0.f || xIn != 0.f) {
-            float az = atan2f(yIn, xIn);
-            int sel = di >> 2;
+            const float az = atan2_fast(yIn, xIn);
+            const int sel = di >> 2;
             float ad = (az - (float)(-PST_RAD_PI_7_8 + PST_RAD_45 * sel)) * inv_45f;
             ad = fmaxf(-0.5f, fminf(ad, 0.5f));
             if (ad > 0.f) {
-              wS += 1.f - ad;
-              wC += 1.f - ad;
+              wAdd += 1.f - ad;
               SHOT_NEIGHBOUR((di + 4) % 32, ad);
             } else {
-              wS += 1.f + ad;
-              wC += 1.f + ad;
+              wAdd += 1.f + ad;
               SHOT_NEIGHBOUR((di - 4 + 32) % 32, -ad);
             }
           }
 #undef SHOT_NEIGHBOUR
-          hist_add(hist, volS + stepS, wS, fix_scale);
-          if (COLOR) hist_add(hist, volC + stepC, wC, fix_scale);
+          hist_add(hist, volS + stepS, wS + wAdd, fix_scale);
+          if (COLOR) hist_add(hist, volC + stepC, wC + wAdd, fix_scale);
         }
-        } while (!multi && fromC < T);
+        } while (!DENSE && fromC < T);
       }
       nshot = warp_sum(nshot);
-      if (have && lane == 0 && a.nbr_counts && frame_ok) atomicAdd(&a.nbr_counts[1], (unsigned long long)nshot);
+      if (lane == 0 && a.nbr_counts && frame_ok) atomicAdd(&a.nbr_counts[1], (unsigned long long)nshot);
       __syncwarp();
-      if (have) {
+      {
         float* out = a.desc_out + (size_t)kidx * D;
         if (!frame_ok || nshot < 5) {
           for (int j = lane; j < D; j += 32) out[j] = __int_as_float(0x7fc00000);
@@ -712,7 +815,7 @@ static int shot_warps(bool color) { return color ? kWarpsCshot : kWarpsShot; }
 static size_t shot_smem_for(bool color, int stage_cap) {
   const int D = color ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   const size_t W = (size_t)shot_warps(color);
-  return sizeof(float4) * (size_t)stage_cap * (color ? 3 : 2) + sizeof(unsigned) * W * D +
+  return (size_t)stage_cap * (color ? 44 : 28) + sizeof(unsigned) * W * D +
          (stage_cap ? sizeof(unsigned short) * W * kList : 0);
 }
 size_t shot_smem_bytes(bool color) { return shot_smem_for(color, kChunk); }
@@ -783,8 +886,8 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   a.item_beg = w.item_beg.as<long long>();
   a.item_len = w.item_len.as<int>();
   unsigned long long h_pop = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&h_pop, max_pop, sizeof(h_pop), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &h_pop, max_pop, sizeof(h_pop)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   a.glist = nullptr;
   a.gcap = 0;
   a.dense = 0;
@@ -805,22 +908,30 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
     PCDB_CUDA(w.shot_glist.ensure(bytes));
     a.glist = w.shot_glist.as<unsigned>();
   }
+  // keypoints drawn per item (the helper scheme of the staged launch)
+  PCDB_CUDA(w.item_next.ensure(sizeof(int) * (size_t)(Q + 1)));
+  PCDB_CUDA(cudaMemsetAsync(w.item_next.p, 0, sizeof(int) * (size_t)(Q + 1), st));
+  a.item_next = w.item_next.as<int>();
+  static const int blocked = [] { const char* e = getenv("PCDB_SHOT_BLOCKED"); return e ? atoi(e) : 1; }();
+  a.blocked = blocked;
   if (color) {
-    PCDB_CUDA(cudaFuncSetAttribute(k_shot<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_shot<true><<<grid, kThreads, smem, st>>>(a);
+    PCDB_CUDA(cudaFuncSetAttribute(k_shot<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_shot<true, false><<<grid, kThreads, smem, st>>>(a);
   } else {
-    PCDB_CUDA(cudaFuncSetAttribute(k_shot<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_shot<false><<<grid, kThreads, smem, st>>>(a);
+    PCDB_CUDA(cudaFuncSetAttribute(k_shot<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_shot<false, false><<<grid, kThreads, smem, st>>>(a);
   }
   PCDB_LAUNCH_CHECK();
   if (a.glist) {  // the keypoints whose 27 cells do not fit the stage: second launch, warp per keypoint
     a.dense = 1;
     a.stage_cap = 0;
     const size_t dsmem = shot_smem_for(color, 0);
-    if (color)
-      k_shot<true><<<dense_grid, kThreads, dsmem, st>>>(a);
-    else
-      k_shot<false><<<dense_grid, kThreads, dsmem, st>>>(a);
+    if (color) {
+      PCDB_CUDA(cudaFuncSetAttribute(k_shot<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+      k_shot<true, true><<<dense_grid, kThreads, dsmem, st>>>(a);
+    } else {
+      k_shot<false, true><<<dense_grid, kThreads, dsmem, st>>>(a);
+    }
     PCDB_LAUNCH_CHECK();
   }
   return PCDB_OK;

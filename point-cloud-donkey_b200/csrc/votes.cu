@@ -244,8 +244,8 @@ int stage_cast_votes(pcdb_ctx* ctx, const float* feat_xyz_d, const float* feat_l
   PCDB_LAUNCH_CHECK();
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, w.vote_cnt.as<int>(), w.vote_pos.as<int>(), T + 1));
   int V = 0;
-  PCDB_CUDA(cudaMemcpyAsync(&V, w.vote_pos.as<int>() + T, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PCDB_CUDA(cudaStreamSynchronize(st));
+  PCDB_TRY(pcdb_read_small(ctx, &V, w.vote_pos.as<int>() + T, sizeof(int)));
+  PCDB_TRY(pcdb_sync_reads(ctx));
   PCDB_CUDA(w.votes.ensure(sizeof(pcdb_vote) * (size_t)(V + 1)));
   PCDB_CUDA(w.vote_pw.ensure(sizeof(float4) * (size_t)(V + 1)));
   PCDB_CUDA(w.vote_cloud.ensure(sizeof(int) * (size_t)(V + 1)));
