@@ -71,7 +71,8 @@ struct ShotArgs {
   int* work_counter_dense;
   int* item_next;    // staged launch: keypoints drawn so far from every item (global, so that helper CTAs share an item)
   int blocked;       // pass C: lane-blocked (1) or lane-strided (0) walk of the in-radius list
-  unsigned* glist;   // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of in-radius points
+  float4* glist;     // dense neighbourhoods (more than kChunk points in the 27 cells): per-warp lists of the in-radius
+                     // points themselves, (x, y, z, sorted-surface index bits): the passes read them back coalesced
   long long gcap;    // entries per warp (>= the largest 27-cell population of the batch)
 };
 
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
   unsigned short* list = s_list + (size_t)warp * (DENSE ? 0 : kList);
   long long* s_rbeg = s_rbeg_all[DENSE ? warp : 0];
   int* s_rlen = s_rlen_all[DENSE ? warp : 0];
-  unsigned* glist = DENSE ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
+  float4* glist = DENSE ? a.glist + ((size_t)blockIdx.x * kWarps + warp) * a.gcap : nullptr;
   // helper passes over the last n_tail items (see above); few items (a single cloud) => many CTAs share each of them
   const int n_tail = min(n_items, (int)gridDim.x);
   const int n_pass = DENSE ? 0 : (n_items >= (int)gridDim.x ? 4 : min(64, max(4, 2 * (int)gridDim.x / max(1, n_items))));
@@ -389,33 +390,38 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
         __syncwarp();
         return n;
       };
-      // Dense neighbourhood: one sweep over the nine runs (coalesced float4 reads, served by L2) keeps the indices of
-      // the points inside the larger of the two radii; the passes below then touch only those (typically < 10 % of the
-      // 27-cell population) and apply their own radius inline.  No block-wide barrier in this mode.
+      // Dense neighbourhood: one sweep over the nine runs (coalesced float4 reads, served by L2, two independent loads
+      // per lane and iteration) copies the points inside the larger of the two radii into this warp's global list; the
+      // passes below then read only those (typically < 10 % of the 27-cell population), coalesced and without a
+      // dependent index load, and apply their own radius inline.  No block-wide barrier in this mode.
       int n_g = 0;
       if (DENSE) {
         for (int r = 0; r < 9; ++r) {
           const long long rb = s_rbeg[r];
           const int rl = s_rlen[r];
-          for (int e0 = 0; e0 < rl; e0 += 32) {
-            const int e = e0 + lane;
-            bool in = false;
-            if (e < rl) {
-              const float4 p = a.surfS[rb + e];
-              in = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z) < r2_max;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (in) glist[n_g + __popc(m & ((1u << lane) - 1u))] = (unsigned)(rb + e);
-            n_g += __popc(m);
+          for (int e0 = 0; e0 < rl; e0 += 64) {
+            const int ea = e0 + lane, eb = ea + 32;
+            float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+            if (ea < rl) pa = a.surfS[rb + ea];
+            if (eb < rl) pb = a.surfS[rb + eb];
+            const bool ina = ea < rl && sqdist3_rn(kx, ky, kz, pa.x, pa.y, pa.z) < r2_max;
+            const bool inb = eb < rl && sqdist3_rn(kx, ky, kz, pb.x, pb.y, pb.z) < r2_max;
+            const unsigned ma = __ballot_sync(0xffffffffu, ina), mb = __ballot_sync(0xffffffffu, inb);
+            const unsigned below = (1u << lane) - 1u;
+            if (ina) glist[n_g + __popc(ma & below)] = make_float4(pa.x, pa.y, pa.z, __int_as_float((int)(rb + ea)));
+            n_g += __popc(ma);
+            if (inb) glist[n_g + __popc(mb & below)] = make_float4(pb.x, pb.y, pb.z, __int_as_float((int)(rb + eb)));
+            n_g += __popc(mb);
           }
         }
         __syncwarp();
       }
-      auto pt_at = [&](int i) -> float4 {  // .w: rgb bits (dense) / surface index bits (staged) — neither is used as xyz
-        if constexpr (DENSE) return a.surfS[glist[i]]; else return s_pts[list[i]];
+      auto pt_at = [&](int i) -> float4 {  // .w: sorted-surface index (dense) / index inside the cloud (staged), as bits
+        if constexpr (DENSE) return glist[i]; else return s_pts[list[i]];
       };
       auto idx_at = [&](int i) -> int {  // index of the point inside its cloud (tie-break key of the sorted kd-tree result)
-        if constexpr (DENSE) return __float_as_int(a.snrmS[glist[i]].w); else return __float_as_int(s_pts[list[i]].w);
+        if constexpr (DENSE) return __float_as_int(a.snrmS[__float_as_int(glist[i].w)].w);
+        else return __float_as_int(s_pts[list[i]].w);
       };
       float rf[9];
       bool lrf_ok = true;
@@ -597,10 +603,15 @@ __global__ void __launch_bounds__((COLOR ? kWarpsCshot : kWarpsShot) * 32, COLOR
         for (int j = 0; j < m_blk; ++j) {
           const int i = i_base + j * i_step;
           if (i >= n_in) continue;
-          unsigned gi = 0;
-          int li = 0;
-          if (DENSE) gi = glist[i]; else li = list[i];
-          const float4 p = DENSE ? a.surfS[gi] : s_pts[li];
+          int gi = 0, li = 0;
+          float4 p;
+          if (DENSE) {
+            p = glist[i];
+            gi = __float_as_int(p.w);
+          } else {
+            li = list[i];
+            p = s_pts[li];
+          }
           const float d2 = sqdist3_rn(kx, ky, kz, p.x, p.y, p.z);
           if (DENSE && !(d2 < a.r2_shot)) continue;
           ++nshot;
@@ -901,12 +912,12 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   const int dense_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * (color ? 1 : 2), cdiv(Q, kWarps));
   if (h_pop > (unsigned long long)kChunk) {
     a.gcap = (long long)((h_pop + 31) & ~31ull);
-    const size_t bytes = sizeof(unsigned) * (size_t)a.gcap * (size_t)dense_grid * kWarps;
-    if (bytes > (16ull << 30))
+    const size_t bytes = sizeof(float4) * (size_t)a.gcap * (size_t)dense_grid * kWarps;
+    if (bytes > (32ull << 30))
       return ctx->fail(PCDB_E_INVALID, "a 27-cell neighbourhood holds %llu points: radius too large for this cloud density",
                        h_pop);
     PCDB_CUDA(w.shot_glist.ensure(bytes));
-    a.glist = w.shot_glist.as<unsigned>();
+    a.glist = w.shot_glist.as<float4>();
   }
   // keypoints drawn per item (the helper scheme of the staged launch)
   PCDB_CUDA(w.item_next.ensure(sizeof(int) * (size_t)(Q + 1)));
@@ -914,14 +925,32 @@ int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lr
   a.item_next = w.item_next.as<int>();
   static const int blocked = [] { const char* e = getenv("PCDB_SHOT_BLOCKED"); return e ? atoi(e) : 1; }();
   a.blocked = blocked;
-  if (color) {
-    PCDB_CUDA(cudaFuncSetAttribute(k_shot<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_shot<true, false><<<grid, kThreads, smem, st>>>(a);
-  } else {
-    PCDB_CUDA(cudaFuncSetAttribute(k_shot<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_shot<false, false><<<grid, kThreads, smem, st>>>(a);
+  // Staged launch.  With both stages requested it runs as two launches of the same kernel — frames first, descriptors
+  // second (reading the frames back): the 32 resident warps of an SM then loop over ~5 KB of code instead of ~25 KB
+  // spread over five phases, which is what the 6 KB L0 instruction caches can hold (one fused launch measured 2.4
+  // no-instruction stalls per issue).  The cloud is staged twice; that is 57 KB per item against ~4 M instructions.
+  static const int split_env = [] { const char* e = getenv("PCDB_SHOT_SPLIT"); return e ? atoi(e) : 1; }();
+  const bool split = split_env && do_lrf && do_desc && lrf_out_d != nullptr;
+  for (int phase = 0; phase < (split ? 2 : 1); ++phase) {
+    ShotArgs b = a;
+    if (split) {
+      b.do_lrf = phase == 0;
+      b.do_desc = phase == 1;
+      b.lrf_in = lrf_out_d;
+      if (phase == 1) {
+        PCDB_CUDA(cudaMemsetAsync(w.scalars.p, 0, 4, st));  // the staged launch's work counter
+        PCDB_CUDA(cudaMemsetAsync(w.item_next.p, 0, sizeof(int) * (size_t)(Q + 1), st));
+      }
+    }
+    if (color) {
+      PCDB_CUDA(cudaFuncSetAttribute(k_shot<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_shot<true, false><<<grid, kThreads, smem, st>>>(b);
+    } else {
+      PCDB_CUDA(cudaFuncSetAttribute(k_shot<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_shot<false, false><<<grid, kThreads, smem, st>>>(b);
+    }
+    PCDB_LAUNCH_CHECK();
   }
-  PCDB_LAUNCH_CHECK();
   if (a.glist) {  // the keypoints whose 27 cells do not fit the stage: second launch, warp per keypoint
     a.dense = 1;
     a.stage_cap = 0;
