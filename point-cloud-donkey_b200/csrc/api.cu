@@ -899,6 +899,7 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
   Workspace& w = ctx->ws;
   PCDB_TRY(upload(ctx, w.feat_desc, queries, sizeof(float) * (size_t)ctx->cb.D * Q));
   ctx->comm_events_valid = false;
+  ctx->gemm_events_valid = false;
   PCDB_TRY(activate(ctx, w.feat_desc.as<float>(), Q, k, dist_type, mode, ctx->prm.use_distance_ratio != 0,
                     ctx->prm.distance_ratio_threshold));
   ctx->stats.comm_ms = 0;
@@ -907,6 +908,11 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
   PCDB_TRY(download(ctx, count_out, w.knn_cnt.p, sizeof(int) * Q));
   PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.comm_ms = comm_last_exchange_ms(ctx);
+  ctx->stats.knn_gemm_ms = 0;
+  if (ctx->gemm_events_valid) {
+    float g = 0;
+    if (cudaEventElapsedTime(&g, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->stats.knn_gemm_ms = g;
+  }
   return PCDB_OK;
 }
 

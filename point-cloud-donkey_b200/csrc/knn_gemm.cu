@@ -320,7 +320,7 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             mbar_wait(&bars->empty[stage], phase ^ 1);
             unsigned char* sb = stage0 + stage * STAGE_BYTES;
             if (leader) mbar_expect_tx(&bars->full[stage], (unsigned)(2 * STAGE_BYTES));
-            tma_load_2d_pair(sb, &map_b, &bars->full[stage], kb * BK, t * BN + (int)rank * BN_HALF);
+            tma_load_2d_pair(sb, &map_b, &bars->full[stage], 0, ((t * 2 + (int)rank) * KB + kb) * BN_HALF);  // box-major operand
             if (!A_RES) tma_load_2d_pair(sb + B_BOX_BYTES, &map_a, &bars->full[stage], kb * BK, q_row0);
             if (++stage == STAGES) {
               stage = 0;
@@ -532,6 +532,14 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int
   const int lane = threadIdx.x & 31;
   if (r >= n) return;
   const int Dh = D + (aug ? K_AUG : 0);  // aug == 0: plain fp16 copy (streaming-query variant)
+  // Codebook operand: stored box by box — [128-row block][K block][128 rows][64 columns] — so that every TMA box of the
+  // sweep is ONE contiguous 16 KB run of HBM instead of 128 segments of 128 B at a row stride (a lone cloud's activation
+  // streams the codebook straight from HBM: 2.9 TB/s row-major).  Queries stay row-major (loaded once per work unit).
+  const int KBt = (Dh + BK - 1) / BK;
+  auto at = [&](int j) -> size_t {
+    if (CODEBOOK) return ((((size_t)(r >> 7) * KBt + (j >> 6)) << 7 | (size_t)(r & 127)) << 6) | (size_t)(j & 63);
+    return (size_t)r * Dh + j;
+  };
   double s2 = 0, e2 = 0, h2 = 0;
   bool bad = false;
   for (int j = lane; j < D; j += 32) {
@@ -542,7 +550,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int
     }
     __half h = __float2half_rn(v);
     float hv = __half2float(h);
-    xh[r * Dh + j] = (CODEBOOK && aug) ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
+    xh[at(j)] = (CODEBOOK && aug) ? __float2half_rn(-2.0f * hv) : h;  // exact: a power-of-two multiple
     s2 += (double)v * v;
     h2 += (double)hv * hv;
     double dd = (double)v - (double)hv;
@@ -568,7 +576,7 @@ __global__ void k_prep_rows(const float* __restrict__ x, long long n, int D, int
     } else if (lane < 2) {
       a = __float2half_rn(1.0f);
     }
-    xh[r * Dh + D + lane] = a;
+    xh[at(D + lane)] = a;
   }
   if (lane == 0) {
     if (norm2) norm2[r] = (float)s2;
@@ -709,9 +717,11 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows) {
+// blocked: the box-major codebook operand (k_prep_rows), a [rows][BK] array of which every box is one contiguous run
+int make_map(pcdb_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int D, int box_rows, bool blocked = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return ctx->fail(PCDB_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (blocked) D = BK;
   cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__half)};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
@@ -819,7 +829,10 @@ int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
   GemmState* gs = state_of(ctx);
   GemmOperand& op = gs->op[fam];
   const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
-  PCDB_CUDA(op.words_h.ensure(sizeof(__half) * (size_t)cb.N * Dh + 256));
+  const int KBt = (Dh + BK - 1) / BK;
+  const int64_t blk_rows = (int64_t)cdiv(cb.N, BN_HALF) * KBt * BN_HALF;  // rows of the box-major [rows][BK] operand
+  PCDB_CUDA(op.words_h.ensure(sizeof(__half) * (size_t)blk_rows * BK + 256));
+  PCDB_CUDA(cudaMemsetAsync(op.words_h.p, 0, sizeof(__half) * (size_t)blk_rows * BK, st));  // padding rows / columns
   PCDB_CUDA(op.cnorm.ensure(sizeof(float) * (n_pad + 4)));
   PCDB_CUDA(op.cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
   PCDB_CUDA(op.cerr.ensure(sizeof(float) * (cb.N + 1)));
@@ -855,7 +868,7 @@ int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
     op.release();  // non-finite codewords, or negative entries under chi^2: scan path only
     return PCDB_OK;
   }
-  PCDB_TRY(make_map(ctx, &op.map_b, op.words_h.p, cb.N, Dh, BN_HALF));
+  PCDB_TRY(make_map(ctx, &op.map_b, op.words_h.p, blk_rows, Dh, BN_HALF, true));
   cb.gemm_ready[fam] = true;
   return PCDB_OK;
 }
@@ -942,6 +955,8 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
     }
     S = best_s;
   }
+  static const int s_env = [] { const char* e = getenv("PCDB_GEMM_S"); return e ? atoi(e) : 0; }();  // experiments
+  if (s_env > 0) S = s_env;
   S = std::max(1, std::min(S, g.n_ntiles));
   g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
   S = (int)cdiv(g.n_ntiles, g.tiles_per_split);

@@ -557,6 +557,7 @@ __device__ void quat_avg_eig(const float S[4][4], float q[4]) {
 }
 
 // ---- K10: per-maximum reduction (voting.cpp:130-236), one warp per maximum -------------------------------------
+constexpr int kInstSlots = 256;  // per-warp hash set of the distinct instance ids of one maximum (k_max_reduce)
 __global__ void k_max_reduce(const int* __restrict__ M_ptr, const float4* __restrict__ mpos,
                              const int* __restrict__ mseg, const unsigned* __restrict__ seg_key,
                              const int* __restrict__ mem_off, const long long* __restrict__ mem_idx,
@@ -578,19 +579,60 @@ __global__ void k_max_reduce(const int* __restrict__ M_ptr, const float4* __rest
   sx = warp_sum(sx);
   sy = warp_sum(sy);
   sz = warp_sum(sz);
-  // instance with the largest summed weight (std::map order: ascending id, strict >)  (:140-167)
+  // instance with the largest summed weight (std::map order: ascending id, strict >)  (:140-167).  Every instance's
+  // weights are summed in member order (the order the reference adds them to its map entry).  The distinct ids of the
+  // maximum are collected in a small per-warp hash set first; then every lane owns one id and walks the members once:
+  // n * ceil(I / 32) steps instead of the n^2 of "every member rescans all members" (a dense scene puts 10^4..10^5
+  // votes into one maximum but only a few dozen training instances).
+  __shared__ unsigned s_set[4][kInstSlots];
+  __shared__ int s_nset[4];
+  unsigned* set = s_set[threadIdx.x >> 5];
+  for (int i = lane; i < kInstSlots; i += 32) set[i] = 0xffffffffu;
+  if (lane == 0) s_nset[threadIdx.x >> 5] = 0;
+  __syncwarp();
+  bool overflow = false;
+  for (int i = o0 + lane; i < o1; i += 32) {
+    const unsigned inst = votes[mem_idx[i]].instance_id;
+    if (inst == 0xffffffffu) { overflow = true; continue; }  // the empty marker itself: slow path
+    unsigned h = (inst * 2654435761u) % kInstSlots;
+    for (int probe = 0; probe < kInstSlots; ++probe) {
+      const unsigned prev = atomicCAS(&set[h], 0xffffffffu, inst);
+      if (prev == 0xffffffffu) { atomicAdd(&s_nset[threadIdx.x >> 5], 1); break; }
+      if (prev == inst) break;
+      h = (h + 1) % kInstSlots;
+    }
+    if (s_nset[threadIdx.x >> 5] > kInstSlots / 2) { overflow = true; break; }
+  }
+  overflow = __any_sync(0xffffffffu, overflow);
+  __syncwarp();
   float bw = 0.f;
   unsigned bid = 0xffffffffu;
   float w_inst0 = 0.f;
-  for (int i = o0 + lane; i < o1; i += 32) {
-    unsigned inst = votes[mem_idx[i]].instance_id;
-    float tot = 0.f;
-    for (int j = o0; j < o1; ++j)
-      if (votes[mem_idx[j]].instance_id == inst) tot = __fadd_rn(tot, mem_w[j]);
-    if (inst == 0) w_inst0 = tot;
-    if (tot > bw || (tot == bw && tot > 0.f && inst < bid)) {
-      bw = tot;
-      bid = inst;
+  if (!overflow) {
+    for (int base = 0; base < kInstSlots; base += 32) {
+      const unsigned inst = set[base + lane];
+      if (!__any_sync(0xffffffffu, inst != 0xffffffffu)) continue;
+      float tot = 0.f;
+      for (int j = o0; j < o1; ++j)
+        if (votes[mem_idx[j]].instance_id == inst) tot = __fadd_rn(tot, mem_w[j]);
+      if (inst == 0xffffffffu) continue;
+      if (inst == 0) w_inst0 = tot;
+      if (tot > bw || (tot == bw && tot > 0.f && inst < bid)) {
+        bw = tot;
+        bid = inst;
+      }
+    }
+  } else {
+    for (int i = o0 + lane; i < o1; i += 32) {
+      unsigned inst = votes[mem_idx[i]].instance_id;
+      float tot = 0.f;
+      for (int j = o0; j < o1; ++j)
+        if (votes[mem_idx[j]].instance_id == inst) tot = __fadd_rn(tot, mem_w[j]);
+      if (inst == 0) w_inst0 = tot;
+      if (tot > bw || (tot == bw && tot > 0.f && inst < bid)) {
+        bw = tot;
+        bid = inst;
+      }
     }
   }
 #pragma unroll

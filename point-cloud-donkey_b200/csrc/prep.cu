@@ -20,8 +20,47 @@ int pcdb_cub_exclusive_sum_i32(pcdb_ctx* ctx, const int* in, int* out, int64_t n
   ctx->stats.kernel_launches++;
   return PCDB_OK;
 }
+// One cloud at a time (the GUI / detect() latency path) sorts ~2000 keys: the device-wide radix sort spends 7 onesweep
+// launches of ~9 us each on that.  Up to 4096 pairs are sorted by ONE CTA instead (block radix sort, stable like the
+// device-wide one; keys beyond n are padded with all-ones and sort behind every real key of equal low bits).
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_sort_small_u64(const unsigned long long* __restrict__ kin,
+                                                            unsigned long long* __restrict__ kout,
+                                                            const int* __restrict__ vin, int* __restrict__ vout, int n,
+                                                            int end_bit) {
+  using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS, int>;
+  __shared__ typename Sort::TempStorage tmp;
+  unsigned long long k[ITEMS];
+  int v[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = threadIdx.x * ITEMS + i;
+    k[i] = idx < n ? kin[idx] : ~0ull;
+    v[i] = idx < n ? vin[idx] : -1;
+  }
+  Sort(tmp).Sort(k, v, 0, end_bit);
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int idx = threadIdx.x * ITEMS + i;
+    if (idx < n) {
+      kout[idx] = k[i];
+      vout[idx] = v[i];
+    }
+  }
+}
+
 int pcdb_cub_sort_pairs_u64(pcdb_ctx* ctx, const unsigned long long* kin, unsigned long long* kout, const int* vin,
                             int* vout, int64_t n, int end_bit) {
+  if (n > 0 && n <= 1024) {
+    k_sort_small_u64<256, 4><<<1, 256, 0, ctx->stream>>>(kin, kout, vin, vout, (int)n, end_bit);
+    PCDB_LAUNCH_CHECK();
+    return PCDB_OK;
+  }
+  if (n > 0 && n <= 4096) {
+    k_sort_small_u64<512, 8><<<1, 512, 0, ctx->stream>>>(kin, kout, vin, vout, (int)n, end_bit);
+    PCDB_LAUNCH_CHECK();
+    return PCDB_OK;
+  }
   size_t tmp = 0;
   PCDB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, end_bit, ctx->stream));
   PCDB_CUDA(ctx->ws.cub_tmp.ensure(tmp));
