@@ -97,10 +97,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def build_world(name, n_words_override, ctx, rank_log=True):
-    """Synthetic training set -> GPU features -> GPU-activated codebook (untimed set-up)."""
+def build_world(name, n_words_override, ctx, rank_log=True, dist=""):
+    """Synthetic training set -> GPU features -> GPU-activated codebook (untimed set-up).  `dist` overrides the
+    workload's DistanceType BEFORE training: the per-class sigma^2 of the vote filter is learned from training-time
+    distances, so a codebook trained under one functor casts no votes under the other."""
     wl = synth.WORKLOADS[name]
     prm = synth.workload_params(name)
+    if dist:
+        prm.distance_type = 1 if dist == "chisquared" else 0
     n_cls, P = wl["n_classes"], wl["P"]
     n_words = n_words_override or wl["n_words"]
     ctx.set_params(prm)
@@ -167,10 +171,12 @@ class _CpuTrainCtx:
         return self.orc.distance(a, b, dist_type)
 
 
-def build_world_cpu(name, n_words_override, orc):
+def build_world_cpu(name, n_words_override, orc, dist=""):
     """build_world on the host cores only (oracle features + identity-rule training): the reference arm's set-up."""
     wl = synth.WORKLOADS[name]
     prm = synth.workload_params(name)
+    if dist:
+        prm.distance_type = 1 if dist == "chisquared" else 0
     n_cls, P = wl["n_classes"], wl["P"]
     n_words = n_words_override or wl["n_words"]
     t0 = time.time()
@@ -419,9 +425,7 @@ def main():
         # host cores only: no libpcdb200, no CUDA context (the codebook is trained on the CPU by the identity rule)
         from oracle import oracle_py as orc
         orc.set_num_threads(os.cpu_count() or 1)
-        wl, prm, cb = build_world_cpu(args.workload, args.words, orc)
-        if args.dist:
-            prm.distance_type = 1 if args.dist == "chisquared" else 0
+        wl, prm, cb = build_world_cpu(args.workload, args.words, orc, args.dist)
         config = workload_config(args.workload, wl, cb, args.batch, args.words)
         model = orc.Model(prm, cb)
         cores = orc.num_threads()
@@ -466,10 +470,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = api.Context(device=local_rank)
-    wl, prm, cb = build_world(args.workload, args.words, ctx, rank_log=(rank == 0))
-    if args.dist:
-        prm.distance_type = 1 if args.dist == "chisquared" else 0
-        ctx.set_params(prm)
+    wl, prm, cb = build_world(args.workload, args.words, ctx, rank_log=(rank == 0), dist=args.dist)
     config = workload_config(args.workload, wl, cb, args.batch, args.words)
     if args.dist == "chisquared":
         config["workload"] = config["workload"].replace("Euclidean", "ChiSquared")

@@ -233,6 +233,13 @@ int pcdb_get_maximum_votes(pcdb_ctx* ctx, int64_t* vote_index_out, float* vote_w
                            int64_t* n_out);
 /* Votes of the last pcdb_classify_batch call (Voting::getVotes, read by training_gui.cpp:1012). */
 int pcdb_get_votes(pcdb_ctx* ctx, pcdb_vote* votes_out, int64_t* vote_off_out, int64_t capacity);
+/* Sizes of what the last pcdb_classify_batch / pcdb_find_maxima / pcdb_cast_votes call left on the device: votes,
+ * maxima kept after the per-cloud threshold / BestK, member entries of pcdb_get_maximum_votes.  Callers size their
+ * buffers from these instead of from the point count (std::vector<VotingMaximum> grows on demand in the reference). */
+int pcdb_get_last_sizes(pcdb_ctx* ctx, int64_t* n_votes_out, int64_t* n_maxima_out, int64_t* n_members_out);
+/* Maxima of the last pcdb_classify_batch / pcdb_find_maxima call again (no recomputation): a caller that passed
+ * maxima_out == NULL, or too small a capacity, fetches them once it knows the count. */
+int pcdb_get_maxima(pcdb_ctx* ctx, pcdb_maximum* maxima_out, int64_t* maxima_off_out, int64_t maxima_capacity);
 
 /* ---- fused batch path (the throughput entry) -------------------------- */
 /* ImplicitShapeModel::detect (implicit_shape_model.cpp:583-712) for B clouds at once, label pick of

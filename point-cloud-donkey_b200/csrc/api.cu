@@ -453,7 +453,7 @@ int features_pipeline(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, int64_t* F_
 
 // copies the per-cloud sorted maxima out (host compaction of the padded device layout)
 int fetch_maxima(pcdb_ctx* ctx, int B, int64_t M, pcdb_maximum* maxima_out, int64_t* maxima_off_out,
-                 int64_t maxima_capacity, int32_t* label_out) {
+                 int64_t maxima_capacity, int32_t* label_out, bool count = true) {
   Workspace& w = ctx->ws;
   std::vector<int> kept(B), first(B), labels(B);
   PCDB_TRY(pcdb_read_small(ctx, kept.data(), w.max_kept.p, sizeof(int) * B));
@@ -462,19 +462,24 @@ int fetch_maxima(pcdb_ctx* ctx, int B, int64_t M, pcdb_maximum* maxima_out, int6
   std::vector<pcdb_maximum> all((size_t)std::max<int64_t>(M, 1));
   if (maxima_out && M > 0) PCDB_TRY(pcdb_read_small(ctx, all.data(), w.max_sorted.p, sizeof(pcdb_maximum) * M));
   PCDB_TRY(pcdb_sync_reads(ctx));
+  int64_t need = 0;
+  for (int b = 0; b < B; ++b) {
+    if (label_out) label_out[b] = labels[b];  // labels are complete even when the maxima do not fit
+    need += kept[b];
+  }
+  ctx->last_kept = need;
+  if (maxima_out && need > maxima_capacity)
+    return ctx->fail(PCDB_E_CAPACITY, "maxima_capacity %lld < %lld maxima (pcdb_get_last_sizes, then pcdb_get_maxima)",
+                     (long long)maxima_capacity, (long long)need);
   int64_t total = 0;
   if (maxima_off_out) maxima_off_out[0] = 0;
   for (int b = 0; b < B; ++b) {
-    if (label_out) label_out[b] = labels[b];
-    if (maxima_out) {
-      if (total + kept[b] > maxima_capacity)
-        return ctx->fail(PCDB_E_CAPACITY, "maxima_capacity %lld too small", (long long)maxima_capacity);
+    if (maxima_out)
       for (int i = 0; i < kept[b]; ++i) maxima_out[total + i] = all[(size_t)first[b] + i];
-    }
     total += kept[b];
     if (maxima_off_out) maxima_off_out[b + 1] = total;
   }
-  ctx->stats.n_maxima += total;
+  if (count) ctx->stats.n_maxima += total;
   return PCDB_OK;
 }
 
@@ -1020,6 +1025,21 @@ int pcdb_get_votes(pcdb_ctx* ctx, pcdb_vote* votes_out, int64_t* vote_off_out, i
   PCDB_TRY(download(ctx, vote_off_out, ctx->ws.vote_off.p, sizeof(int64_t) * (ctx->last_B + 1)));
   PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
   return PCDB_OK;
+}
+
+int pcdb_get_last_sizes(pcdb_ctx* ctx, int64_t* n_votes_out, int64_t* n_maxima_out, int64_t* n_members_out) {
+  if (!ctx) return PCDB_E_INVALID;
+  if (n_votes_out) *n_votes_out = ctx->last_V;
+  if (n_maxima_out) *n_maxima_out = ctx->last_kept;
+  if (n_members_out) *n_members_out = ctx->last_members;
+  return PCDB_OK;
+}
+
+int pcdb_get_maxima(pcdb_ctx* ctx, pcdb_maximum* maxima_out, int64_t* maxima_off_out, int64_t maxima_capacity) {
+  if (!ctx) return PCDB_E_INVALID;
+  PCDB_CUDA(cudaSetDevice(ctx->device));
+  if (!maxima_out && maxima_capacity > 0) return ctx->fail(PCDB_E_INVALID, "maxima_out is required");
+  return fetch_maxima(ctx, ctx->last_B, ctx->last_M, maxima_out, maxima_off_out, maxima_capacity, nullptr, false);
 }
 
 static void record_stage_times(pcdb_ctx* ctx, const float t[4]) {

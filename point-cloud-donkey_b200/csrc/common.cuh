@@ -131,7 +131,7 @@ struct pcdb_ctx {
   float* lab_lut_d = nullptr;  // 256 + 4000 floats, built on the host with powf (features_cshot.cpp:52-71)
   // host mirrors of the last batch (for pcdb_get_votes / pcdb_get_maximum_votes)
   std::vector<float> class_dim_first, class_dim_second;  // Voting::m_dimensions_map by class id (pcdb_set_class_dimensions)
-  int64_t last_V = 0, last_M = 0, last_members = 0;
+  int64_t last_V = 0, last_M = 0, last_members = 0, last_kept = 0;
   int last_B = 0;
   std::vector<int64_t> h_off_a, h_off_b;
   // Small device->host reads (counts, flags) land in a pinned area and are handed to their destinations at the next

@@ -867,32 +867,28 @@ bool ImplicitShapeModel::detectBatch(const std::vector<std::string>& filenames,
     }
     const int B = (int)(b1 - b0);
     std::vector<int32_t> labels((size_t)B);
-    const int64_t cap = std::max<int64_t>(64, off.back());
-    std::vector<pcdb_maximum> mx((size_t)cap);
+    // labels and per-cloud maxima counts first, then buffers of exactly the size the device produced (the maxima are
+    // bounded by the seeds, the votes by F * k * votes per codeword: neither by the point count)
     std::vector<int64_t> moff((size_t)B + 1);
     double t[7];
-    check(pcdb_classify_batch(m_ctx, xyz.data(), nrm.data(), rgb.data(), off.data(), B, labels.data(), mx.data(),
-                              moff.data(), cap, t));
+    check(pcdb_classify_batch(m_ctx, xyz.data(), nrm.data(), rgb.data(), off.data(), B, labels.data(), nullptr,
+                              moff.data(), 0, t));
+    int64_t n_votes = 0, n_max = 0, n_mem = 0;
+    check(pcdb_get_last_sizes(m_ctx, &n_votes, &n_max, &n_mem));
+    std::vector<pcdb_maximum> mx((size_t)std::max<int64_t>(1, n_max));
+    check(pcdb_get_maxima(m_ctx, mx.data(), moff.data(), (int64_t)mx.size()));
     static const char* keys[7] = {"complete", "features", "keypoints", "normals", "flann", "voting", "maxima"};
     for (int i = 0; i < 7; ++i) m_processing_times[keys[i]] += t[i];
     std::vector<pcdb_vote> votes;
     std::vector<int64_t> midx, voff((size_t)B + 1, 0);
     std::vector<float> mw;
     if (with_votes) {
+      midx.resize((size_t)n_mem + 1);
+      mw.resize((size_t)n_mem + 1);
       int64_t n = 0;
-      pcdb_get_maximum_votes(m_ctx, nullptr, nullptr, 0, &n);
-      midx.resize((size_t)n + 1);
-      mw.resize((size_t)n + 1);
-      check(pcdb_get_maximum_votes(m_ctx, midx.data(), mw.data(), n + 1, &n));
-      pcdb_stats st;
-      check(pcdb_get_stats(m_ctx, &st));
-      votes.resize((size_t)std::max<int64_t>(1, off.back() * std::max(1, m_params.knn_k) * 4));
-      int rc = pcdb_get_votes(m_ctx, votes.data(), voff.data(), (int64_t)votes.size());
-      if (rc == PCDB_E_CAPACITY) {
-        votes.resize((size_t)st.n_votes + 1);
-        rc = pcdb_get_votes(m_ctx, votes.data(), voff.data(), (int64_t)votes.size());
-      }
-      check(rc);
+      check(pcdb_get_maximum_votes(m_ctx, midx.data(), mw.data(), n_mem + 1, &n));
+      votes.resize((size_t)n_votes + 1);
+      check(pcdb_get_votes(m_ctx, votes.data(), voff.data(), (int64_t)votes.size()));
     }
     for (int b = 0; b < B; ++b)
       maxima[b0 + b] = toMaxima(mx.data() + moff[b], moff[b + 1] - moff[b], with_votes ? &votes : nullptr,
@@ -941,12 +937,14 @@ std::tuple<std::vector<VotingMaximum>, std::map<std::string, double>> ImplicitSh
   if (!m_codebook_uploaded) uploadCodebook();
   const int64_t off[2] = {0, (int64_t)points.size()};
   int32_t label;
-  const int64_t cap = std::max<int64_t>(64, (int64_t)points.size());
-  std::vector<pcdb_maximum> mx((size_t)cap);
   int64_t moff[2];
   double t[7];
   check(pcdb_classify_batch(m_ctx, points.xyz.data(), hasNormals ? points.normals.data() : nullptr,
-                            points.has_rgb ? points.rgb.data() : nullptr, off, 1, &label, mx.data(), moff, cap, t));
+                            points.has_rgb ? points.rgb.data() : nullptr, off, 1, &label, nullptr, moff, 0, t));
+  int64_t n_max = 0;
+  check(pcdb_get_last_sizes(m_ctx, nullptr, &n_max, nullptr));
+  std::vector<pcdb_maximum> mx((size_t)std::max<int64_t>(1, n_max));
+  check(pcdb_get_maxima(m_ctx, mx.data(), moff, (int64_t)mx.size()));
   static const char* keys[7] = {"complete", "features", "keypoints", "normals", "flann", "voting", "maxima"};
   for (int i = 0; i < 7; ++i) m_processing_times[keys[i]] += t[i];
   return std::make_tuple(toMaxima(mx.data(), moff[1], nullptr, nullptr, nullptr), m_processing_times);

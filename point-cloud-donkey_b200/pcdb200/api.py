@@ -21,7 +21,7 @@ SYMBOLS = [
     "pcdb_abi_version", "pcdb_create", "pcdb_destroy", "pcdb_last_error", "pcdb_default_params", "pcdb_set_params",
     "pcdb_set_stream", "pcdb_set_codebook", "pcdb_voxel_keypoints", "pcdb_radius_neighbours", "pcdb_shot_lrf",
     "pcdb_shot_describe", "pcdb_compute_normals", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
-    "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
+    "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_get_last_sizes", "pcdb_get_maxima", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
     "pcdb_get_stats", "pcdb_reset_stats", "pcdb_comm_unique_id", "pcdb_comm_init", "pcdb_comm_destroy", "pcdb_comm_info",
     "pcdb_set_codebook_sharded", "pcdb_comm_shard_keypoints", "pcdb_set_class_dimensions",
 ]
