@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PCDB_ABI_VERSION 3
+#define PCDB_ABI_VERSION 4
 
 typedef enum pcdb_status {
   PCDB_OK = 0,
@@ -51,6 +51,9 @@ enum { PCDB_KNN_AUTO = 0, PCDB_KNN_SCAN = 1, PCDB_KNN_GEMM = 2 }; /* which exact
 enum { PCDB_RADIUS_CONFIG = 0, PCDB_RADIUS_FIRST_DIM = 1, PCDB_RADIUS_SECOND_DIM = 2 };
 /* Voting.SingleObjectMaxType (maxima_handler.h:42-58): Default|None, BandwidthVotes, VotingSpaceVotes, ModelRadiusVotes */
 enum { PCDB_SOMAX_DEFAULT = 0, PCDB_SOMAX_BANDWIDTH = 1, PCDB_SOMAX_VOTING_SPACE = 2, PCDB_SOMAX_MODEL_RADIUS = 3 };
+/* Voting.RansacInlierThresholdType (voting/voting.cpp:50,112-122): the threshold as configured, or times the class'
+ * learned object radius / median bounding-box dimension (pcdb_set_class_dimensions) */
+enum { PCDB_RANSAC_FIXED = 0, PCDB_RANSAC_OBJECT_RADIUS = 1, PCDB_RANSAC_BBOX_MEDIAN = 2 };
 
 #define PCDB_SHOT_DIM 352
 #define PCDB_CSHOT_DIM 1344
@@ -99,6 +102,18 @@ typedef struct pcdb_params {
    * centroid, votes collected within the bandwidth / the model radius / the whole voting space.  Only consulted when
    * single_object_mode != 0; needs the cloud, so the fused entries support it and pcdb_find_maxima does not */
   int32_t single_object_max_type;    /* PCDB_SOMAX_*; Voting.SingleObjectMaxType */
+  /* RANSAC vote filtering of every maximum before it is reduced (voting/voting.cpp:47-50,110-127,356-433): a rigid
+   * transform between the member votes' training keypoints and scene keypoints is fitted by sample consensus (3
+   * correspondences per hypothesis, at most 10000 iterations, PCL's adaptive stop at probability 0.99); only the
+   * inlier votes stay, and a maximum whose fit fails, has fewer than 3 inliers or is the identity (Eigen isIdentity
+   * at 1e-4, as written in the reference) is dropped.  The reference draws its samples from PCL's Boost RNG (seed and
+   * shuffle state are PCL internals); here sample `it` of a maximum is a pure function of (class, ordinal of the
+   * maximum in its class, it) — same model, same stopping rule, a defined and reproducible sequence.
+   * RansacRefineModel = true is rejected (PCDB_E_UNSUPPORTED). */
+  int32_t ransac_vote_filtering;     /* Voting.RansacVoteFiltering */
+  float ransac_inlier_threshold;     /* Voting.RansacInlierThreshold */
+  int32_t ransac_threshold_type;     /* PCDB_RANSAC_*; Voting.RansacInlierThresholdType */
+  int32_t ransac_refine_model;       /* Voting.RansacRefineModel: must be 0 */
 } pcdb_params;
 
 /* One Hough vote — ism3d::Vote, voting/voting_maximum.h:25-42 (80 bytes). */

@@ -1485,6 +1485,232 @@ void quat_average(const std::vector<Quat>& qs, const std::vector<float>& ws, Qua
 }
 
 /* Voting::findMaxima (voting/voting.cpp:79-328) for one cloud */
+/* ---- Voting::filterVotesWithRansac (voting/voting.cpp:356-433) ------------------------------------------------------
+ * pcl::registration::CorrespondenceRejectorSampleConsensus over the member votes of one maximum: source = the votes'
+ * training keypoints, target = their scene keypoints, model = rigid transform from 3 correspondences, RANSAC with
+ * max 10000 iterations, probability 0.99 and PCL's adaptive stop (RandomSampleConsensus::computeModel), sample
+ * goodness by SampleConsensusModelRegistration (pairwise source distances above the PCA-derived threshold, at most
+ * 1000 draws per iteration).  PCL is not available here and its sample sequence comes from a Boost RNG with internal
+ * shuffle state, so the SEQUENCE is defined by this restatement (PARITY UNPINNED for this stage): sample `it` is a
+ * pure function of (key, it, attempt); model fit and residuals are evaluated in double (PCL: float, JacobiSVD).
+ * Returns false when the maximum is to be dropped; `keep` marks the inlier votes otherwise. */
+inline uint32_t ransac_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  uint32_t h = 0x811C9DC5u;
+  const uint32_t v[4] = {a, b, c, d};
+  for (int i = 0; i < 4; ++i) {
+    h ^= v[i];
+    h *= 0x01000193u;
+    h ^= h >> 15;
+  }
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+/* cyclic Jacobi for a symmetric n x n matrix (n <= 4): eigenvalues on the diagonal of A, eigenvectors in the columns of V */
+template <int N>
+void jacobi_sym(double A[N][N], double V[N][N]) {
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < N; ++p)
+      for (int q = p + 1; q < N; ++q) off += std::fabs(A[p][q]);
+    if (off == 0.0) break;
+    for (int p = 0; p < N - 1; ++p)
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (!std::isfinite(theta)) t = 0.0;
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < N; ++k) {
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < N; ++k) {
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        A[p][q] = A[q][p] = 0.0;
+        for (int k = 0; k < N; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+/* rigid transform (R row-major, t) that maps the three source points onto the three target points in the least-squares
+ * sense: Horn's closed form — the rotation is the eigenvector of the largest eigenvalue of the 4 x 4 matrix built from
+ * the cross-covariance (equals the SVD solution PCL's TransformationEstimationSVD returns) */
+void rigid_from_three(const double s[3][3], const double g[3][3], double R[9], double t[3]) {
+  double cs[3], cg[3];
+  for (int a = 0; a < 3; ++a) {
+    cs[a] = ((s[0][a] + s[1][a]) + s[2][a]) / 3.0;
+    cg[a] = ((g[0][a] + g[1][a]) + g[2][a]) / 3.0;
+  }
+  double M[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double acc = 0;
+      for (int k = 0; k < 3; ++k) acc += (s[k][a] - cs[a]) * (g[k][b] - cg[b]);
+      M[a][b] = acc;
+    }
+  double Nm[4][4] = {
+      {(M[0][0] + M[1][1]) + M[2][2], M[1][2] - M[2][1], M[2][0] - M[0][2], M[0][1] - M[1][0]},
+      {0, (M[0][0] - M[1][1]) - M[2][2], M[0][1] + M[1][0], M[2][0] + M[0][2]},
+      {0, 0, (M[1][1] - M[0][0]) - M[2][2], M[1][2] + M[2][1]},
+      {0, 0, 0, (M[2][2] - M[0][0]) - M[1][1]}};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < i; ++j) Nm[i][j] = Nm[j][i];
+  double V[4][4];
+  jacobi_sym<4>(Nm, V);
+  int best = 0;
+  for (int i = 1; i < 4; ++i)
+    if (Nm[i][i] > Nm[best][best]) best = i;
+  double q[4] = {V[0][best], V[1][best], V[2][best], V[3][best]};
+  const double qn = std::sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= qn;
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1.0 - 2.0 * (y * y + z * z);
+  R[1] = 2.0 * (x * y - w * z);
+  R[2] = 2.0 * (x * z + w * y);
+  R[3] = 2.0 * (x * y + w * z);
+  R[4] = 1.0 - 2.0 * (x * x + z * z);
+  R[5] = 2.0 * (y * z - w * x);
+  R[6] = 2.0 * (x * z - w * y);
+  R[7] = 2.0 * (y * z + w * x);
+  R[8] = 1.0 - 2.0 * (x * x + y * y);
+  for (int a = 0; a < 3; ++a) t[a] = cg[a] - ((R[3 * a] * cs[0] + R[3 * a + 1] * cs[1]) + R[3 * a + 2] * cs[2]);
+}
+
+inline double ransac_residual2(const double R[9], const double t[3], const float* s, const float* g) {
+  double d2 = 0;
+  for (int a = 0; a < 3; ++a) {
+    const double p = ((R[3 * a] * (double)s[0] + R[3 * a + 1] * (double)s[1]) + R[3 * a + 2] * (double)s[2]) + t[a];
+    const double d = p - (double)g[a];
+    d2 += d * d;
+  }
+  return d2;
+}
+
+bool ransac_filter_votes(const pcdb_vote* votes, const std::vector<int64_t>& idx, float inlier_threshold, uint32_t key,
+                         std::vector<char>& keep) {
+  const int n = (int)idx.size();
+  keep.assign((size_t)n, 0);
+  if (n < 3) return false;
+  /* SampleConsensusModelRegistration::computeSampleDistanceThreshold: ((sum of sqrt eigenvalues of the source
+   * covariance) / 3)^2 */
+  /* nine moment sums as 256 strided partial sums combined in order (the summation tree of the device kernel) */
+  double tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < 256; ++t) {
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = t; i < n; i += 256) {
+      const float* s = votes[idx[i]].keypoint_training;
+      const double x = s[0], y = s[1], z = s[2];
+      acc[0] += x; acc[1] += y; acc[2] += z;
+      acc[3] += x * x; acc[4] += x * y; acc[5] += x * z; acc[6] += y * y; acc[7] += y * z; acc[8] += z * z;
+    }
+    for (int j = 0; j < 9; ++j) tot[j] += acc[j];
+  }
+  const double inv_n = 1.0 / (double)n;
+  for (int j = 0; j < 9; ++j) tot[j] *= inv_n;
+  double C[3][3] = {{tot[3] - tot[0] * tot[0], tot[4] - tot[0] * tot[1], tot[5] - tot[0] * tot[2]},
+                    {0, tot[6] - tot[1] * tot[1], tot[7] - tot[1] * tot[2]},
+                    {0, 0, tot[8] - tot[2] * tot[2]}};
+  C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
+  double V3[3][3];
+  jacobi_sym<3>(C, V3);
+  double sdt = 0;
+  for (int a = 0; a < 3; ++a) sdt += std::sqrt(C[a][a] > 0 ? C[a][a] : 0.0);
+  sdt /= 3.0;
+  sdt *= sdt;
+  const double thr2 = (double)inlier_threshold * (double)inlier_threshold;
+  const double kLogP = -4.605170185988091;   /* log(1 - 0.99) */
+  const double kEps = 2.220446049250313e-16;
+  double k = 1e300;
+  int best = -1, bs[3] = {0, 0, 0};
+  for (int it = 0; (double)it < k;) {
+    int smp[3] = {-1, -1, -1};
+    for (uint32_t at = 0; at < 1000; ++at) { /* max_sample_checks_ */
+      int i0 = (int)(ransac_hash(key, (uint32_t)it, at, 0) % (uint32_t)n);
+      int i1 = (int)(ransac_hash(key, (uint32_t)it, at, 1) % (uint32_t)(n - 1));
+      if (i1 >= i0) ++i1;
+      int i2 = (int)(ransac_hash(key, (uint32_t)it, at, 2) % (uint32_t)(n - 2));
+      const int lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+      if (i2 >= lo) ++i2;
+      if (i2 >= hi) ++i2;
+      const float* a = votes[idx[i0]].keypoint_training;
+      const float* b = votes[idx[i1]].keypoint_training;
+      const float* c = votes[idx[i2]].keypoint_training;
+      auto d2 = [](const float* p, const float* q) {
+        const double dx = (double)p[0] - (double)q[0], dy = (double)p[1] - (double)q[1], dz = (double)p[2] - (double)q[2];
+        return (dx * dx + dy * dy) + dz * dz;
+      };
+      if (d2(b, a) > sdt && d2(c, a) > sdt && d2(c, b) > sdt) {
+        smp[0] = i0; smp[1] = i1; smp[2] = i2;
+        break;
+      }
+    }
+    if (smp[0] < 0) break; /* no good sample: RandomSampleConsensus stops */
+    double S[3][3], G[3][3], R[9], t[3];
+    for (int j = 0; j < 3; ++j)
+      for (int a = 0; a < 3; ++a) {
+        S[j][a] = votes[idx[smp[j]]].keypoint_training[a];
+        G[j][a] = votes[idx[smp[j]]].keypoint[a];
+      }
+    rigid_from_three(S, G, R, t);
+    int cnt = 0;
+    for (int i = 0; i < n; ++i)
+      if (ransac_residual2(R, t, votes[idx[i]].keypoint_training, votes[idx[i]].keypoint) < thr2) ++cnt;
+    if (cnt > best) {
+      best = cnt;
+      bs[0] = smp[0]; bs[1] = smp[1]; bs[2] = smp[2];
+      const double w = (double)best * inv_n;
+      double p_no = 1.0 - (w * w) * w;
+      p_no = p_no > kEps ? p_no : kEps;
+      p_no = p_no < 1.0 - kEps ? p_no : 1.0 - kEps;
+      k = kLogP / std::log(p_no);
+    }
+    ++it;
+    if (it > 10000) break;
+  }
+  if (best < 3) return false; /* no model, or fewer than 3 inliers: best_transformation_ stays the identity */
+  double S[3][3], G[3][3], R[9], t[3];
+  for (int j = 0; j < 3; ++j)
+    for (int a = 0; a < 3; ++a) {
+      S[j][a] = votes[idx[bs[j]]].keypoint_training[a];
+      G[j][a] = votes[idx[bs[j]]].keypoint[a];
+    }
+  rigid_from_three(S, G, R, t);
+  /* Eigen::Matrix4f::isIdentity(1e-4): diagonal isApprox(1), everything else isMuchSmallerThan(1) */
+  bool identity = true;
+  for (int a = 0; a < 3 && identity; ++a) {
+    for (int b = 0; b < 3; ++b) {
+      const float m = (float)R[3 * a + b];
+      if (a == b) {
+        const float am = std::fabs(m);
+        if (!(std::fabs(m - 1.0f) <= (am < 1.0f ? am : 1.0f) * 1e-4f)) identity = false;
+      } else if (!(std::fabs(m) <= 1e-4f)) {
+        identity = false;
+      }
+    }
+    if (!(std::fabs((float)t[a]) <= 1e-4f)) identity = false;
+  }
+  if (identity) return false;
+  for (int i = 0; i < n; ++i)
+    keep[(size_t)i] = ransac_residual2(R, t, votes[idx[i]].keypoint_training, votes[idx[i]].keypoint) < thr2 ? 1 : 0;
+  return true;
+}
+
 struct ClassDims {
   const std::vector<float>* first;
   const std::vector<float>* second;
@@ -1555,6 +1781,33 @@ void find_maxima_cloud(const pcdb_params& P, const ClassDims& dims, const float*
         m_bandwidth = std::sqrt(mx);
       }
       ms_single_maximum(P, m_bandwidth, cv, centre, maxima, members, mw);
+    }
+    if (P.ransac_vote_filtering) { /* voting.cpp:110-127: before the maxima are reduced; dropped maxima vanish */
+      float thr = P.ransac_inlier_threshold;
+      if (P.ransac_threshold_type == PCDB_RANSAC_OBJECT_RADIUS && kv.first < d1.size()) thr *= d1[kv.first];
+      if (P.ransac_threshold_type == PCDB_RANSAC_BBOX_MEDIAN && kv.first < d2.size()) thr *= d2[kv.first];
+      for (size_t i = 0; i < maxima.size(); ++i) {
+        std::vector<int>& mem = members[i];
+        if ((int)mem.size() < P.min_votes_threshold || mem.empty()) { /* voting.cpp:373: not even tried */
+          mem.clear();
+          mw[i].clear();
+          continue;
+        }
+        std::vector<int64_t> gi(mem.size());
+        for (size_t t = 0; t < mem.size(); ++t) gi[t] = cv.gidx[mem[t]];
+        std::vector<char> keep;
+        const bool ok = ransac_filter_votes(votes, gi, thr, kv.first * 65536u + (uint32_t)i, keep);
+        std::vector<int> m2;
+        std::vector<float> w2;
+        if (ok)
+          for (size_t t = 0; t < mem.size(); ++t)
+            if (keep[t]) {
+              m2.push_back(mem[t]);
+              w2.push_back(mw[i][t]);
+            }
+        mem.swap(m2);
+        mw[i].swap(w2);
+      }
     }
     for (size_t i = 0; i < maxima.size(); ++i) {
       const std::vector<int>& mem = members[i];
@@ -1929,6 +2182,10 @@ void orc_default_params(pcdb_params* p) {
   p->radius_type = PCDB_RADIUS_CONFIG;
   p->radius_factor = 1.0f;
   p->single_object_max_type = PCDB_SOMAX_DEFAULT;
+  p->ransac_vote_filtering = 0;
+  p->ransac_inlier_threshold = 0.1f;
+  p->ransac_threshold_type = PCDB_RANSAC_FIXED;
+  p->ransac_refine_model = 0;
 }
 
 int orc_voxel_keypoints(const float* xyz, const uint32_t* rgb, const int64_t* cloud_off, int32_t B, float leaf,

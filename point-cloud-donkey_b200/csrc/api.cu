@@ -93,6 +93,13 @@ int check_params(pcdb_ctx* ctx, const pcdb_params& p) {
     return ctx->fail(PCDB_E_INVALID, "invalid Voting.SingleObjectMaxType %d", p.single_object_max_type);
   if (p.max_filter_type < PCDB_MAXFILTER_NONE || p.max_filter_type > PCDB_MAXFILTER_MERGE)
     return ctx->fail(PCDB_E_INVALID, "invalid Voting.MaxFilterType %d", p.max_filter_type);
+  if (p.ransac_vote_filtering) {
+    if (p.ransac_threshold_type < PCDB_RANSAC_FIXED || p.ransac_threshold_type > PCDB_RANSAC_BBOX_MEDIAN)
+      return ctx->fail(PCDB_E_INVALID, "invalid Voting.RansacInlierThresholdType %d", p.ransac_threshold_type);
+    if (!(p.ransac_inlier_threshold > 0.f)) return ctx->fail(PCDB_E_INVALID, "Voting.RansacInlierThreshold must be positive");
+    if (p.ransac_refine_model)
+      return ctx->fail(PCDB_E_UNSUPPORTED, "Voting.RansacRefineModel = true is not built (voting.cpp:363)");
+  }
   return PCDB_OK;
 }
 
@@ -594,6 +601,10 @@ void pcdb_default_params(pcdb_params* p) {
   p->radius_type = PCDB_RADIUS_CONFIG;
   p->radius_factor = 1.0f;
   p->single_object_max_type = PCDB_SOMAX_DEFAULT;
+  p->ransac_vote_filtering = 0;
+  p->ransac_inlier_threshold = 0.1f;
+  p->ransac_threshold_type = PCDB_RANSAC_FIXED;
+  p->ransac_refine_model = 0;
 }
 
 int pcdb_create(pcdb_ctx** out, int device) {

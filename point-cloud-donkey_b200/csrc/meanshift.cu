@@ -1130,6 +1130,11 @@ int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, bool have_cloud, int64_t*
                                      w.mem_off.as<int>(), P, w.vote_w_work.as<float>(), w.mem_idx.as<long long>(),
                                      w.mem_w.as<float>());
   PCDB_LAUNCH_CHECK();
+  if (p.ransac_vote_filtering && hM > 0) {  // voting.cpp:110-127: only the inlier votes of every maximum go on
+    int64_t mem_io = hMem;
+    PCDB_TRY(stage_ransac_filter(ctx, hM, M_ptr, &mem_io));
+    hMem = (int)mem_io;
+  }
   if (hM > 0) {
     k_max_reduce<<<cdiv((int64_t)hM * 32, 128), 128, 0, st>>>(M_ptr, w.mpos.as<float4>(), w.mseg.as<int>(),
                                                               w.seg2_key.as<unsigned>(), w.mem_off.as<int>(),

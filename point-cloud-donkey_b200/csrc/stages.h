@@ -45,6 +45,10 @@ int stage_votes_unpack(pcdb_ctx* ctx, int B, int64_t V);
 // have_cloud: ws.surf4 / ws.surf_off hold the clouds the votes came from (fused path) — the single-object max types need it
 int stage_find_maxima(pcdb_ctx* ctx, int B, int64_t V, bool have_cloud, int64_t* M_out, int64_t* members_out);  // syncs
 
+// ransac.cu: Voting.RansacVoteFiltering — replaces ws.mem_idx / mem_w / mem_off by the inlier votes of the surviving
+// maxima (M_ptr: device count of maxima, hM its host copy); syncs
+int stage_ransac_filter(pcdb_ctx* ctx, int64_t hM, const int* M_ptr, int64_t* hMem_io);
+
 // api.cu: exact kNN of device-resident queries against this context's descriptor rows (GEMM or scan by `mode`)
 int pcdb_run_knn(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, int mode, bool use_ratio,
                  float ratio_thr);

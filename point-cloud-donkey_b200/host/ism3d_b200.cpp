@@ -309,8 +309,16 @@ void ImplicitShapeModel::configFromJson(const jsonmin::Value& oc) {
   if (vr.boolean("UseGlobalFeatures", false))
     outside.push_back("Voting.UseGlobalFeatures=true (global-descriptor classifiers: GlobalFeatures child, SVM / KNN merge of "
                       "global and local hypotheses, voting.cpp:217-300)");
-  if (vo["Parameters"].isMember("RansacVoteFiltering") && vr.boolean("RansacVoteFiltering", false))
-    outside.push_back("Voting.RansacVoteFiltering=true (PCL's CorrespondenceRejectorSampleConsensus, voting.cpp:356-433)");
+  // Voting::filterVotesWithRansac (voting.cpp:47-50,110-127,356-433)
+  P.ransac_vote_filtering = vr.boolean("RansacVoteFiltering", false);
+  P.ransac_refine_model = vr.boolean("RansacRefineModel", false);
+  P.ransac_inlier_threshold = (float)vr.num("RansacInlierThreshold", 0.1);
+  const std::string rth = vr.str("RansacInlierThresholdType", "Fixed");
+  if (rth == "ObjectRadius") P.ransac_threshold_type = PCDB_RANSAC_OBJECT_RADIUS;
+  else if (rth == "BoundingBoxMedian") P.ransac_threshold_type = PCDB_RANSAC_BBOX_MEDIAN;
+  else P.ransac_threshold_type = PCDB_RANSAC_FIXED;  // voting.cpp:112-122: anything else keeps the configured value
+  if (P.ransac_vote_filtering && P.ransac_refine_model)
+    outside.push_back("Voting.RansacRefineModel=true (PCL's SampleConsensus::refineModel, voting.cpp:363)");
   if (!outside.empty()) {
     std::string msg = "this configuration asks for parts of the reference outside the built hot path; set them to false: ";
     for (size_t i = 0; i < outside.size(); ++i) msg += (i ? "; " : "") + outside[i];

@@ -11,6 +11,7 @@ MAXFILTER_NONE, MAXFILTER_SIMPLE, MAXFILTER_MERGE = 0, 1, 2
 KNN_AUTO, KNN_SCAN, KNN_GEMM = 0, 1, 2
 RADIUS_CONFIG, RADIUS_FIRST_DIM, RADIUS_SECOND_DIM = 0, 1, 2
 SOMAX_DEFAULT, SOMAX_BANDWIDTH, SOMAX_VOTING_SPACE, SOMAX_MODEL_RADIUS = 0, 1, 2, 3
+RANSAC_FIXED, RANSAC_OBJECT_RADIUS, RANSAC_BBOX_MEDIAN = 0, 1, 2
 SHOT_DIM, CSHOT_DIM, MAX_K = 352, 1344, 16
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_STATE, E_UNSUPPORTED, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
@@ -49,6 +50,10 @@ class Params(C.Structure):
         ("radius_type", C.c_int32),
         ("radius_factor", C.c_float),
         ("single_object_max_type", C.c_int32),
+        ("ransac_vote_filtering", C.c_int32),
+        ("ransac_inlier_threshold", C.c_float),
+        ("ransac_threshold_type", C.c_int32),
+        ("ransac_refine_model", C.c_int32),
     ]
 
     @property
@@ -88,6 +93,10 @@ def default_params(**kw):
     p.radius_type = RADIUS_CONFIG
     p.radius_factor = 1.0
     p.single_object_max_type = SOMAX_DEFAULT
+    p.ransac_vote_filtering = 0
+    p.ransac_inlier_threshold = 0.1
+    p.ransac_threshold_type = RANSAC_FIXED
+    p.ransac_refine_model = 0
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)

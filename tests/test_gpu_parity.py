@@ -655,6 +655,44 @@ def test_find_maxima_radius_types_and_cross_class_filters(api, orc, radius_type,
     c.close()
 
 
+@pytest.mark.parametrize("thr_type", [0, 1, 2])
+def test_find_maxima_ransac_vote_filtering(api, orc, thr_type):
+    """Voting.RansacVoteFiltering (voting.cpp:110-127,356-433): same surviving maxima and the same inlier votes as the
+    oracle (the sample sequence is a pure function of (class, maximum, iteration) on both sides; residuals in fp64
+    without FMA contraction), incl. the per-class threshold types and maxima that the fit drops."""
+    from test_oracle import _ransac_votes
+    rng = np.random.default_rng(40 + thr_type)
+    clouds = []
+    for b in range(4):
+        parts = [_ransac_votes(rng, 70 + 10 * b, 50, (0, 0, 0), 0, noise=0.003),
+                 _ransac_votes(rng, 40, 25, (2, 0.5, 0), 1, noise=0.003),
+                 _ransac_votes(rng, 30, 0, (0, 3, 0), 1, R=np.eye(3), t=np.zeros(3)),   # identity: dropped
+                 _ransac_votes(rng, 0, 35, (-3, 0, 1), 2),                              # no consensus
+                 _ransac_votes(rng, 400, 300, (5, 5, 5), 3, noise=0.003)]
+        v = np.concatenate(parts)
+        rng.shuffle(v)
+        clouds.append(v)
+    clouds.insert(1, clouds[0][:0])
+    votes = np.concatenate(clouds)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64)
+    prm = default_params(bandwidth=0.3, single_object_mode=0, min_votes_threshold=5, average_rotation=1,
+                         ransac_vote_filtering=1, ransac_inlier_threshold=0.03, ransac_threshold_type=thr_type)
+    first, second = [1.0, 0.8, 1.2, 1.0], [0.9, 1.1, 1.0, 1.3]
+    cb = _dummy_codebook(np.zeros((4, 352), np.float32), n_classes=4)
+    c = api.Context(prm, cb)
+    c.set_class_dimensions(first, second)
+    m = orc.Model(prm, cb)
+    m.set_class_dimensions(first, second)
+    a, b = c.find_maxima(votes, off), m.find_maxima(votes, off)
+    _compare_maxima(a, b)
+    big = a[0][a[0]["n_votes"] >= 20]
+    assert set(big["class_id"].tolist()) == {0, 1, 3}   # the identity-pose and the no-consensus maxima are gone
+    prm.ransac_refine_model = 1
+    with pytest.raises(api.PcdbError):
+        c.set_params(prm)
+    c.close()
+
+
 @pytest.mark.parametrize("max_type", [1, 2, 3])
 def test_classify_single_object_max_types(api, orc, small_world, max_type):
     """SingleObjectMode with SingleObjectMaxType BandwidthVotes / VotingSpaceVotes / ModelRadiusVotes

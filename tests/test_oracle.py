@@ -569,6 +569,60 @@ def test_cross_class_merge_filter_known_answer(orc):
     assert sorted(zip(mx["class_id"].tolist(), mx["n_votes"].tolist())) == [(0, 50), (1, 10)]
 
 
+def _ransac_votes(rng, n_in, n_out, centre, cls, R=None, t=None, noise=0.0):
+    """Votes of one maximum: n_in whose scene keypoint is the rigid image R kt + t of the training keypoint (+ noise),
+    n_out whose scene keypoint is unrelated."""
+    v = _votes([centre], n_in + n_out, cls, rng, sigma=0.01)
+    kt = rng.uniform(-0.5, 0.5, size=(n_in + n_out, 3))
+    if R is None:
+        ang = 0.7
+        R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    if t is None:
+        t = np.array([0.3, -0.2, 0.1])
+    ks = kt @ R.T + t + rng.normal(scale=noise, size=kt.shape) if noise > 0 else kt @ R.T + t
+    ks[n_in:] = rng.uniform(-2, 2, size=(n_out, 3))
+    v["keypoint_training"] = kt.astype(np.float32)
+    v["keypoint"] = ks.astype(np.float32)
+    return v
+
+
+def test_ransac_vote_filtering_known_answer(orc):
+    """Voting.RansacVoteFiltering (voting.cpp:110-127,356-433): only the votes whose (training keypoint -> scene
+    keypoint) correspondence agrees with the dominant rigid transform stay in the maximum; a maximum whose transform is
+    the identity, or that has no consistent transform at all, is dropped (as written in the reference)."""
+    from pcdb200.structs import Codebook, default_params
+    rng = np.random.default_rng(11)
+    a = _ransac_votes(rng, 60, 40, (0, 0, 0), 0, noise=0.002)            # 60 % inliers
+    b = _ransac_votes(rng, 50, 0, (3, 0, 0), 1, R=np.eye(3), t=np.zeros(3))  # identity transform: dropped
+    c = _ransac_votes(rng, 0, 30, (0, 3, 0), 1)                          # no consistent transform
+    votes = np.concatenate([a, b, c])
+    off = np.array([0, len(votes)], np.int64)
+    W = np.zeros((2, 352), np.float32)
+    cb = Codebook(W, np.arange(3), np.zeros((2, 3)), np.ones(2), np.zeros(2), np.zeros(2), np.zeros((2, 7)), np.ones(2),
+                  np.zeros((2, 3)), np.arange(2), np.ones(2))
+    prm = default_params(bandwidth=0.3, single_object_mode=0, min_votes_threshold=4)
+    m = orc.Model(prm, cb)
+    assert sorted(m.find_maxima(votes, off)[0]["n_votes"].tolist()) == [30, 50, 100]
+    prm.ransac_vote_filtering = 1
+    prm.ransac_inlier_threshold = 0.02
+    m.set_params(prm)
+    mx, moff, mi, mw = m.find_maxima(votes, off)
+    # the random maximum c may keep a few accidental inliers of its best 3-point fit, never a real consensus
+    big = mx[mx["n_votes"] >= 10]
+    assert len(big) == 1 and big["class_id"][0] == 0 and big["n_votes"][0] == 60
+    members = mi[big["vote_begin"][0]:big["vote_begin"][0] + 60]
+    assert sorted(members.tolist()) == list(range(60))            # exactly the inlier votes
+    assert np.isclose(big["raw_weight"][0], mw[big["vote_begin"][0]:big["vote_begin"][0] + 60].sum(), rtol=1e-5)
+    assert not np.any((mx["class_id"] == 1) & (mx["n_votes"] >= 40))  # the identity-pose maximum is gone
+    # per-class threshold types scale the threshold by the learned class dimension (voting.cpp:112-122)
+    prm.ransac_threshold_type = 1
+    prm.ransac_inlier_threshold = 0.04
+    m.set_params(prm)
+    m.set_class_dimensions([0.5, 1.0], [2.0, 1.0])   # 0.04 * 0.5 = the same 0.02 for class 0
+    mx2 = m.find_maxima(votes, off)[0]
+    assert mx2[mx2["n_votes"] >= 10]["n_votes"].tolist() == [60]
+
+
 def test_single_object_max_types_known_answer(orc, small_world):
     """SingleObjectMaxType VotingSpaceVotes collects every vote of a class at the centroid; ModelRadiusVotes those
     within the farthest point's distance; BandwidthVotes those within Voting.Bandwidth."""
