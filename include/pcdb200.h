@@ -211,6 +211,12 @@ int pcdb_shot_describe(pcdb_ctx* ctx, int32_t feature_type, const float* surf_xy
  * they are called with normals == NULL (the reference's hasNormals == false path). */
 int pcdb_compute_normals(pcdb_ctx* ctx, const float* xyz, const int64_t* cloud_off, int32_t B, float* normals_out,
                          float* curvature_out);
+/* The organized branch of ImplicitShapeModel::computeNormals (implicit_shape_model.cpp:948-966), taken by the reference
+ * when a cloud isOrganized() (PCD HEIGHT > 1, Kinect-style grids with NaN holes): pcl::IntegralImageNormalEstimation,
+ * AVERAGE_3D_GRADIENT, MaxDepthChangeFactor 0.02, NormalSmoothingSize 10, normals flipped towards the sensor origin.
+ * xyz and normals_out: height x width x 3, row-major; normals are NaN where PCL leaves them NaN (image border of 10
+ * pixels, holes, depth discontinuities). */
+int pcdb_compute_normals_organized(pcdb_ctx* ctx, const float* xyz, int32_t width, int32_t height, float* normals_out);
 
 /* Features::operator() + removeNaNFeatures (features/features.cpp:40-116, implicit_shape_model.cpp:1276-1308):
  * keypoints -> LRF -> drop invalid -> descriptor -> drop NaN; uses the context's params.  Outputs are the

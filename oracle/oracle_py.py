@@ -120,6 +120,16 @@ def compute_normals(prm, xyz, cloud_off):
     return nrm, curv
 
 
+def compute_normals_organized(xyz_hw3):
+    """ImplicitShapeModel::computeNormals for an organized cloud (height x width x 3): IntegralImageNormalEstimation,
+    AVERAGE_3D_GRADIENT, depth-change factor 0.02, smoothing size 10, normals towards the sensor origin."""
+    xyz = f32(xyz_hw3)
+    h, w = xyz.shape[0], xyz.shape[1]
+    nrm = np.empty((h, w, 3), np.float32)
+    _check(lib().orc_compute_normals_organized(ptr(xyz, F), w, h, ptr(nrm, F)))
+    return nrm
+
+
 def compute_features(prm, xyz, normals, rgb, cloud_off):
     xyz, normals, rgb, cloud_off = f32(xyz), f32(normals), u32(rgb), i64(cloud_off)
     B = len(cloud_off) - 1

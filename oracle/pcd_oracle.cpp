@@ -2296,6 +2296,125 @@ int orc_compute_normals(const pcdb_params* prm, const float* xyz, const int64_t*
   return PCDB_OK;
 }
 
+/* ImplicitShapeModel::computeNormals, organized branch (implicit_shape_model.cpp:948-966):
+ * pcl::IntegralImageNormalEstimation, AVERAGE_3D_GRADIENT, MaxDepthChangeFactor 0.02, NormalSmoothingSize 10, border
+ * policy IGNORE, no depth-dependent smoothing, viewpoint = sensor origin (0,0,0).  Restated from PCL's published
+ * algorithm (features/integral_image_normal.hpp, integral_image2D.hpp) — PARITY UNPINNED (no PCL here):
+ *   1. 3D gradients: dx = right - left, dy = down - up for the interior pixels, 0 on the image border;
+ *   2. integral images of both (fp64 sums, non-finite gradients skipped and counted out);
+ *   3. depth-change map (|dz| to the right / lower neighbour > 0.02 (|z| + 1) 2, or a non-finite depth) -> chamfer
+ *      distance transform (1 / 1.4 weights, two raster passes over the flat array exactly as PCL indexes it);
+ *   4. per pixel at least 10 inside the image: s = min(distance, 10); s <= 2 -> NaN; else box sums of both gradients
+ *      over an int(s) x int(s) rectangle, normal = gy x gx normalised, flipped towards the viewpoint.
+ * xyz: height x width x 3 row-major; normals_out the same shape (NaN where PCL yields NaN). */
+int orc_compute_normals_organized(const float* xyz, int32_t width, int32_t height, float* normals_out) {
+  const int W = width, H = height;
+  const size_t n = (size_t)W * H;
+  for (size_t i = 0; i < 3 * n; ++i) normals_out[i] = kNaNf;
+  if (W < 3 || H < 3) return PCDB_OK;
+  std::vector<float> dx(3 * n, 0.f), dy(3 * n, 0.f);
+  for (int r = 1; r < H - 1; ++r)
+    for (int c = 1; c < W - 1; ++c) {
+      const size_t i = (size_t)r * W + c;
+      for (int a = 0; a < 3; ++a) {
+        dx[3 * i + a] = xyz[3 * (i + 1) + a] - xyz[3 * (i - 1) + a];
+        dy[3 * i + a] = xyz[3 * (i + W) + a] - xyz[3 * (i - W) + a];
+      }
+    }
+  /* integral images, (W + 1) x (H + 1), IntegralImage2D<float, 3>::computeIntegralImages */
+  const size_t IW = (size_t)W + 1;
+  std::vector<double> Ix(3 * IW * (H + 1), 0.0), Iy(3 * IW * (H + 1), 0.0);
+  std::vector<unsigned> Cx(IW * (H + 1), 0u), Cy(IW * (H + 1), 0u);
+  auto integrate = [&](const std::vector<float>& d, std::vector<double>& I, std::vector<unsigned>& Cn) {
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < W; ++c) {
+        const size_t cur = (size_t)(r + 1) * IW + (c + 1), up = (size_t)r * IW + (c + 1), lf = (size_t)(r + 1) * IW + c,
+                     ul = (size_t)r * IW + c;
+        for (int a = 0; a < 3; ++a) I[3 * cur + a] = I[3 * up + a] + I[3 * lf + a] - I[3 * ul + a];
+        Cn[cur] = Cn[up] + Cn[lf] - Cn[ul];
+        const float* e = &d[3 * ((size_t)r * W + c)];
+        if (std::isfinite(e[0] + e[1] + e[2])) {
+          for (int a = 0; a < 3; ++a) I[3 * cur + a] += (double)e[a];
+          ++Cn[cur];
+        }
+      }
+  };
+  integrate(dx, Ix, Cx);
+  integrate(dy, Iy, Cy);
+  /* depth-change map and chamfer distance transform */
+  std::vector<unsigned char> change(n, 255);
+  for (int r = 0; r < H - 1; ++r)
+    for (int c = 0; c < W - 1; ++c) {
+      const size_t i = (size_t)r * W + c;
+      const float depth = xyz[3 * i + 2], depthR = xyz[3 * (i + 1) + 2], depthD = xyz[3 * (i + W) + 2];
+      const float lim = (0.02f * (std::fabs(depth) + 1.0f) * 2.0f);
+      if (std::fabs(depth - depthR) > lim || !std::isfinite(depth) || !std::isfinite(depthR)) {
+        change[i] = 0;
+        change[i + 1] = 0;
+      }
+      if (std::fabs(depth - depthD) > lim || !std::isfinite(depth) || !std::isfinite(depthD)) {
+        change[i] = 0;
+        change[i + W] = 0;
+      }
+    }
+  std::vector<float> dist(n);
+  for (size_t i = 0; i < n; ++i) dist[i] = change[i] == 0 ? 0.0f : static_cast<float>(W + H);
+  for (int r = 1; r < H; ++r) {
+    float* prev = &dist[(size_t)(r - 1) * W];
+    float* cur = &dist[(size_t)r * W];
+    for (int c = 1; c < W; ++c) {
+      const float upLeft = prev[c - 1] + 1.4f, up = prev[c] + 1.0f, upRight = prev[c + 1] + 1.4f; /* prev[W] = cur[0] */
+      const float left = cur[c - 1] + 1.0f, center = cur[c];
+      const float mn = std::min(std::min(upLeft, up), std::min(left, upRight));
+      if (mn < center) cur[c] = mn;
+    }
+  }
+  for (int r = H - 2; r >= 0; --r) {
+    float* next = &dist[(size_t)(r + 1) * W];
+    float* cur = &dist[(size_t)r * W];
+    for (int c = W - 2; c >= 0; --c) {
+      const float lowerLeft = next[c - 1] + 1.4f, lower = next[c] + 1.0f, lowerRight = next[c + 1] + 1.4f; /* next[-1] = cur[W-1] */
+      const float right = cur[c + 1] + 1.0f, center = cur[c];
+      const float mn = std::min(std::min(lowerLeft, lower), std::min(right, lowerRight));
+      if (mn < center) cur[c] = mn;
+    }
+  }
+  const int border = 10; /* int(normal_smoothing_size_) */
+  for (int r = border; r < H - border; ++r)
+    for (int c = border; c < W - border; ++c) {
+      const size_t i = (size_t)r * W + c;
+      if (!std::isfinite(xyz[3 * i + 2])) continue;
+      const float smoothing = std::min(dist[i], 10.0f);
+      if (!(smoothing > 2.0f)) continue;
+      const int rw = static_cast<int>(smoothing), rh = rw;
+      const int sx = c - rw / 2, sy = r - rh / 2;
+      const size_t ul = (size_t)sy * IW + sx, ur = ul + rw, ll = (size_t)(sy + rh) * IW + sx, lr = ll + rw;
+      const unsigned cx = Cx[lr] + Cx[ul] - Cx[ur] - Cx[ll], cy = Cy[lr] + Cy[ul] - Cy[ur] - Cy[ll];
+      if (cx == 0 || cy == 0) continue;
+      double gx[3], gy[3];
+      for (int a = 0; a < 3; ++a) {
+        gx[a] = Ix[3 * lr + a] + Ix[3 * ul + a] - Ix[3 * ur + a] - Ix[3 * ll + a];
+        gy[a] = Iy[3 * lr + a] + Iy[3 * ul + a] - Iy[3 * ur + a] - Iy[3 * ll + a];
+      }
+      double nv[3] = {gy[1] * gx[2] - gy[2] * gx[1], gy[2] * gx[0] - gy[0] * gx[2], gy[0] * gx[1] - gy[1] * gx[0]};
+      const double len2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+      if (len2 == 0.0) continue;
+      const double len = std::sqrt(len2);
+      float nx = static_cast<float>(nv[0] / len), ny = static_cast<float>(nv[1] / len), nz = static_cast<float>(nv[2] / len);
+      /* pcl::flipNormalTowardsViewpoint with the viewpoint at the sensor origin */
+      const float vx = 0.f - xyz[3 * i], vy = 0.f - xyz[3 * i + 1], vz = 0.f - xyz[3 * i + 2];
+      if (vx * nx + vy * ny + vz * nz < 0) {
+        nx *= -1;
+        ny *= -1;
+        nz *= -1;
+      }
+      normals_out[3 * i] = nx;
+      normals_out[3 * i + 1] = ny;
+      normals_out[3 * i + 2] = nz;
+    }
+  return PCDB_OK;
+}
+
 int orc_compute_features(const pcdb_params* prm, const float* xyz, const float* normals, const uint32_t* rgb,
                          const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
                          float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity) {

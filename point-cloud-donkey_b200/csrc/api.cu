@@ -875,6 +875,21 @@ int pcdb_compute_normals(pcdb_ctx* ctx, const float* xyz, const int64_t* cloud_o
   return PCDB_OK;
 }
 
+int pcdb_compute_normals_organized(pcdb_ctx* ctx, const float* xyz, int32_t width, int32_t height, float* normals_out) {
+  if (!ctx) return PCDB_E_INVALID;
+  PCDB_CUDA(cudaSetDevice(ctx->device));
+  if (width < 0 || height < 0 || (int64_t)width * height > 0x7fffff00ll)
+    return ctx->fail(PCDB_E_INVALID, "bad organized cloud size %d x %d", width, height);
+  if (!xyz || !normals_out) return ctx->fail(PCDB_E_INVALID, "xyz and normals_out are required");
+  Workspace& w = ctx->ws;
+  const int64_t P = (int64_t)width * height;
+  PCDB_TRY(upload(ctx, w.in_xyz, xyz, sizeof(float) * 3 * P));
+  PCDB_TRY(stage_normals_organized(ctx, width, height));
+  PCDB_TRY(download(ctx, normals_out, w.in_nrm.p, sizeof(float) * 3 * P));
+  PCDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PCDB_OK;
+}
+
 int pcdb_compute_features(pcdb_ctx* ctx, const float* xyz, const float* normals, const uint32_t* rgb,
                           const int64_t* cloud_off, int32_t B, float* feat_xyz_out, float* feat_lrf9_out,
                           float* feat_desc_out, int64_t* feat_off_out, int64_t feat_capacity) {

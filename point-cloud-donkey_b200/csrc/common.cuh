@@ -97,7 +97,7 @@ struct Codebook_d {
   X(max_raw) X(max_sorted) X(max_kept) X(max_first) X(labels) X(nbr_cnt) \
   X(nbr_off) X(nbr_key) X(nbr_key2) X(merge_a) X(merge_b) X(nrm_pca) \
   X(nrm_cen) X(nrm_inv) X(nrm_curv) X(max_flag) X(shot_glist) X(item_beg) X(item_len) X(feat_kp) X(vote_feat) \
-  X(item_next) X(rs_mul) X(rs_keep) X(rs_cnt) X(mem_off2) X(ms_grp) X(ms_close) X(ms_src_dst) X(ms_cls_h) X(ms_cloud_cm) X(mem_idx2) X(mem_w2)
+  X(item_next) X(org_ch) X(org_int) X(org_dist) X(rs_mul) X(rs_keep) X(rs_cnt) X(mem_off2) X(ms_grp) X(ms_close) X(ms_src_dst) X(ms_cls_h) X(ms_cloud_cm) X(mem_idx2) X(mem_w2)
 struct Workspace {
 #define X(n) DevBuf n;
   PCDB_WS_FIELDS(X)

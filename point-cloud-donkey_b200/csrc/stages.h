@@ -12,6 +12,9 @@ int stage_grid(pcdb_ctx* ctx, int B, int64_t n_surf, int64_t Q, bool color);
 // normals.cu: ws.in_xyz -> ws.in_nrm (and optionally the curvature) for clouds without normals; syncs
 int stage_normals(pcdb_ctx* ctx, int B, int64_t P, float* curv_out_d);
 
+// normals_organized.cu: ws.in_xyz (H x W x 3) -> ws.in_nrm, the organized branch of computeNormals
+int stage_normals_organized(pcdb_ctx* ctx, int W, int H);
+
 // shot.cu
 size_t shot_smem_bytes(bool color);
 int stage_shot(pcdb_ctx* ctx, int64_t n_surf, int64_t Q, bool color, double r_lrf, double r_shot, bool do_lrf,

@@ -118,7 +118,11 @@ struct Cloud {  // pcl::PointCloud<pcl::PointXYZRGBNormal> as flat arrays
   std::vector<float> xyz, normals;
   std::vector<uint32_t> rgb;
   bool has_normals = false, has_rgb = false;
+  // pcl::PointCloud::width / height: height > 1 = an organized cloud (isOrganized(), a PCD with HEIGHT > 1);
+  // 0 x 0 = unorganized / unknown
+  size_t width = 0, height = 0;
   size_t size() const { return rgb.size(); }
+  bool organized() const { return height > 1 && width * height == size(); }
 };
 
 // LZF decompression (the stream format of liblzf 3.6): a control byte < 32 starts a literal run of ctrl+1 bytes,
@@ -200,6 +204,8 @@ inline bool load_pcd(const std::string& path, Cloud& out, std::string& err) {
   const int inx = idx_of("normal_x"), iny = idx_of("normal_y"), inz = idx_of("normal_z");
   if (ix < 0 || iy < 0 || iz < 0) { err = "PCD file has no x/y/z fields: " + path; return false; }
   out.has_normals = inx >= 0 && iny >= 0 && inz >= 0;
+  out.width = width;
+  out.height = height;
   out.has_rgb = irgb >= 0;
   out.xyz.assign(points * 3, 0.f);
   out.normals.assign(points * 3, 0.f);

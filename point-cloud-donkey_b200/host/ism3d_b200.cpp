@@ -865,7 +865,10 @@ bool ImplicitShapeModel::detectBatch(const std::vector<std::string>& filenames,
         const int64_t o1[2] = {0, (int64_t)c.size()};
         c.normals.assign(c.size() * 3, 0.f);
         const auto t0 = std::chrono::steady_clock::now();
-        check(pcdb_compute_normals(m_ctx, c.xyz.data(), o1, 1, c.normals.data(), nullptr));
+        if (c.organized())  // points->isOrganized(): integral-image normals (implicit_shape_model.cpp:948-966)
+          check(pcdb_compute_normals_organized(m_ctx, c.xyz.data(), (int32_t)c.width, (int32_t)c.height, c.normals.data()));
+        else
+          check(pcdb_compute_normals(m_ctx, c.xyz.data(), o1, 1, c.normals.data(), nullptr));
         m_processing_times["normals"] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       }
       xyz.insert(xyz.end(), c.xyz.begin(), c.xyz.end());
@@ -947,8 +950,16 @@ std::tuple<std::vector<VotingMaximum>, std::map<std::string, double>> ImplicitSh
   int32_t label;
   int64_t moff[2];
   double t[7];
-  check(pcdb_classify_batch(m_ctx, points.xyz.data(), hasNormals ? points.normals.data() : nullptr,
-                            points.has_rgb ? points.rgb.data() : nullptr, off, 1, &label, nullptr, moff, 0, t));
+  std::vector<float> org_normals;
+  const float* normals_in = hasNormals ? points.normals.data() : nullptr;
+  if (!hasNormals && points.organized()) {  // isOrganized(): integral-image normals (implicit_shape_model.cpp:948-966)
+    org_normals.assign(points.size() * 3, 0.f);
+    check(pcdb_compute_normals_organized(m_ctx, points.xyz.data(), (int32_t)points.width, (int32_t)points.height,
+                                         org_normals.data()));
+    normals_in = org_normals.data();
+  }
+  check(pcdb_classify_batch(m_ctx, points.xyz.data(), normals_in, points.has_rgb ? points.rgb.data() : nullptr, off, 1,
+                            &label, nullptr, moff, 0, t));
   int64_t n_max = 0;
   check(pcdb_get_last_sizes(m_ctx, nullptr, &n_max, nullptr));
   std::vector<pcdb_maximum> mx((size_t)std::max<int64_t>(1, n_max));

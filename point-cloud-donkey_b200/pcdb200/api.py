@@ -21,7 +21,7 @@ SYMBOLS = [
     "pcdb_abi_version", "pcdb_create", "pcdb_destroy", "pcdb_last_error", "pcdb_default_params", "pcdb_set_params",
     "pcdb_set_stream", "pcdb_set_codebook", "pcdb_voxel_keypoints", "pcdb_radius_neighbours", "pcdb_shot_lrf",
     "pcdb_shot_describe", "pcdb_compute_normals", "pcdb_compute_features", "pcdb_knn", "pcdb_distance_pairs", "pcdb_cast_votes", "pcdb_find_maxima",
-    "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_get_last_sizes", "pcdb_get_maxima", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
+    "pcdb_get_maximum_votes", "pcdb_get_votes", "pcdb_get_last_sizes", "pcdb_get_maxima", "pcdb_compute_normals_organized", "pcdb_classify_batch", "pcdb_classify_batch_d", "pcdb_merge_topk",
     "pcdb_get_stats", "pcdb_reset_stats", "pcdb_comm_unique_id", "pcdb_comm_init", "pcdb_comm_destroy", "pcdb_comm_info",
     "pcdb_set_codebook_sharded", "pcdb_comm_shard_keypoints", "pcdb_set_class_dimensions",
 ]
@@ -189,6 +189,15 @@ class Context:
         self._check(lib().pcdb_compute_normals(self.h, ptr(xyz, F), ptr(cloud_off, I64), len(cloud_off) - 1,
                                                ptr(nrm, F), ptr(curv, F)))
         return nrm, curv
+
+    def compute_normals_organized(self, xyz_hw3):
+        """Organized branch of ImplicitShapeModel::computeNormals: (height, width, 3) points -> (height, width, 3)
+        normals (IntegralImageNormalEstimation, AVERAGE_3D_GRADIENT)."""
+        xyz = f32(xyz_hw3)
+        h, w = xyz.shape[0], xyz.shape[1]
+        nrm = np.empty((h, w, 3), np.float32)
+        self._check(lib().pcdb_compute_normals_organized(self.h, ptr(xyz, F), w, h, ptr(nrm, F)))
+        return nrm
 
     def compute_features(self, xyz, normals, rgb, cloud_off):
         xyz, normals, rgb, cloud_off = f32(xyz), f32(normals), u32(rgb), i64(cloud_off)

@@ -655,6 +655,41 @@ def test_find_maxima_radius_types_and_cross_class_filters(api, orc, radius_type,
     c.close()
 
 
+def _depth_image(rng, H, W):
+    """A Kinect-like organized cloud: a tilted background plane, a box in front of it (depth jumps), a ramp, NaN holes."""
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    z = 2.0 + 0.0015 * u + 0.0008 * v
+    z[H // 4:H // 2, W // 3:2 * W // 3] = 1.2 + 0.0005 * u[H // 4:H // 2, W // 3:2 * W // 3]
+    z[2 * H // 3:, : W // 2] -= 0.004 * (u[2 * H // 3:, : W // 2])
+    z += rng.normal(scale=2e-4, size=z.shape)
+    x = (u - W / 2) * z / 525.0
+    y = (v - H / 2) * z / 525.0
+    xyz = np.stack([x, y, z], -1).astype(np.float32)
+    holes = rng.random((H, W)) < 0.01
+    xyz[holes] = np.nan
+    xyz[5:9, 40:60] = np.nan
+    return xyz
+
+
+@pytest.mark.parametrize("shape", [(120, 160), (97, 131), (24, 40)])
+def test_organized_normals_match_the_oracle(api, orc, shape):
+    """Organized branch of computeNormals (implicit_shape_model.cpp:948-966, pcl::IntegralImageNormalEstimation
+    AVERAGE_3D_GRADIENT): same NaN pattern (border, holes, depth jumps through the chamfer distance map) and the same
+    normals within 1e-5 (the integral images are fp64 on both sides; summation order differs)."""
+    rng = np.random.default_rng(shape[0])
+    xyz = _depth_image(rng, *shape)
+    c = api.Context(default_params())
+    a = c.compute_normals_organized(xyz)
+    b = orc.compute_normals_organized(xyz)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b[..., 0])
+    assert ok.sum() > 0.3 * ok.size or shape[0] < 30
+    assert np.abs(a[ok] - b[ok]).max() < 1e-5
+    assert np.allclose(np.linalg.norm(a[ok], axis=1), 1.0, atol=1e-5)
+    assert np.all((a[ok] * -np.nan_to_num(xyz[ok])).sum(1) >= 0)   # towards the sensor origin
+    c.close()
+
+
 @pytest.mark.parametrize("thr_type", [0, 1, 2])
 def test_find_maxima_ransac_vote_filtering(api, orc, thr_type):
     """Voting.RansacVoteFiltering (voting.cpp:110-127,356-433): same surviving maxima and the same inlier votes as the

@@ -569,6 +569,28 @@ def test_cross_class_merge_filter_known_answer(orc):
     assert sorted(zip(mx["class_id"].tolist(), mx["n_votes"].tolist())) == [(0, 50), (1, 10)]
 
 
+def test_organized_normals_known_answer(orc):
+    """Integral-image normals of an exactly planar organized cloud are the plane normal, pointing at the sensor; the
+    10-pixel image border, NaN holes and the pixels next to a depth jump stay NaN (PCL's IntegralImageNormalEstimation,
+    AVERAGE_3D_GRADIENT, border policy IGNORE; implicit_shape_model.cpp:948-966)."""
+    H, W = 50, 70
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    nrm = np.array([0.2, -0.1, -1.0]); nrm /= np.linalg.norm(nrm)
+    x, y = (u - W / 2) * 0.01, (v - H / 2) * 0.01
+    z = (1.5 * nrm[2] - nrm[0] * x - nrm[1] * y) / nrm[2]   # plane n . p = 1.5 n_z: z = 1.5 on the optical axis
+    xyz = np.stack([x, y, z], -1).astype(np.float32)
+    n = orc.compute_normals_organized(xyz)
+    inner = n[10:-10, 10:-10]
+    assert np.isnan(n[:10]).all() and np.isnan(n[:, :10]).all() and np.isnan(n[-10:]).all() and np.isnan(n[:, -10:]).all()
+    assert np.allclose(inner, nrm, atol=2e-5)
+    xyz[25, 35] = np.nan
+    xyz[30:, 50:, 2] += 0.5                      # a depth jump
+    n = orc.compute_normals_organized(xyz)
+    assert np.isnan(n[25, 35]).all() and np.isnan(n[24:27, 34:37]).all()
+    assert np.isnan(n[30, 50]).all() and np.isnan(n[29, 49]).all()
+    assert np.allclose(n[15, 15], nrm, atol=2e-5) and np.allclose(n[38, 58], nrm, atol=2e-5)
+
+
 def _ransac_votes(rng, n_in, n_out, centre, cls, R=None, t=None, noise=0.0):
     """Votes of one maximum: n_in whose scene keypoint is the rigid image R kt + t of the training keypoint (+ noise),
     n_out whose scene keypoint is unrelated."""
