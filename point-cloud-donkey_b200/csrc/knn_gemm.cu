@@ -229,17 +229,19 @@ struct GemmArgs {
   int stage_cap;         // entries of one private list: 64 for K <= 4, 128 for K <= 8, 256 beyond (longer staircases)
   // POOL variant (second pass of the chi^2 sandwich): `margin` holds a FIXED per-query threshold on the accumulator
   // (-inf = skip the query) and every column at or below it is appended to one global pool of (query, row) pairs
-  int2* pool_rc;         // (row, accumulator bits)
+  int2* pool_rc;         // (row, unused)
   int* pool_q;
   unsigned long long* pool_count;  // entries wanted so far (may run past pool_cap: the host grows the pool and re-runs)
   long long pool_cap;
   int* q_cnt;            // [Q] pool entries per query (for the CSR the re-rank works on)
+  int q_cap;             // > 0: a query whose pool entries exceed this stops appending (the host re-searches it exactly)
 };
 
 // moves a thread's staged candidates into the global pool: one returning atomic per flush
 __device__ __forceinline__ void pool_flush(const GemmArgs& g, long long row, const int2* stage, int cnt) {
+  const int before = atomicAdd(g.q_cnt + row, cnt);
+  if (g.q_cap > 0 && before > g.q_cap) return;  // hopeless query (PCA pre-filter): flagged from q_cnt afterwards
   const unsigned long long pos = atomicAdd(g.pool_count, (unsigned long long)cnt);
-  atomicAdd(g.q_cnt + row, cnt);
   for (int i = 0; i < cnt; ++i)
     if ((long long)(pos + i) < g.pool_cap) {
       g.pool_rc[pos + i] = stage[i];
@@ -406,6 +408,9 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // bound carried over from the slices already swept for this query (any stale value is still an upper bound)
       const float gb = (active && !POOL) ? __ldcg(g.bound + row) : __int_as_float(0x7f800000);
       float thr = POOL ? margin : gb + margin;
+      // pre-filter pool: a query already past its cap is searched by the plain sweep afterwards — stop collecting for it
+      bool hopeless = false;
+      if (POOL && g.q_cap > 0 && active && __ldcg(g.q_cnt + row) > g.q_cap) thr = __int_as_float(0xff800000);
       // Candidates of this unit are staged in a list private to this thread (plain stores, local counter) and moved
       // to the query's shared list at the end of the unit with ONE atomic reservation: a returning global atomic per
       // append put a ~1 us round trip into the filter loop (C4: 1724 -> 1412 TFLOP/s).
@@ -453,16 +458,35 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     const float mn = fminf(fminf(m16[0], m16[1]), fminf(m16[2], m16[3]));                          \
     if (mn <= thr) {                                                                               \
       const int n_base = t * BN + col0 + (C) * 32;                                                 \
-      _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                             \
-        const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c */                               \
-        if (d <= thr && active && n_base + e < g.N) {                                              \
-          if (POOL) {                                                                              \
-            stage[cnt] = make_int2(n_base + e, __float_as_int(d));                                 \
-            if (++cnt == stage_cap) {                                                              \
-              pool_flush(g, row, stage, cnt);                                                      \
-              cnt = 0;                                                                             \
-            }                                                                                      \
+      if (POOL) {                                                                                  \
+        /* the passing columns as a bit mask (32 independent compares), then one append per set bit: a */ \
+        /* column-by-column scan is ~300 dependent instructions of ONE warp while its 7 siblings and   */ \
+        /* the MMA pipe wait for the accumulator (measured 0.5 ms per pooled row per query at Q = 88 k) */ \
+        unsigned pm = 0;                                                                           \
+        _Pragma("unroll") for (int e = 0; e < 32; ++e)                                             \
+          pm |= (__uint_as_float(REG[e]) <= thr ? 1u : 0u) << e;                                   \
+        if (!active) pm = 0;                                                                       \
+        if (n_base + 32 > g.N) pm &= n_base < g.N ? (0xffffffffu >> (32 - (int)(g.N - n_base))) : 0u; \
+        while (pm) {                                                                               \
+          const int e = __ffs(pm) - 1;                                                             \
+          pm &= pm - 1;                                                                            \
+          if (cnt < stage_cap) {                                                                   \
+            stage[cnt] = make_int2(n_base + e, 0);                                                 \
+            ++cnt;                                                                                 \
+          } else if (g.q_cap > 0) { /* a full private list inside ONE unit: the query is hopeless */ \
+            hopeless = true;                                                                       \
+            thr = __int_as_float(0xff800000);                                                      \
+            pm = 0;                                                                                \
           } else {                                                                                 \
+            pool_flush(g, row, stage, cnt);                                                        \
+            stage[0] = make_int2(n_base + e, 0);                                                   \
+            cnt = 1;                                                                               \
+          }                                                                                        \
+        }                                                                                          \
+      } else {                                                                                     \
+        _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                           \
+          const float d = __uint_as_float(REG[e]);  /* |c|^2 - 2 q.c */                             \
+          if (d <= thr && active && n_base + e < g.N) {                                            \
             if (cnt < stage_cap) stage[cnt] = make_int2(n_base + e, __float_as_int(d));            \
             ++cnt;                                                                                 \
             float x = d;                                                                           \
@@ -496,7 +520,40 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         }
       }
       if (POOL) {
-        if (active && cnt > 0) pool_flush(g, row, stage, cnt);
+        // end of the unit: ONE reservation in the global pool per warp (a returning atomic per thread and unit on the
+        // single pool counter serialised the whole launch: 12 M same-address atomics per C3 step)
+        int take = active ? cnt : 0;
+        if (take > 0 || hopeless) {
+          const int before = atomicAdd(g.q_cnt + row, hopeless ? g.q_cap + 1 + take : take);
+          if (hopeless || (g.q_cap > 0 && before > g.q_cap)) take = 0;  // flagged from q_cnt afterwards
+        }
+        int incl = take;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot > 0) {  // warp-uniform
+          unsigned long long base = 0;
+          if (lane == 31) base = atomicAdd(g.pool_count, (unsigned long long)tot);
+          base = __shfl_sync(0xffffffffu, base, 31);
+          const unsigned long long pos = base + (unsigned long long)(incl - take);
+          // the 32 private lists are copied one after the other by the whole warp: coalesced, independent loads (a
+          // per-lane copy loop was a chain of dependent L2 round trips that held the accumulator back)
+          for (int src = 0; src < 32; ++src) {
+            const int n_src = __shfl_sync(0xffffffffu, take, src);
+            if (n_src == 0) continue;
+            const unsigned long long p_src = __shfl_sync(0xffffffffu, pos, src);
+            const long long r_src = __shfl_sync(0xffffffffu, row, src);
+            const int2* st_src = stage + ((long long)src - lane) * stage_cap;  // lane `src`'s private list
+            for (int i = lane; i < n_src; i += 32)
+              if ((long long)(p_src + i) < g.pool_cap) {
+                g.pool_rc[p_src + i] = __ldcg(st_src + i);
+                g.pool_q[p_src + i] = (int)r_src;
+              }
+          }
+        }
       } else if (active && cnt > 0) {
         if (best[KT - 1] < gb) atomic_min_float(g.bound + row, best[KT - 1]);
         // a staging list that overflowed, or a shared list above its capacity, marks the query for the exact-scan
@@ -738,26 +795,73 @@ struct GemmOperand {
   CUtensorMap map_b;
   DevBuf words_h, cnorm, cnorm_h, cerr;
   float cmax_h = 0, cerr_max = 0, cmax2 = 0;
+  int64_t n = 0;   // rows
+  int D = 0;       // row length before augmentation
+  bool ready = false;
   void release() {
     DevBuf* all[] = {&words_h, &cnorm, &cnorm_h, &cerr};
+    for (DevBuf* b : all) b->release();
+    ready = false;
+    n = 0;
+  }
+};
+
+// PCA pre-filter of the Euclidean activation (large codebooks, large batches):
+//   * `sample`: every f-th codeword (one random row of each block of f), full-length rows.  A sweep over it gives U(q),
+//     the exact K-th nearest distance INSIDE the sample, an upper bound of the K-th nearest distance overall.
+//   * `proj`: every codeword projected on the d leading principal axes P of the codebook, y = P^T (c - mu).  With P
+//     orthonormal |y_q - y_c| <= |q - c|, so ONE sweep over the d-dimensional operands (d + 16 instead of D + 16 columns
+//     of MMA work) pools every codeword whose projected distance can still be <= U; the exact functor decides.
+// Sound whatever the basis is (orthonormality is checked numerically and its defect enters the threshold); the basis
+// only decides how many rows survive.  Measured on C3 (profiles/r02_prefilter_experiment.json): d = 128, f = 16 keeps a
+// median of 30 codewords per query out of 1.07 M; 1 % of the queries keep more than 2048 and are searched the old way.
+struct PcaFilter {
+  bool ready = false;
+  int d = 0, f = 0;
+  GemmOperand sample, proj;
+  DevBuf s2g;      // sample row -> codebook row
+  DevBuf basis;    // [D][d] fp32, orthonormal columns
+  DevBuf mean;     // [D]
+  double orth_defect = 0;  // bound on ||P^T P - I||_2
+  float eta_c = 0;         // bound on |fl(y_c) - y_c| over the codebook (fp32 projection rounding)
+  float mean_norm = 0;
+  // per batch
+  DevBuf yq, yq_h, rnorm_q, qn2p, qnormp, qerrp, epsp, marginp;
+  void release() {
+    sample.release();
+    proj.release();
+    DevBuf* all[] = {&s2g, &basis, &mean, &yq, &yq_h, &rnorm_q, &qn2p, &qnormp, &qerrp, &epsp, &marginp};
+    for (DevBuf* b : all) b->release();
+    ready = false;
+  }
+};
+
+struct FallbackBufs {
+  DevBuf q, idx, dist, cnt, list;
+  void release() {
+    DevBuf* all[] = {&q, &idx, &dist, &cnt, &list};
     for (DevBuf* b : all) b->release();
   }
 };
 
 struct GemmState {
   GemmOperand op[2];
-  DevBuf qnorm_h, qerr, qn2, qbad, margin, eps, bound, stage, fb_q, fb_flag, fb_pos, fb_idx, fb_dist, fb_cnt, fb_list;
+  PcaFilter pca;
+  FallbackBufs fb[2];  // [0]: queries the pre-filtered search hands to the plain sweep, [1]: that sweep's own fallback
+  DevBuf qnorm_h, qerr, qn2, qbad, margin, eps, bound, stage, fb_flag, fb_pos;
   // chi^2 second pass: pooled candidates and their CSR by query
   DevBuf thr2, pool_rc, pool_q, q_cnt, q_off, q_fill, csr_row, csr_q, csr_d;
   int64_t pool_cap = 0;
   int max_clusters[2] = {0, 0};  // co-resident CTA pairs of the streaming / resident-query kernel on this device
   ~GemmState() {
-    DevBuf* all[] = {&qnorm_h, &qerr, &qn2, &qbad, &margin, &eps, &bound, &stage, &fb_q, &fb_flag, &fb_pos, &fb_idx,
-                     &fb_dist, &fb_cnt, &fb_list, &thr2, &pool_rc, &pool_q, &q_cnt, &q_off, &q_fill, &csr_row, &csr_q,
-                     &csr_d};
+    DevBuf* all[] = {&qnorm_h, &qerr, &qn2, &qbad, &margin, &eps, &bound, &stage, &fb_flag, &fb_pos, &thr2, &pool_rc,
+                     &pool_q, &q_cnt, &q_off, &q_fill, &csr_row, &csr_q, &csr_d};
     for (DevBuf* b : all) b->release();
     op[0].release();
     op[1].release();
+    pca.release();
+    fb[0].release();
+    fb[1].release();
   }
 };
 // owned by the context (freed by pcdb_destroy through gemm_state_free)
@@ -810,51 +914,42 @@ int launch_gemm_kt(pcdb_ctx* ctx, int K, const CUtensorMap& map_a, const CUtenso
   return launch_gemm<A_RES, 17, false>(ctx, map_a, map_b, g, grid);
 }
 
-}  // namespace
-
-bool gemm_supported(const pcdb_ctx* ctx, int dist_type) { return ctx->cb.gemm_ready[dist_type == PCDB_DIST_CHISQUARED]; }
-
-// fp16 operand copy of the codebook for one distance family (the rows, or their square roots for chi^2), |c|^2, error
-// maxima and the codebook-side tensor map.  Called by pcdb_set_codebook for the context's DistanceType and lazily by the
-// first search that uses the other one.
-int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
-  Codebook_d& cb = ctx->cb;
+// fp16 operand copy of n fp32 rows of length D (the rows, or their square roots for chi^2): box-major rows, |row|^2,
+// error maxima and the tensor map.  op.ready stays false when the rows cannot be used (non-finite / negative entries).
+int prepare_operand(pcdb_ctx* ctx, const float* rows_d, int64_t n, int D, bool sqrt_rows, GemmOperand& op) {
   cudaStream_t st = ctx->stream;
-  const int fam = dist_type == PCDB_DIST_CHISQUARED ? 1 : 0;
-  cb.gemm_ready[fam] = false;
-  cb.gemm_tried[fam] = true;
-  if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
-  const int aug = (cb.D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;  // resident-query variant <=> augmented operands
-  const int Dh = cb.D + (aug ? K_AUG : 0);
-  GemmState* gs = state_of(ctx);
-  GemmOperand& op = gs->op[fam];
-  const int64_t n_pad = (int64_t)cdiv(cb.N, BN) * BN;
+  op.ready = false;
+  op.n = n;
+  op.D = D;
+  const int aug = (D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;  // resident-query variant <=> augmented operands
+  const int Dh = D + (aug ? K_AUG : 0);
+  const int64_t n_pad = (int64_t)cdiv(n, BN) * BN;
   const int KBt = (Dh + BK - 1) / BK;
-  const int64_t blk_rows = (int64_t)cdiv(cb.N, BN_HALF) * KBt * BN_HALF;  // rows of the box-major [rows][BK] operand
+  const int64_t blk_rows = (int64_t)cdiv(n, BN_HALF) * KBt * BN_HALF;  // rows of the box-major [rows][BK] operand
   PCDB_CUDA(op.words_h.ensure(sizeof(__half) * (size_t)blk_rows * BK + 256));
   PCDB_CUDA(cudaMemsetAsync(op.words_h.p, 0, sizeof(__half) * (size_t)blk_rows * BK, st));  // padding rows / columns
   PCDB_CUDA(op.cnorm.ensure(sizeof(float) * (n_pad + 4)));
-  PCDB_CUDA(op.cnorm_h.ensure(sizeof(float) * (cb.N + 1)));
-  PCDB_CUDA(op.cerr.ensure(sizeof(float) * (cb.N + 1)));
+  PCDB_CUDA(op.cnorm_h.ensure(sizeof(float) * (n + 1)));
+  PCDB_CUDA(op.cerr.ensure(sizeof(float) * (n + 1)));
   PCDB_CUDA(ctx->ws.scalars.ensure(256));
   unsigned* mx = reinterpret_cast<unsigned*>(ctx->ws.scalars.as<char>() + 128);
   PCDB_CUDA(cudaMemsetAsync(mx, 0, 32, st));
-  if (fam)
-    k_prep_rows<true, true><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(
-        cb.words.as<float>(), cb.N, cb.D, aug, op.words_h.as<__half>(), op.cnorm.as<float>(), op.cnorm_h.as<float>(),
-        op.cerr.as<float>(), nullptr, reinterpret_cast<int*>(mx + 4));
+  if (sqrt_rows)
+    k_prep_rows<true, true><<<cdiv(n * 32, 256), 256, 0, st>>>(rows_d, n, D, aug, op.words_h.as<__half>(),
+                                                              op.cnorm.as<float>(), op.cnorm_h.as<float>(),
+                                                              op.cerr.as<float>(), nullptr, reinterpret_cast<int*>(mx + 4));
   else
-    k_prep_rows<true, false><<<cdiv(cb.N * 32, 256), 256, 0, st>>>(
-        cb.words.as<float>(), cb.N, cb.D, aug, op.words_h.as<__half>(), op.cnorm.as<float>(), op.cnorm_h.as<float>(),
-        op.cerr.as<float>(), nullptr, nullptr);
+    k_prep_rows<true, false><<<cdiv(n * 32, 256), 256, 0, st>>>(rows_d, n, D, aug, op.words_h.as<__half>(),
+                                                               op.cnorm.as<float>(), op.cnorm_h.as<float>(),
+                                                               op.cerr.as<float>(), nullptr, nullptr);
   PCDB_LAUNCH_CHECK();
-  if (n_pad > cb.N) {
-    k_pad_inf<<<cdiv(n_pad - cb.N, 256), 256, 0, st>>>(op.cnorm.as<float>(), cb.N, n_pad);
+  if (n_pad > n) {
+    k_pad_inf<<<cdiv(n_pad - n, 256), 256, 0, st>>>(op.cnorm.as<float>(), n, n_pad);
     PCDB_LAUNCH_CHECK();
   }
-  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(op.cnorm_h.as<float>(), op.cerr.as<float>(), cb.N, mx);
+  k_max2<<<cdiv(n, 256), 256, 0, st>>>(op.cnorm_h.as<float>(), op.cerr.as<float>(), n, mx);
   PCDB_LAUNCH_CHECK();
-  k_max2<<<cdiv(cb.N, 256), 256, 0, st>>>(op.cnorm.as<float>(), op.cnorm.as<float>(), cb.N, mx + 2);
+  k_max2<<<cdiv(n, 256), 256, 0, st>>>(op.cnorm.as<float>(), op.cnorm.as<float>(), n, mx + 2);
   PCDB_LAUNCH_CHECK();
   float h[8];
   PCDB_CUDA(cudaMemcpyAsync(h, mx, 32, cudaMemcpyDeviceToHost, st));
@@ -865,34 +960,453 @@ int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
   int any_bad = 0;
   std::memcpy(&any_bad, &h[4], sizeof(int));
   if (!std::isfinite(h[0]) || !std::isfinite(h[2]) || any_bad) {
-    op.release();  // non-finite codewords, or negative entries under chi^2: scan path only
+    op.release();  // non-finite rows, or negative entries under chi^2: scan path only
     return PCDB_OK;
   }
   PCDB_TRY(make_map(ctx, &op.map_b, op.words_h.p, blk_rows, Dh, BN_HALF, true));
-  cb.gemm_ready[fam] = true;
+  op.ready = true;
+  return PCDB_OK;
+}
+
+// ---- PCA pre-filter set-up (one-off, at codebook upload) ---------------------------------------------------------
+// column sums of n rows taken with a stride (fp64 atomics on D accumulators)
+__global__ void k_col_sums(const float* __restrict__ x, long long n, long long stride, int D, double* sums) {
+  const int j = threadIdx.x;
+  double acc = 0;
+  for (long long r = blockIdx.x; r < n; r += gridDim.x)
+    if (j < D) acc += (double)x[r * stride * D + j];
+  if (j < D) atomicAdd(&sums[j], acc);
+}
+// covariance tile: C[16 a .. 16 a + 15][16 b .. 16 b + 15] over n strided rows, fp64; one CTA of 256 threads per tile
+__global__ void __launch_bounds__(256) k_cov_tile(const float* __restrict__ x, long long n, long long stride, int D,
+                                                  const double* __restrict__ mean, double* cov) {
+  __shared__ float sa[64][17], sb[64][17];
+  const int ta = blockIdx.x * 16, tb = blockIdx.y * 16;
+  const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+  double acc = 0;
+  for (long long r0 = 0; r0 < n; r0 += 64) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int rr = e >> 4, cc = e & 15;
+      const long long r = r0 + rr;
+      sa[rr][cc] = r < n ? (float)((double)x[r * stride * D + ta + cc] - mean[ta + cc]) : 0.f;
+      sb[rr][cc] = r < n ? (float)((double)x[r * stride * D + tb + cc] - mean[tb + cc]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < 64; ++rr) acc += (double)sa[rr][i] * (double)sb[rr][j];
+    __syncthreads();
+  }
+  cov[(size_t)(ta + i) * D + tb + j] = acc / (double)n;
+}
+// y = P^T (x - mu): rows x [n][D] -> y [n][d]; CTA = 64 rows x d columns, K staged 16 at a time; DC = d / 32
+template <int DC>
+__global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, long long n, int D,
+                                                 const float* __restrict__ mean, const float* __restrict__ basis,
+                                                 float* __restrict__ y) {
+  constexpr int d = DC * 32;
+  __shared__ float sx[16][65];
+  __shared__ float sp[16][d];
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty: 8 row groups of 8, tx: columns tx + 32 c
+  float acc[8][DC];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < DC; ++c) acc[a][c] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int rr = e >> 4, kk = e & 15;
+      const long long r = r0 + rr;
+      sx[kk][rr] = (r < n && k0 + kk < D) ? __fsub_rn(x[r * D + k0 + kk], mean[k0 + kk]) : 0.f;
+    }
+    for (int e = threadIdx.x; e < 16 * d; e += 256) {
+      const int kk = e / d, c = e % d;
+      sp[kk][c] = k0 + kk < D ? basis[(size_t)(k0 + kk) * d + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float pv[DC];
+#pragma unroll
+      for (int c = 0; c < DC; ++c) pv[c] = sp[kk][tx + 32 * c];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const float xv = sx[kk][ty * 8 + a];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) acc[a][c] = fmaf(xv, pv[c], acc[a][c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const long long r = r0 + ty * 8 + a;
+    if (r < n)
+#pragma unroll
+      for (int c = 0; c < DC; ++c) y[r * d + tx + 32 * c] = acc[a][c];
+  }
+}
+// |x - mu| per row, rounded up (one warp per row); out_max (optional): maximum over the rows
+__global__ void k_centered_norm(const float* __restrict__ x, long long n, int D, const float* __restrict__ mean,
+                                float* out, unsigned* out_max) {
+  const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  double s = 0;
+  for (int j = lane; j < D; j += 32) {
+    const double v = (double)x[r * D + j] - (double)mean[j];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float v = (float)sqrt(s) * 1.000001f;
+    if (out) out[r] = v;
+    if (out_max) atomicMax(out_max, __float_as_uint(v));
+  }
+}
+__global__ void k_sample_rows(const float* __restrict__ words, long long N, int D, int f, long long n_s, int* s2g,
+                              float* out) {
+  const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n_s) return;
+  unsigned h = (unsigned)i * 2654435761u;
+  h ^= h >> 15;
+  h *= 2246822519u;
+  h ^= h >> 13;
+  long long g = i * f + (long long)(h % (unsigned)f);  // one pseudo-random row of every block of f
+  if (g >= N) g = N - 1;
+  if (lane == 0) s2g[i] = (int)g;
+  for (int j = lane; j < D; j += 32) out[i * D + j] = words[g * D + j];
+}
+// candidate lists of the sample sweep: sample rows -> codebook rows (the re-rank reads the codebook)
+__global__ void k_remap_cands(int* cand_idx, const int* __restrict__ cand_cnt, long long Q, int S, int cap,
+                              const int* __restrict__ s2g) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= Q * S * cap) return;
+  const long long list = t / cap;  // [s][q]
+  const int i = (int)(t % cap);
+  if (i < min(cand_cnt[list], cap)) {
+    const long long s = list / Q, q = list % Q;
+    int* p = cand_idx + ((size_t)q * S + s) * cap + i;
+    *p = s2g[*p];
+  }
+}
+// Threshold of the pooled sweep over the projected operands.  A codeword c with |q - c|^2 <= U' has
+//   |y_q - y_c| <= sqrt(1 + e) |q - c| + eta_q + eta_c =: T      (e: orthonormality defect of the basis, eta: fp32
+//   rounding of the two projections), hence accumulator = |y_c|^2 - 2 y_q.y_c (known to within eps) <= T^2 - |y_q|^2 + eps.
+// U' = U (1 + 1.01 g): U is an fp32 FLANN-order functor value, g bounds its rounding (see k_chi_thr).
+__global__ void k_pca_thr(const float* __restrict__ part_d, int K, const float* __restrict__ qn2p,
+                          const float* __restrict__ epsp, const float* __restrict__ rnorm_q, int* skip,
+                          long long Q, int D, int d, double orth_defect, float eta_c, float* thr) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const float U = part_d[q * K + K - 1];
+  if (skip[q] || !(U < __int_as_float(0x7f800000))) {
+    skip[q] = 1;  // no bound (fewer than K usable sample candidates): searched by the plain sweep
+    thr[q] = __int_as_float(0xff800000);
+    return;
+  }
+  const double g = 1.01 * (double)(D + 8) * 5.9604644775390625e-08;
+  const double eta_q = 1.01 * (double)(D + 3) * 5.9604644775390625e-08 * sqrt((double)d) * (double)rnorm_q[q];
+  const double T = sqrt((1.0 + orth_defect) * (double)U * (1.0 + g)) + eta_q + (double)eta_c;
+  const double t = T * T * (1.0 + 1e-9) - (double)qn2p[q] * (1.0 - 2.4e-7) + (double)epsp[q] + 1e-12;
+  float f = (float)t;
+  if ((double)f < t) f = __uint_as_float(__float_as_uint(f) + (f >= 0.f ? 1u : -1u));  // round up
+  thr[q] = f;
+}
+// queries whose pool went past the cap: flag them for the plain sweep and drop their pool entries
+__global__ void k_pool_cap_flags(int* q_cnt, long long Q, int cap, int* flag) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q > Q) return;
+  if (q == Q) {
+    q_cnt[q] = 0;
+    return;
+  }
+  if (q_cnt[q] > cap) {
+    flag[q] = 1;
+    q_cnt[q] = 0;
+  } else if (flag[q]) {
+    q_cnt[q] = 0;
+  }
+}
+
+// symmetric eigen-decomposition on the host (cyclic Jacobi, fp64): only the ORTHONORMALITY of V matters for soundness
+// and plane rotations keep it to rounding whatever the sweep count; the sweeps just have to find the leading subspace
+void host_jacobi(std::vector<double>& A, int n, std::vector<double>& V, int sweeps) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  for (int sw = 0; sw < sweeps; ++sw) {
+    double off = 0, diag = 0;
+    for (int p = 0; p < n; ++p) {
+      diag += A[(size_t)p * n + p] * A[(size_t)p * n + p];
+      for (int q = p + 1; q < n; ++q) off += A[(size_t)p * n + q] * A[(size_t)p * n + q];
+    }
+    if (off <= 1e-22 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[(size_t)p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        double* Ap = &A[(size_t)p * n];
+        double* Aq = &A[(size_t)q * n];
+        for (int k = 0; k < n; ++k) {  // rows p, q
+          const double a = Ap[k], b = Aq[k];
+          Ap[k] = c * a - sn * b;
+          Aq[k] = sn * a + c * b;
+        }
+        for (int k = 0; k < n; ++k) {  // columns p, q
+          const double a = A[(size_t)k * n + p], b = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * a - sn * b;
+          A[(size_t)k * n + q] = sn * a + c * b;
+        }
+        double* Vp = &V[(size_t)p * n];  // V stored by ROWS = eigenvectors (transposed accumulation)
+        double* Vq = &V[(size_t)q * n];
+        for (int k = 0; k < n; ++k) {
+          const double a = Vp[k], b = Vq[k];
+          Vp[k] = c * a - sn * b;
+          Vq[k] = sn * a + c * b;
+        }
+      }
+  }
+}
+
+template <int DC>
+int launch_project(pcdb_ctx* ctx, const float* x, int64_t n, int D, const float* mean, const float* basis, float* y) {
+  k_project<DC><<<cdiv(n, 64), 256, 0, ctx->stream>>>(x, n, D, mean, basis, y);
+  PCDB_LAUNCH_CHECK();
+  return PCDB_OK;
+}
+int project_rows(pcdb_ctx* ctx, const float* x, int64_t n, int D, int d, const float* mean, const float* basis, float* y) {
+  switch (d / 32) {
+    case 2: return launch_project<2>(ctx, x, n, D, mean, basis, y);
+    case 3: return launch_project<3>(ctx, x, n, D, mean, basis, y);
+    case 4: return launch_project<4>(ctx, x, n, D, mean, basis, y);
+    case 5: return launch_project<5>(ctx, x, n, D, mean, basis, y);
+  }
+  return ctx->fail(PCDB_E_INVALID, "PCA pre-filter: unsupported dimension %d", d);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// builds the sample and projected operands of the PCA pre-filter for the resident codebook (Euclidean family)
+int pca_prepare(pcdb_ctx* ctx) {
+  Codebook_d& cb = ctx->cb;
+  cudaStream_t st = ctx->stream;
+  GemmState* gs = state_of(ctx);
+  PcaFilter& pf = gs->pca;
+  pf.release();
+  const int d = env_int("PCDB_GEMM_PCA_D", 128), f = env_int("PCDB_GEMM_SAMPLE", 16);
+  const int64_t min_rows = env_int("PCDB_GEMM_PCA_MIN_ROWS", 262144);
+  if (!env_int("PCDB_GEMM_PCA", 1) || cb.N < min_rows || cb.D % 16 != 0 || d % 32 != 0 || d < 64 || d > 160 ||
+      d + K_AUG >= cb.D || f < 2 || (cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX)
+    return PCDB_OK;
+  const int D = cb.D;
+  const float* words = cb.words.as<float>();
+  // ---- mean and covariance of up to 65536 strided rows
+  const int64_t stride = std::max<int64_t>(1, cb.N / 65536), n_cov = cb.N / stride;
+  DevBuf dsum, dcov;
+  PCDB_CUDA(dsum.ensure(sizeof(double) * D));
+  PCDB_CUDA(dcov.ensure(sizeof(double) * (size_t)D * D));
+  auto free_tmp = [&]() { dsum.release(); dcov.release(); };
+  PCDB_CUDA(cudaMemsetAsync(dsum.p, 0, sizeof(double) * D, st));
+  k_col_sums<<<256, ((D + 31) / 32) * 32, 0, st>>>(words, n_cov, stride, D, dsum.as<double>());
+  PCDB_LAUNCH_CHECK();
+  std::vector<double> hmean(D);
+  PCDB_CUDA(cudaMemcpyAsync(hmean.data(), dsum.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  for (double& v : hmean) v /= (double)n_cov;
+  PCDB_CUDA(cudaMemcpyAsync(dsum.p, hmean.data(), sizeof(double) * D, cudaMemcpyHostToDevice, st));
+  k_cov_tile<<<dim3(D / 16, D / 16), 256, 0, st>>>(words, n_cov, stride, D, dsum.as<double>(), dcov.as<double>());
+  PCDB_LAUNCH_CHECK();
+  std::vector<double> cov((size_t)D * D), V;
+  PCDB_CUDA(cudaMemcpyAsync(cov.data(), dcov.p, sizeof(double) * (size_t)D * D, cudaMemcpyDeviceToHost, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  free_tmp();
+  for (double v : cov)
+    if (!std::isfinite(v)) return PCDB_OK;  // non-finite codewords: no pre-filter
+  host_jacobi(cov, D, V, 8);
+  std::vector<int> order(D);
+  for (int i = 0; i < D; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return cov[(size_t)a * D + a] > cov[(size_t)b * D + b]; });
+  // basis [D][d] in fp32 + its orthonormality defect ||P^T P - I||_2 <= max row sum of |P^T P - I| (evaluated in fp64
+  // on the fp32 values the device multiplies with)
+  std::vector<float> hb((size_t)D * d), hm(D);
+  for (int c = 0; c < d; ++c)
+    for (int k = 0; k < D; ++k) hb[(size_t)k * d + c] = (float)V[(size_t)order[c] * D + k];
+  double defect = 0;
+  for (int a = 0; a < d; ++a) {
+    double row = 0;
+    for (int b = 0; b < d; ++b) {
+      double g = 0;
+      for (int k = 0; k < D; ++k) g += (double)hb[(size_t)k * d + a] * (double)hb[(size_t)k * d + b];
+      row += std::fabs(g - (a == b ? 1.0 : 0.0));
+    }
+    defect = std::max(defect, row);
+  }
+  if (!(defect < 1e-3)) return PCDB_OK;
+  double mn2 = 0;
+  for (int k = 0; k < D; ++k) {
+    hm[k] = (float)hmean[k];
+    mn2 += (double)hm[k] * hm[k];
+  }
+  PCDB_CUDA(pf.basis.ensure(sizeof(float) * (size_t)D * d));
+  PCDB_CUDA(pf.mean.ensure(sizeof(float) * D));
+  PCDB_CUDA(cudaMemcpyAsync(pf.basis.p, hb.data(), sizeof(float) * (size_t)D * d, cudaMemcpyHostToDevice, st));
+  PCDB_CUDA(cudaMemcpyAsync(pf.mean.p, hm.data(), sizeof(float) * D, cudaMemcpyHostToDevice, st));
+  PCDB_CUDA(cudaStreamSynchronize(st));
+  pf.orth_defect = defect * 1.01 + 1e-12;
+  pf.mean_norm = (float)std::sqrt(mn2);
+  pf.d = d;
+  pf.f = f;
+  // ---- projected codebook operand
+  DevBuf tmp;
+  PCDB_CUDA(tmp.ensure(sizeof(float) * (size_t)cb.N * d));
+  int rc = project_rows(ctx, words, cb.N, D, d, pf.mean.as<float>(), pf.basis.as<float>(), tmp.as<float>());
+  if (rc == PCDB_OK) rc = prepare_operand(ctx, tmp.as<float>(), cb.N, d, false, pf.proj);
+  unsigned* mx = reinterpret_cast<unsigned*>(ctx->ws.scalars.as<char>() + 160);
+  if (rc == PCDB_OK && cudaMemsetAsync(mx, 0, 4, st) != cudaSuccess) rc = PCDB_E_CUDA;
+  if (rc == PCDB_OK) {
+    k_centered_norm<<<cdiv(cb.N * 32, 256), 256, 0, st>>>(words, cb.N, D, pf.mean.as<float>(), nullptr, mx);
+    float rmax = 0;
+    if (cudaMemcpyAsync(&rmax, mx, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      rc = PCDB_E_CUDA;
+    pf.eta_c = (float)(1.01 * (double)(D + 3) * 5.9604644775390625e-08 * std::sqrt((double)d) * (double)rmax * 1.000001);
+  }
+  tmp.release();
+  PCDB_TRY(rc);
+  if (!pf.proj.ready) return PCDB_OK;
+  // ---- sample operand (full-length rows)
+  const int64_t n_s = cb.N / f;
+  if (n_s < 4 * BN) return PCDB_OK;
+  PCDB_CUDA(pf.s2g.ensure(sizeof(int) * (size_t)n_s));
+  PCDB_CUDA(tmp.ensure(sizeof(float) * (size_t)n_s * D));
+  k_sample_rows<<<cdiv(n_s * 32, 256), 256, 0, st>>>(words, cb.N, D, f, n_s, pf.s2g.as<int>(), tmp.as<float>());
+  rc = cudaGetLastError() == cudaSuccess ? PCDB_OK : PCDB_E_CUDA;
+  if (rc == PCDB_OK) rc = prepare_operand(ctx, tmp.as<float>(), n_s, D, false, pf.sample);
+  tmp.release();
+  PCDB_TRY(rc);
+  pf.ready = pf.sample.ready && pf.proj.ready;
+  return PCDB_OK;
+}
+
+}  // namespace
+
+bool gemm_supported(const pcdb_ctx* ctx, int dist_type) { return ctx->cb.gemm_ready[dist_type == PCDB_DIST_CHISQUARED]; }
+
+// fp16 operand copy of the codebook for one distance family (the rows, or their square roots for chi^2), |c|^2, error
+// maxima and the codebook-side tensor map.  Called by pcdb_set_codebook for the context's DistanceType and lazily by the
+// first search that uses the other one.
+int gemm_prepare_codebook(pcdb_ctx* ctx, int dist_type) {
+  Codebook_d& cb = ctx->cb;
+  const int fam = dist_type == PCDB_DIST_CHISQUARED ? 1 : 0;
+  cb.gemm_ready[fam] = false;
+  cb.gemm_tried[fam] = true;
+  GemmState* gs = state_of(ctx);
+  if (fam == 0) gs->pca.release();
+  if (cb.D % 16 != 0 || cb.D < BK || cb.N < 1) return PCDB_OK;  // scan path only
+  PCDB_TRY(prepare_operand(ctx, cb.words.as<float>(), cb.N, cb.D, fam == 1, gs->op[fam]));
+  cb.gemm_ready[fam] = gs->op[fam].ready;
+  if (fam == 0 && cb.gemm_ready[0]) PCDB_TRY(pca_prepare(ctx));
+  return PCDB_OK;
+}
+
+namespace {
+
+// sweep geometry of one launch: slices, candidate capacity, grid
+struct SweepPlan {
+  GemmArgs g;
+  int grid = 0;
+  bool a_res = false;
+};
+
+// fills the part of GemmArgs that depends on (queries, operand rows, row length) only
+int plan_sweep(pcdb_ctx* ctx, GemmState* gs, int64_t Q, int64_t n_rows, int Dh, bool a_res, int K, SweepPlan& p) {
+  GemmArgs& g = p.g;
+  std::memset(&g, 0, sizeof(g));
+  g.Q = Q;
+  g.N = n_rows;
+  g.D = Dh;
+  g.n_mpairs = (int)cdiv(Q, 2 * BM);
+  g.n_ntiles = (int)cdiv(n_rows, BN);
+  // codebook slices: small enough to stay L2-resident while every query-tile pair passes over them (20 MB of fp16
+  // rows), and at least as many as it takes to give every CTA pair a unit when there are few queries
+  const int max_pairs = std::max(1, ctx->sm_count / 2);
+  const int64_t tile_bytes = (int64_t)BN * Dh * (int64_t)sizeof(__half);
+  static const int64_t slice_mb = [] {  // tuning knob for experiments; the default is what profiles/ was measured with
+    const char* e = getenv("PCDB_GEMM_SLICE_MB");
+    const long v = e ? atol(e) : 0;
+    return (int64_t)(v > 0 ? v : 20);
+  }();
+  // (the streaming-query variant for D = 1344 re-reads its query tile with every codebook tile and sits on the L2->SM
+  // limit either way; it keeps the query-major sweep, whose L2 hit rate measured 99 %)
+  int S = a_res ? (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20) : 1;
+  if (g.n_mpairs < max_pairs) {
+    // Few queries (one cloud): every (slice, query pair) unit runs at the same time, the kernel takes as long as the
+    // CTA pair with the most tiles.  Units are dealt round-robin, so pick the slice count that minimises
+    // rounds x tiles per slice — 2 query pairs on 74 CTA pairs want 37 slices (one round), not 38 (two).
+    const int pairs = gs->max_clusters[a_res ? 1 : 0] > 0 ? gs->max_clusters[a_res ? 1 : 0] : max_pairs;
+    long long best = -1;
+    int best_s = S;
+    for (int s = 1; s <= std::min(g.n_ntiles, 4 * pairs); ++s) {
+      const long long cost = (long long)cdiv((int64_t)g.n_mpairs * s, pairs) * (long long)cdiv(g.n_ntiles, s);
+      if (best < 0 || cost < best) {
+        best = cost;
+        best_s = s;
+      }
+    }
+    S = best_s;
+  }
+  static const int s_env = [] { const char* e = getenv("PCDB_GEMM_S"); return e ? atoi(e) : 0; }();  // experiments
+  if (s_env > 0) S = s_env;
+  S = std::max(1, std::min(S, g.n_ntiles));
+  g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
+  S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
+  g.n_splits = S;
+  // Slices of one query tile run one after the other when there are more tile pairs than CTA pairs; with few queries
+  // they run side by side, each starting from an empty bound and contributing its own descending staircase
+  const int in_flight = std::min(S, (int)cdiv(max_pairs, g.n_mpairs));
+  g.stage_cap = K <= 4 ? 64 : (K <= 8 ? 128 : CAND_CAP_MAX);
+  g.cand_cap = g.stage_cap * std::max(1, in_flight);
+  PCDB_CUDA(gs->stage.ensure(sizeof(int2) * (size_t)ctx->sm_count * EPI_THREADS * CAND_CAP_MAX));
+  g.stage = gs->stage.as<int2>();
+  p.grid = 2 * std::min(g.n_mpairs * S, max_pairs);  // CTA pairs (cluster of 2)
+  p.a_res = a_res;
   return PCDB_OK;
 }
 
 // Exact kNN on the tensor cores.
-//   Euclidean: one sweep with the running-bound filter, exact fp32 re-rank of the candidates.
+//   Euclidean: one sweep with the running-bound filter, exact fp32 re-rank of the candidates.  Large codebooks and
+//   batches take the PCA pre-filter (struct PcaFilter): the bound sweep runs over a 1/f sample of the codebook, a pooled
+//   sweep over the projected operands collects every codeword that can still be among the K nearest, the exact functor
+//   decides, and the few queries whose pool runs past its cap are searched by the plain sweep.
 //   ChiSquared: the Hellinger sandwich, two sweeps over the sqrt-transformed operands.  Sweep 1 is the Euclidean
 //   machinery on sqrt rows (its candidates, re-ranked with the exact chi^2 functor, give U = the K-th smallest chi^2
 //   of K real codewords); sweep 2 collects EVERY row whose Hellinger value can still be <= U into a pooled list, and
 //   the exact FLANN-order chi^2 of those rows decides.  The result is the exact scan's, bit for bit.
-int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
-                   float ratio_thr) {
+// depth: 0 = a caller's search, 1 = the search of the queries a depth-0 call could not settle (plain sweep, own buffers)
+int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
+                  float ratio_thr, int depth) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const Codebook_d& cb = ctx->cb;
   GemmState* gs = state_of(ctx);
   const bool chi = dist_type == PCDB_DIST_CHISQUARED;
-  GemmOperand& op = gs->op[chi ? 1 : 0];
   PCDB_CUDA(w.knn_idx.ensure(sizeof(int) * (Q * k + 1)));
   PCDB_CUDA(w.knn_dist.ensure(sizeof(float) * (Q * k + 1)));
   PCDB_CUDA(w.knn_cnt.ensure(sizeof(int) * (Q + 1)));
   if (Q == 0) return PCDB_OK;
   const int K = use_ratio ? k + 1 : k;
   const int D = cb.D;
+  PcaFilter& pf = gs->pca;
+  static const int pca_min_q = env_int("PCDB_GEMM_PCA_MIN_Q", 8192);
+  const bool pca = !chi && depth == 0 && pf.ready && pf.sample.n > K && Q >= pca_min_q;
+  GemmOperand& op = pca ? pf.sample : gs->op[chi ? 1 : 0];  // operand of the bound sweep
   // query side: fp16 copy + norms + margins
   const int aug = (D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;
   const int Dh = D + (aug ? K_AUG : 0);
@@ -919,56 +1433,14 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   PCDB_LAUNCH_CHECK();
   CUtensorMap map_a;
   PCDB_TRY(make_map(ctx, &map_a, w.feat_h.p, Q, Dh, BM));
-  GemmArgs g;
-  std::memset(&g, 0, sizeof(g));
-  g.Q = Q;
-  g.N = cb.N;
-  g.D = Dh;
-  g.n_mpairs = (int)cdiv(Q, 2 * BM);
-  g.n_ntiles = (int)cdiv(cb.N, BN);
-  // codebook slices: small enough to stay L2-resident while every query-tile pair passes over them (20 MB of fp16
-  // rows), and at least as many as it takes to give every CTA pair a unit when there are few queries
-  const int max_pairs = std::max(1, ctx->sm_count / 2);
-  const int64_t tile_bytes = (int64_t)BN * Dh * (int64_t)sizeof(__half);
-  static const int64_t slice_mb = [] {  // tuning knob for experiments; the default is what profiles/ was measured with
-    const char* e = getenv("PCDB_GEMM_SLICE_MB");
-    const long v = e ? atol(e) : 0;
-    return (int64_t)(v > 0 ? v : 20);
-  }();
   const bool a_res = aug != 0;
-  // (the streaming-query variant for D = 1344 re-reads its query tile with every codebook tile and sits on the L2->SM
-  // limit either way; it keeps the query-major sweep, whose L2 hit rate measured 99 %)
-  int S = a_res ? (int)cdiv((int64_t)g.n_ntiles * tile_bytes, slice_mb << 20) : 1;
-  if (g.n_mpairs < max_pairs) {
-    // Few queries (one cloud): every (slice, query pair) unit runs at the same time, the kernel takes as long as the
-    // CTA pair with the most tiles.  Units are dealt round-robin, so pick the slice count that minimises
-    // rounds x tiles per slice — 2 query pairs on 74 CTA pairs want 37 slices (one round), not 38 (two).
-    const int pairs = gs->max_clusters[a_res ? 1 : 0] > 0 ? gs->max_clusters[a_res ? 1 : 0] : max_pairs;
-    long long best = -1;
-    int best_s = S;
-    for (int s = 1; s <= std::min(g.n_ntiles, 4 * pairs); ++s) {
-      const long long cost = (long long)cdiv((int64_t)g.n_mpairs * s, pairs) * (long long)cdiv(g.n_ntiles, s);
-      if (best < 0 || cost < best) {
-        best = cost;
-        best_s = s;
-      }
-    }
-    S = best_s;
-  }
-  static const int s_env = [] { const char* e = getenv("PCDB_GEMM_S"); return e ? atoi(e) : 0; }();  // experiments
-  if (s_env > 0) S = s_env;
-  S = std::max(1, std::min(S, g.n_ntiles));
-  g.tiles_per_split = (int)cdiv(g.n_ntiles, S);
-  S = (int)cdiv(g.n_ntiles, g.tiles_per_split);
-  g.n_splits = S;
+  SweepPlan sp;
+  PCDB_TRY(plan_sweep(ctx, gs, Q, op.n, Dh, a_res, K, sp));
+  GemmArgs& g = sp.g;
+  const int grid = sp.grid;
   g.margin = gs->margin.as<float>();
   g.cnorm = op.cnorm.as<float>();
   const int S2 = 2;  // candidate lists: one per column half, shared by all slices
-  // Slices of one query tile run one after the other when there are more tile pairs than CTA pairs; with few queries
-  // they run side by side, each starting from an empty bound and contributing its own descending staircase
-  const int in_flight = std::min(S, (int)cdiv(max_pairs, g.n_mpairs));
-  g.stage_cap = K <= 4 ? 64 : (K <= 8 ? 128 : CAND_CAP_MAX);
-  g.cand_cap = g.stage_cap * std::max(1, in_flight);
   const size_t nc = (size_t)Q * S2 * g.cand_cap;
   PCDB_CUDA(w.cand_idx.ensure(sizeof(int) * nc + 16));
   PCDB_CUDA(w.cand_apx.ensure(sizeof(float) * nc + 16));
@@ -981,48 +1453,90 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
   g.cand_cnt = w.cand_cnt.as<int>();
   PCDB_CUDA(gs->bound.ensure(sizeof(float) * (Q + 1)));
   g.bound = gs->bound.as<float>();
-  PCDB_CUDA(gs->stage.ensure(sizeof(int2) * (size_t)ctx->sm_count * EPI_THREADS * CAND_CAP_MAX));
-  g.stage = gs->stage.as<int2>();
   PCDB_CUDA(cudaMemsetAsync(w.cand_cnt.p, 0, sizeof(int) * (size_t)Q * S2, st));
   k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, Q, INFINITY);
   PCDB_LAUNCH_CHECK();
-  const int grid = 2 * std::min(g.n_mpairs * S, max_pairs);  // CTA pairs (cluster of 2)
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
-  PCDB_CUDA(cudaEventRecord(e0, st));
+  if (depth == 0) PCDB_CUDA(cudaEventRecord(e0, st));
   if (a_res)
     PCDB_TRY((launch_gemm_kt<true>(ctx, K, map_a, op.map_b, g, grid)));
   else
     PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, op.map_b, g, grid)));
-  if (!chi) {
+  if (!chi && !pca && depth == 0) {
     PCDB_CUDA(cudaEventRecord(e1, st));
     ctx->gemm_events_valid = true;
   }
+  if (depth == 0) pcdb_trace_point(ctx, pca ? "knn: sample sweep" : "knn: sweep");
   k_final_thr<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, g.margin, Q, w.cand_thr.as<float>());
   PCDB_LAUNCH_CHECK();
+  if (pca) {  // the re-rank reads the codebook: sample rows -> codebook rows
+    k_remap_cands<<<cdiv((int64_t)nc, 256), 256, 0, st>>>(w.cand_idx.as<int>(), w.cand_cnt.as<int>(), Q, S2, g.cand_cap,
+                                                          pf.s2g.as<int>());
+    PCDB_LAUNCH_CHECK();
+  }
   // exact functor values of the candidates, the K best per query -> ws.knn_part_*
   PCDB_TRY(stage_knn_rerank(ctx, queries_d, Q, K, S2, g.cand_cap, dist_type));
-  // queries that need the exact scan instead: an overflowed candidate list (or, chi^2, a negative entry)
+  // queries that need another search: an overflowed candidate list (or, chi^2, a negative entry)
   PCDB_CUDA(gs->fb_flag.ensure(sizeof(int) * (Q + 2)));
   PCDB_CUDA(gs->fb_pos.ensure(sizeof(int) * (Q + 2)));
   k_overflow_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(w.cand_cnt.as<int>(), S2, Q, g.cand_cap,
                                                      chi ? gs->qbad.as<int>() : nullptr, gs->fb_flag.as<int>());
   PCDB_LAUNCH_CHECK();
-  PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
 
-  if (chi) {
-    // ---- sweep 2: every row whose Hellinger value can still be <= U, pooled
+  if (depth == 0) pcdb_trace_point(ctx, "knn: re-rank");
+  if (chi || pca) {
+    // ---- sweep 2: every row whose lower bound (Hellinger value / projected distance) can still be <= U, pooled
     PCDB_CUDA(gs->thr2.ensure(sizeof(float) * (Q + 1)));
-    k_chi_thr<<<cdiv(Q, 256), 256, 0, st>>>(w.knn_part_d.as<float>(), K, gs->qn2.as<float>(), gs->eps.as<float>(),
-                                            gs->fb_flag.as<int>(), Q, D, gs->thr2.as<float>());
-    PCDB_LAUNCH_CHECK();
+    CUtensorMap map_a2 = map_a;
+    const GemmOperand* op2 = &op;
+    SweepPlan sp2 = sp;
+    static const int q_cap_env = env_int("PCDB_GEMM_QCAP", 2048);
+    if (chi) {
+      k_chi_thr<<<cdiv(Q, 256), 256, 0, st>>>(w.knn_part_d.as<float>(), K, gs->qn2.as<float>(), gs->eps.as<float>(),
+                                              gs->fb_flag.as<int>(), Q, D, gs->thr2.as<float>());
+      PCDB_LAUNCH_CHECK();
+    } else {
+      // project the queries, build their fp16 operand, the error bound of that operand pair and the pool threshold
+      const int d = pf.d, dh = d + K_AUG;
+      PCDB_CUDA(pf.yq.ensure(sizeof(float) * (size_t)Q * d + 256));
+      PCDB_CUDA(pf.yq_h.ensure(sizeof(__half) * (size_t)Q * dh + 256));
+      for (DevBuf* b : {&pf.rnorm_q, &pf.qn2p, &pf.qnormp, &pf.qerrp, &pf.epsp, &pf.marginp})
+        PCDB_CUDA(b->ensure(sizeof(float) * (Q + 1)));
+      PCDB_TRY(project_rows(ctx, queries_d, Q, D, d, pf.mean.as<float>(), pf.basis.as<float>(), pf.yq.as<float>()));
+      k_centered_norm<<<cdiv(Q * 32, 256), 256, 0, st>>>(queries_d, Q, D, pf.mean.as<float>(), pf.rnorm_q.as<float>(),
+                                                         nullptr);
+      PCDB_LAUNCH_CHECK();
+      k_prep_rows<false, false><<<cdiv(Q * 32, 256), 256, 0, st>>>(pf.yq.as<float>(), Q, d, 1, pf.yq_h.as<__half>(),
+                                                                  pf.qn2p.as<float>(), pf.qnormp.as<float>(),
+                                                                  pf.qerrp.as<float>(), nullptr, nullptr);
+      PCDB_LAUNCH_CHECK();
+      k_margin<<<cdiv(Q, 256), 256, 0, st>>>(pf.qnormp.as<float>(), pf.qerrp.as<float>(), Q, d, 1, pf.proj.cmax_h,
+                                             pf.proj.cerr_max, pf.proj.cmax2, 0, pf.marginp.as<float>(),
+                                             pf.epsp.as<float>());
+      PCDB_LAUNCH_CHECK();
+      k_pca_thr<<<cdiv(Q, 256), 256, 0, st>>>(w.knn_part_d.as<float>(), K, pf.qn2p.as<float>(), pf.epsp.as<float>(),
+                                              pf.rnorm_q.as<float>(), gs->fb_flag.as<int>(), Q, D, d, pf.orth_defect,
+                                              pf.eta_c, gs->thr2.as<float>());
+      PCDB_LAUNCH_CHECK();
+      PCDB_TRY(make_map(ctx, &map_a2, pf.yq_h.p, Q, dh, BM));
+      if (env_int("PCDB_EXP_POOL_NOTHR", 0)) {  // experiment: nothing passes the pooled sweep (kernel floor)
+        k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(gs->thr2.as<float>(), Q, -INFINITY);
+        PCDB_LAUNCH_CHECK();
+      }
+      pcdb_trace_point(ctx, "knn: project queries");
+      op2 = &pf.proj;
+      PCDB_TRY(plan_sweep(ctx, gs, Q, pf.proj.n, dh, true, 8, sp2));  // K = 8: 128-entry private lists
+    }
     PCDB_CUDA(gs->q_cnt.ensure(sizeof(int) * (Q + 2)));
     PCDB_CUDA(gs->q_off.ensure(sizeof(int) * (Q + 2)));
     PCDB_CUDA(gs->q_fill.ensure(sizeof(int) * (Q + 2)));
     unsigned long long* pool_count = reinterpret_cast<unsigned long long*>(w.scalars.as<char>() + 72);
-    GemmArgs g2 = g;
+    GemmArgs g2 = sp2.g;
     g2.margin = gs->thr2.as<float>();
+    g2.cnorm = op2->cnorm.as<float>();
     g2.pool_count = pool_count;
     g2.q_cnt = gs->q_cnt.as<int>();
+    g2.q_cap = pca ? q_cap_env : 0;
     unsigned long long total = 0;
     for (int attempt = 0;; ++attempt) {
       const int64_t want = std::max<int64_t>(gs->pool_cap, std::max<int64_t>((int64_t)1 << 22, Q * 64));
@@ -1034,56 +1548,76 @@ int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
       g2.pool_cap = want;
       PCDB_CUDA(cudaMemsetAsync(pool_count, 0, 8, st));
       PCDB_CUDA(cudaMemsetAsync(gs->q_cnt.p, 0, sizeof(int) * (Q + 1), st));
-      if (a_res)
-        PCDB_TRY((launch_gemm<true, 1, true>(ctx, map_a, op.map_b, g2, grid)));
+      if (sp2.a_res)
+        PCDB_TRY((launch_gemm<true, 1, true>(ctx, map_a2, op2->map_b, g2, sp2.grid)));
       else
-        PCDB_TRY((launch_gemm<false, 1, true>(ctx, map_a, op.map_b, g2, grid)));
+        PCDB_TRY((launch_gemm<false, 1, true>(ctx, map_a2, op2->map_b, g2, sp2.grid)));
       PCDB_TRY(pcdb_read_small(ctx, &total, pool_count, 8));
       PCDB_TRY(pcdb_sync_reads(ctx));
       if ((int64_t)total <= gs->pool_cap) break;
       if (attempt >= 2 || total > 0x7fff0000ull)
-        return ctx->fail(PCDB_E_CAPACITY, "chi^2 candidate pool: %llu entries for %lld queries", total, (long long)Q);
+        return ctx->fail(PCDB_E_CAPACITY, "candidate pool: %llu entries for %lld queries", total, (long long)Q);
       gs->pool_cap = (int64_t)(total + total / 4);  // grow and sweep again (first batches of a new workload only)
     }
-    PCDB_CUDA(cudaEventRecord(e1, st));
-    ctx->gemm_events_valid = true;
+    if (depth == 0) {
+      PCDB_CUDA(cudaEventRecord(e1, st));
+      ctx->gemm_events_valid = true;
+    }
     ctx->stats.knn_candidates += (int64_t)total;
+    if (depth == 0) pcdb_trace_point(ctx, "knn: pooled sweep");
+    if (pca) {  // queries past their pool cap join the fallback list; their pool entries are dropped
+      k_pool_cap_flags<<<cdiv(Q + 1, 256), 256, 0, st>>>(gs->q_cnt.as<int>(), Q, g2.q_cap, gs->fb_flag.as<int>());
+      PCDB_LAUNCH_CHECK();
+    }
     PCDB_TRY(stage_knn_chi_pool(ctx, queries_d, Q, K, (int64_t)total, gs->pool_rc.as<int2>(), gs->pool_q.as<int>(),
                                 gs->q_cnt.as<int>(), gs->q_off.as<int>(), gs->q_fill.as<int>(), &gs->csr_row,
-                                &gs->csr_q, &gs->csr_d));
+                                &gs->csr_d, dist_type, pca ? gs->fb_flag.as<int>() : nullptr));
   }
+  PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q + 1));
   PCDB_TRY(stage_knn_finish(ctx, Q, k, K, use_ratio, ratio_thr));
+  if (depth == 0 && (chi || pca)) pcdb_trace_point(ctx, "knn: pool evaluation");
 
-  // overflow fallback: exact scan of the affected queries (still on the GPU)
+  // queries the search above could not settle: searched again (still on the GPU) and merged back
   int n_fb = 0;
   unsigned long long n_eval = 0;
   PCDB_TRY(pcdb_read_small(ctx, &n_fb, gs->fb_pos.as<int>() + Q, sizeof(int)));
   PCDB_TRY(pcdb_read_small(ctx, &n_eval, w.scalars.as<char>() + 64, sizeof(n_eval)));
   PCDB_TRY(pcdb_sync_reads(ctx));
-  if (!chi) ctx->stats.knn_candidates += (int64_t)n_eval;
-  ctx->stats.knn_fallback_queries += n_fb;
+  if (!chi && !pca) ctx->stats.knn_candidates += (int64_t)n_eval;
+  if (!pca) ctx->stats.knn_fallback_queries += n_fb;  // (with the pre-filter: queries handed to the plain sweep)
   if (n_fb > 0) {
-    PCDB_CUDA(gs->fb_q.ensure(sizeof(float) * (size_t)n_fb * D));
-    PCDB_CUDA(gs->fb_list.ensure(sizeof(int) * n_fb));
-    PCDB_CUDA(gs->fb_idx.ensure(sizeof(int) * ((size_t)Q * k + 1)));
-    PCDB_CUDA(gs->fb_dist.ensure(sizeof(float) * ((size_t)Q * k + 1)));
-    PCDB_CUDA(gs->fb_cnt.ensure(sizeof(int) * (Q + 1)));
+    FallbackBufs& fb = gs->fb[depth ? 1 : 0];
+    PCDB_CUDA(fb.q.ensure(sizeof(float) * (size_t)n_fb * D));
+    PCDB_CUDA(fb.list.ensure(sizeof(int) * n_fb));
+    PCDB_CUDA(fb.idx.ensure(sizeof(int) * ((size_t)Q * k + 1)));
+    PCDB_CUDA(fb.dist.ensure(sizeof(float) * ((size_t)Q * k + 1)));
+    PCDB_CUDA(fb.cnt.ensure(sizeof(int) * (Q + 1)));
     k_overflow_gather<<<cdiv(Q * 32, 256), 256, 0, st>>>(gs->fb_flag.as<int>(), gs->fb_pos.as<int>(), Q, D, queries_d,
-                                                         gs->fb_list.as<int>(), gs->fb_q.as<float>());
+                                                         fb.list.as<int>(), fb.q.as<float>());
     PCDB_LAUNCH_CHECK();
-    // keep the GEMM results aside, scan the fallback queries into the knn_* buffers, then merge back
-    PCDB_CUDA(cudaMemcpyAsync(gs->fb_idx.p, w.knn_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(gs->fb_dist.p, w.knn_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(gs->fb_cnt.p, w.knn_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
-    PCDB_TRY(stage_knn_scan(ctx, gs->fb_q.as<float>(), n_fb, k, dist_type, use_ratio, ratio_thr));
-    k_overflow_scatter<<<cdiv(n_fb, 128), 128, 0, st>>>(gs->fb_list.as<int>(), n_fb, k, w.knn_idx.as<int>(),
-                                                        w.knn_dist.as<float>(), w.knn_cnt.as<int>(),
-                                                        gs->fb_idx.as<int>(), gs->fb_dist.as<float>(),
-                                                        gs->fb_cnt.as<int>());
+    // keep the results aside, search the remaining queries into the knn_* buffers, then merge back
+    PCDB_CUDA(cudaMemcpyAsync(fb.idx.p, w.knn_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(fb.dist.p, w.knn_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(fb.cnt.p, w.knn_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
+    if (pca)  // the plain single sweep over the whole codebook; ITS overflows go to the exact scan
+      PCDB_TRY(knn_gemm_impl(ctx, fb.q.as<float>(), n_fb, k, dist_type, use_ratio, ratio_thr, 1));
+    else
+      PCDB_TRY(stage_knn_scan(ctx, fb.q.as<float>(), n_fb, k, dist_type, use_ratio, ratio_thr));
+    k_overflow_scatter<<<cdiv(n_fb, 128), 128, 0, st>>>(fb.list.as<int>(), n_fb, k, w.knn_idx.as<int>(),
+                                                        w.knn_dist.as<float>(), w.knn_cnt.as<int>(), fb.idx.as<int>(),
+                                                        fb.dist.as<float>(), fb.cnt.as<int>());
     PCDB_LAUNCH_CHECK();
-    PCDB_CUDA(cudaMemcpyAsync(w.knn_idx.p, gs->fb_idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(w.knn_dist.p, gs->fb_dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
-    PCDB_CUDA(cudaMemcpyAsync(w.knn_cnt.p, gs->fb_cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_idx.p, fb.idx.p, sizeof(int) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_dist.p, fb.dist.p, sizeof(float) * Q * k, cudaMemcpyDeviceToDevice, st));
+    PCDB_CUDA(cudaMemcpyAsync(w.knn_cnt.p, fb.cnt.p, sizeof(int) * Q, cudaMemcpyDeviceToDevice, st));
+    if (depth == 0) pcdb_trace_point(ctx, "knn: remaining queries");
   }
   return PCDB_OK;
+}
+
+}  // namespace
+
+int stage_knn_gemm(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int dist_type, bool use_ratio,
+                   float ratio_thr) {
+  return knn_gemm_impl(ctx, queries_d, Q, k, dist_type, use_ratio, ratio_thr, 0);
 }

@@ -353,21 +353,30 @@ __global__ void k_pair_dist(const float* __restrict__ a, const float* __restrict
 }
 
 // ---- chi^2 sandwich, pooled second pass -------------------------------------------------------------------------
-__global__ void k_pool_scatter(const int2* __restrict__ pool_rc, const int* __restrict__ pool_q, long long n,
-                               const int* __restrict__ q_off, int* q_fill, int* csr_row, int* csr_q) {
+// exact functor value of every pooled pair, evaluated IN POOL ORDER: the sweep appends slice by slice, so consecutive
+// entries hit the same L2-sized part of the codebook (grouped by query first, the 27 M pairs of a C3 step re-read the
+// 1.5 GB of fp32 rows from HBM ~25 times over).  The value goes into the entry's second word.
+template <int DIST>
+__global__ void __launch_bounds__(128) k_pool_eval(const float* __restrict__ queries, const float* __restrict__ words,
+                                                   int D, long long n, int2* pool_rc, const int* __restrict__ pool_q,
+                                                   const int* __restrict__ skip) {
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n) return;
   const int q = pool_q[e];
-  const int p = q_off[q] + atomicAdd(q_fill + q, 1);
-  csr_row[p] = pool_rc[e].x;
-  csr_q[p] = q;
+  if (skip && skip[q]) return;
+  pool_rc[e].y = __float_as_int(exact_pair<DIST>(queries + (long long)q * D, words + (long long)pool_rc[e].x * D, D));
 }
-__global__ void __launch_bounds__(128) k_chi_eval(const float* __restrict__ queries, const float* __restrict__ words,
-                                                  int D, long long n, const int* __restrict__ csr_row,
-                                                  const int* __restrict__ csr_q, float* csr_d) {
+__global__ void k_pool_scatter(const int2* __restrict__ pool_rc, const int* __restrict__ pool_q, long long n,
+                               const int* __restrict__ q_off, const int* __restrict__ skip, int* q_fill, int* csr_row,
+                               float* csr_d) {
   long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n) return;
-  csr_d[e] = exact_pair<PCDB_DIST_CHISQUARED>(queries + (long long)csr_q[e] * D, words + (long long)csr_row[e] * D, D);
+  const int q = pool_q[e];
+  if (skip && skip[q]) return;  // a query past its pool cap: its entries are dropped, the fallback path searches it
+  const int p = q_off[q] + atomicAdd(q_fill + q, 1);
+  const int2 rc = pool_rc[e];
+  csr_row[p] = rc.x;
+  csr_d[p] = __int_as_float(rc.y);
 }
 // one warp per query: K successive minima over (distance, row); the order inside a CSR segment is arbitrary
 __global__ void k_chi_select(long long Q, int K, const int* __restrict__ q_off, const int* __restrict__ csr_row,
@@ -530,25 +539,28 @@ int stage_knn_finish(pcdb_ctx* ctx, int64_t Q, int k, int K, bool use_ratio, flo
 // query (count -> scan -> scatter), every pair gets the exact FLANN-order chi^2 (one thread per pair, a flat and
 // therefore balanced launch: a query with 10^4 survivors costs what 10^4 queries with one survivor cost), and one warp
 // per query picks its K best by (distance, row).
-int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, const int2* pool_rc,
-                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_q,
-                       DevBuf* csr_d) {
+int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, int2* pool_rc,
+                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_d,
+                       int dist_type, const int* skip) {
   Workspace& w = ctx->ws;
   cudaStream_t st = ctx->stream;
   const Codebook_d& cb = ctx->cb;
   PCDB_CUDA(w.knn_part_d.ensure(sizeof(float) * (Q * K + 1)));
   PCDB_CUDA(w.knn_part_i.ensure(sizeof(int) * (Q * K + 1)));
   PCDB_CUDA(csr_row->ensure(sizeof(int) * (size_t)(total + 1)));
-  PCDB_CUDA(csr_q->ensure(sizeof(int) * (size_t)(total + 1)));
   PCDB_CUDA(csr_d->ensure(sizeof(float) * (size_t)(total + 1)));
   PCDB_TRY(pcdb_cub_exclusive_sum_i32(ctx, q_cnt, q_off, Q + 1));
   PCDB_CUDA(cudaMemsetAsync(q_fill, 0, sizeof(int) * (Q + 1), st));
   if (total > 0) {
-    k_pool_scatter<<<cdiv(total, 256), 256, 0, st>>>(pool_rc, pool_q, total, q_off, q_fill, csr_row->as<int>(),
-                                                     csr_q->as<int>());
+    if (dist_type == PCDB_DIST_CHISQUARED)
+      k_pool_eval<PCDB_DIST_CHISQUARED><<<cdiv(total, 128), 128, 0, st>>>(queries_d, cb.words.as<float>(), cb.D, total,
+                                                                         pool_rc, pool_q, skip);
+    else
+      k_pool_eval<PCDB_DIST_EUCLIDEAN><<<cdiv(total, 128), 128, 0, st>>>(queries_d, cb.words.as<float>(), cb.D, total,
+                                                                        pool_rc, pool_q, skip);
     PCDB_LAUNCH_CHECK();
-    k_chi_eval<<<cdiv(total, 128), 128, 0, st>>>(queries_d, cb.words.as<float>(), cb.D, total, csr_row->as<int>(),
-                                                 csr_q->as<int>(), csr_d->as<float>());
+    k_pool_scatter<<<cdiv(total, 256), 256, 0, st>>>(pool_rc, pool_q, total, q_off, skip, q_fill, csr_row->as<int>(),
+                                                     csr_d->as<float>());
     PCDB_LAUNCH_CHECK();
   }
   k_chi_select<<<cdiv(Q * 32, 256), 256, 0, st>>>(Q, K, q_off, csr_row->as<int>(), csr_d->as<float>(),

@@ -26,9 +26,9 @@ int stage_knn_scan(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int 
                    float ratio_thr);
 int stage_knn_rerank(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int S, int cap, int dist_type);
 int stage_knn_finish(pcdb_ctx* ctx, int64_t Q, int k, int K, bool use_ratio, float ratio_thr);
-int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, const int2* pool_rc,
-                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_q,
-                       DevBuf* csr_d);
+int stage_knn_chi_pool(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int K, int64_t total, int2* pool_rc,
+                       const int* pool_q, const int* q_cnt, int* q_off, int* q_fill, DevBuf* csr_row, DevBuf* csr_d,
+                       int dist_type, const int* skip);
 
 int stage_pair_distances(pcdb_ctx* ctx, const float* a_d, const float* b_d, int64_t n, int D, int dist_type,
                          float* out_d);

@@ -63,9 +63,23 @@ def test_c3_headline_scale_gemm_equals_scan(api, orc):
     st = ctx.stats()
     b = ctx.knn(Q, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
     assert _same(a, b), "%d of %d rows differ" % ((a[0] != b[0]).sum(), a[0].size)
-    a4 = ctx.knn(Q[:4096], k=4, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
+    if os.environ.get("PCDB_GEMM_PCA", "1") != "0":
+        # >= 8192 queries against >= 262144 words take the PCA pre-filter (sample sweep -> pooled projected sweep -> exact
+        # evaluation): its pool holds tens of rows per query where the plain sweep keeps ~1
+        assert st["knn_candidates"] / Q.shape[0] > 5
+    a4 = ctx.knn(Q[:4096], k=4, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)   # few queries: the plain single sweep
     b4 = ctx.knn(Q[:4096], k=4, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
     assert _same(a4, b4)
+    a3 = ctx.knn(Q[:9000], k=3, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)   # the pre-filter with K > 1
+    b3 = ctx.knn(Q[:9000], k=3, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
+    assert _same(a3, b3)
+    prm_r = prm.copy()
+    prm_r.use_distance_ratio = 1                                             # ratio test: K = k + 1 inside
+    ctx.set_params(prm_r)
+    ar = ctx.knn(Q[:9000], k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
+    br = ctx.knn(Q[:9000], k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
+    assert _same(ar, br)
+    ctx.set_params(prm)
     # ChiSquared through the Hellinger sandwich (two tensor-core sweeps + pooled exact re-rank) vs the exact chi^2 scan
     ctx.reset_stats()
     c = ctx.knn(Q, k=1, dist_type=DIST_CHISQUARED, mode=KNN_GEMM)
