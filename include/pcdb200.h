@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PCDB_ABI_VERSION 4
+#define PCDB_ABI_VERSION 5
 
 typedef enum pcdb_status {
   PCDB_OK = 0,
@@ -320,6 +320,12 @@ typedef struct pcdb_stats {
    * batch's exchanges (query all-gather + top-k all-to-all + merge, or the vote all-gather) */
   int64_t comm_bytes;
   double comm_ms;
+  /* Euclidean activation with the PCA pre-filter / chi^2 sandwich (last batch): device time of the bound sweep (over
+   * the codebook sample / the sqrt rows) and of the pooled sweep (over the projected operands / the sqrt rows again);
+   * projected dimension and sample rows in use (0 = plain single sweep); queries handed back to the plain sweep since
+   * the last reset */
+  double knn_bound_sweep_ms, knn_pool_sweep_ms;
+  int64_t knn_prefilter_dim, knn_prefilter_sample_rows, knn_prefilter_resweep_queries;
 } pcdb_stats;
 int pcdb_get_stats(pcdb_ctx* ctx, pcdb_stats* out);
 int pcdb_reset_stats(pcdb_ctx* ctx);

@@ -643,6 +643,7 @@ int pcdb_create(pcdb_ctx** out, int device) {
   ctx->stream = ctx->own_stream;
   if (cudaMallocHost(&ctx->pinned, 1 << 16) == cudaSuccess) ctx->pinned_cap = 1 << 16;  // else: plain copies
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev_knn[i]);
   // CIELab look-up tables, built on the host with powf exactly as the reference does (features_cshot.cpp:52-71)
   std::vector<float> lut(256 + 4000);
   for (int i = 0; i < 256; i++) {
@@ -676,6 +677,8 @@ void pcdb_destroy(pcdb_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < 8; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->ev_knn[i]) cudaEventDestroy(ctx->ev_knn[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -918,6 +921,14 @@ int pcdb_compute_features(pcdb_ctx* ctx, const float* xyz, const float* normals,
   return PCDB_OK;
 }
 
+static void record_sweep_times(pcdb_ctx* ctx) {
+  ctx->stats.knn_bound_sweep_ms = ctx->stats.knn_pool_sweep_ms = 0;
+  if (!ctx->knn_sweep_events_valid) return;
+  float a = 0, b = 0;
+  if (cudaEventElapsedTime(&a, ctx->ev_knn[0], ctx->ev_knn[1]) == cudaSuccess) ctx->stats.knn_bound_sweep_ms = a;
+  if (cudaEventElapsedTime(&b, ctx->ev_knn[2], ctx->ev_knn[3]) == cudaSuccess) ctx->stats.knn_pool_sweep_ms = b;
+}
+
 int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t dist_type, int32_t mode,
              int32_t* idx_out, float* dist_out, int32_t* count_out) {
   if (!ctx) return PCDB_E_INVALID;
@@ -931,6 +942,7 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
   PCDB_TRY(upload(ctx, w.feat_desc, queries, sizeof(float) * (size_t)ctx->cb.D * Q));
   ctx->comm_events_valid = false;
   ctx->gemm_events_valid = false;
+  ctx->knn_sweep_events_valid = false;
   PCDB_TRY(activate(ctx, w.feat_desc.as<float>(), Q, k, dist_type, mode, ctx->prm.use_distance_ratio != 0,
                     ctx->prm.distance_ratio_threshold));
   ctx->stats.comm_ms = 0;
@@ -944,6 +956,7 @@ int pcdb_knn(pcdb_ctx* ctx, const float* queries, int64_t Q, int32_t k, int32_t 
     float g = 0;
     if (cudaEventElapsedTime(&g, ctx->ev[5], ctx->ev[6]) == cudaSuccess) ctx->stats.knn_gemm_ms = g;
   }
+  record_sweep_times(ctx);
   return PCDB_OK;
 }
 
@@ -1069,6 +1082,7 @@ int pcdb_get_maxima(pcdb_ctx* ctx, pcdb_maximum* maxima_out, int64_t* maxima_off
 }
 
 static void record_stage_times(pcdb_ctx* ctx, const float t[4]) {
+  record_sweep_times(ctx);
   ctx->stats.features_ms = t[0];
   ctx->stats.knn_ms = t[1];
   ctx->stats.votes_ms = t[2];
@@ -1092,6 +1106,7 @@ static int classify_core(pcdb_ctx* ctx, int B, int64_t P, bool has_rgb, bool has
   const int D = p.feature_type == PCDB_FEATURE_CSHOT ? PCDB_CSHOT_DIM : PCDB_SHOT_DIM;
   if (ctx->cb.D != D) return ctx->fail(PCDB_E_INVALID, "codebook dimension %d does not match Features.Type (%d)", ctx->cb.D, D);
   ctx->gemm_events_valid = false;
+  ctx->knn_sweep_events_valid = false;
   PCDB_CUDA(cudaEventRecord(ctx->ev[7], st));
   if (B == 0) {  // nothing of this rank's own to classify; a sharded codebook still needs its rows searched
     for (int i = 0; i < 2; ++i) PCDB_CUDA(cudaEventRecord(ctx->ev[i], st));

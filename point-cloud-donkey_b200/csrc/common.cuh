@@ -141,6 +141,8 @@ struct pcdb_ctx {
   struct PendingRead { void* dst; size_t off, bytes; };
   std::vector<PendingRead> pending_reads;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_knn[4] = {nullptr, nullptr, nullptr, nullptr};  // bound sweep begin/end, pooled sweep begin/end
+  bool knn_sweep_events_valid = false;
 
   int fail(int code, const char* fmt, ...) {
     char buf[1024];

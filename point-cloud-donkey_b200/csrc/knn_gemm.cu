@@ -998,14 +998,13 @@ __global__ void __launch_bounds__(256) k_cov_tile(const float* __restrict__ x, l
   }
   cov[(size_t)(ta + i) * D + tb + j] = acc / (double)n;
 }
-// y = P^T (x - mu): rows x [n][D] -> y [n][d]; CTA = 64 rows x d columns, K staged 16 at a time; DC = d / 32
+// y = P^T (x - mu): rows x [n][D] -> y [n][d]; CTA = 64 rows x d columns, K staged 16 at a time; DC = ceil(d / 32)
 template <int DC>
-__global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, long long n, int D,
+__global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, long long n, int D, int d,
                                                  const float* __restrict__ mean, const float* __restrict__ basis,
                                                  float* __restrict__ y) {
-  constexpr int d = DC * 32;
   __shared__ float sx[16][65];
-  __shared__ float sp[16][d];
+  __shared__ float sp[16][DC * 32];
   const long long r0 = (long long)blockIdx.x * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty: 8 row groups of 8, tx: columns tx + 32 c
   float acc[8][DC];
@@ -1019,9 +1018,9 @@ __global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, lo
       const long long r = r0 + rr;
       sx[kk][rr] = (r < n && k0 + kk < D) ? __fsub_rn(x[r * D + k0 + kk], mean[k0 + kk]) : 0.f;
     }
-    for (int e = threadIdx.x; e < 16 * d; e += 256) {
-      const int kk = e / d, c = e % d;
-      sp[kk][c] = k0 + kk < D ? basis[(size_t)(k0 + kk) * d + c] : 0.f;
+    for (int e = threadIdx.x; e < 16 * DC * 32; e += 256) {
+      const int kk = e / (DC * 32), c = e % (DC * 32);
+      sp[kk][c] = (k0 + kk < D && c < d) ? basis[(size_t)(k0 + kk) * d + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -1043,7 +1042,8 @@ __global__ void __launch_bounds__(256) k_project(const float* __restrict__ x, lo
     const long long r = r0 + ty * 8 + a;
     if (r < n)
 #pragma unroll
-      for (int c = 0; c < DC; ++c) y[r * d + tx + 32 * c] = acc[a][c];
+      for (int c = 0; c < DC; ++c)
+        if (tx + 32 * c < d) y[r * d + tx + 32 * c] = acc[a][c];
   }
 }
 // |x - mu| per row, rounded up (one warp per row); out_max (optional): maximum over the rows
@@ -1173,17 +1173,19 @@ void host_jacobi(std::vector<double>& A, int n, std::vector<double>& V, int swee
 }
 
 template <int DC>
-int launch_project(pcdb_ctx* ctx, const float* x, int64_t n, int D, const float* mean, const float* basis, float* y) {
-  k_project<DC><<<cdiv(n, 64), 256, 0, ctx->stream>>>(x, n, D, mean, basis, y);
+int launch_project(pcdb_ctx* ctx, const float* x, int64_t n, int D, int d, const float* mean, const float* basis,
+                   float* y) {
+  k_project<DC><<<cdiv(n, 64), 256, 0, ctx->stream>>>(x, n, D, d, mean, basis, y);
   PCDB_LAUNCH_CHECK();
   return PCDB_OK;
 }
 int project_rows(pcdb_ctx* ctx, const float* x, int64_t n, int D, int d, const float* mean, const float* basis, float* y) {
-  switch (d / 32) {
-    case 2: return launch_project<2>(ctx, x, n, D, mean, basis, y);
-    case 3: return launch_project<3>(ctx, x, n, D, mean, basis, y);
-    case 4: return launch_project<4>(ctx, x, n, D, mean, basis, y);
-    case 5: return launch_project<5>(ctx, x, n, D, mean, basis, y);
+  switch ((d + 31) / 32) {
+    case 2: return launch_project<2>(ctx, x, n, D, d, mean, basis, y);
+    case 3: return launch_project<3>(ctx, x, n, D, d, mean, basis, y);
+    case 4: return launch_project<4>(ctx, x, n, D, d, mean, basis, y);
+    case 5: return launch_project<5>(ctx, x, n, D, d, mean, basis, y);
+    case 6: return launch_project<6>(ctx, x, n, D, d, mean, basis, y);
   }
   return ctx->fail(PCDB_E_INVALID, "PCA pre-filter: unsupported dimension %d", d);
 }
@@ -1200,9 +1202,9 @@ int pca_prepare(pcdb_ctx* ctx) {
   GemmState* gs = state_of(ctx);
   PcaFilter& pf = gs->pca;
   pf.release();
-  const int d = env_int("PCDB_GEMM_PCA_D", 128), f = env_int("PCDB_GEMM_SAMPLE", 16);
-  const int64_t min_rows = env_int("PCDB_GEMM_PCA_MIN_ROWS", 262144);
-  if (!env_int("PCDB_GEMM_PCA", 1) || cb.N < min_rows || cb.D % 16 != 0 || d % 32 != 0 || d < 64 || d > 160 ||
+  const int d = env_int("PCDB_GEMM_PCA_D", 112), f = env_int("PCDB_GEMM_SAMPLE", 16);
+  const int64_t min_rows = env_int("PCDB_GEMM_PCA_MIN_ROWS", 131072);
+  if (!env_int("PCDB_GEMM_PCA", 1) || cb.N < min_rows || cb.D % 16 != 0 || d % 16 != 0 || d < 48 || d > 192 ||
       d + K_AUG >= cb.D || f < 2 || (cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX)
     return PCDB_OK;
   const int D = cb.D;
@@ -1457,11 +1459,17 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
   k_fill_f32<<<cdiv(Q, 256), 256, 0, st>>>(g.bound, Q, INFINITY);
   PCDB_LAUNCH_CHECK();
   cudaEvent_t e0 = ctx->ev[5], e1 = ctx->ev[6];
-  if (depth == 0) PCDB_CUDA(cudaEventRecord(e0, st));
+  if (depth == 0) {
+    PCDB_CUDA(cudaEventRecord(e0, st));
+    PCDB_CUDA(cudaEventRecord(ctx->ev_knn[0], st));
+    ctx->stats.knn_prefilter_dim = pca ? pf.d : 0;
+    ctx->stats.knn_prefilter_sample_rows = pca ? pf.sample.n : 0;
+  }
   if (a_res)
     PCDB_TRY((launch_gemm_kt<true>(ctx, K, map_a, op.map_b, g, grid)));
   else
     PCDB_TRY((launch_gemm_kt<false>(ctx, K, map_a, op.map_b, g, grid)));
+  if (depth == 0) PCDB_CUDA(cudaEventRecord(ctx->ev_knn[1], st));
   if (!chi && !pca && depth == 0) {
     PCDB_CUDA(cudaEventRecord(e1, st));
     ctx->gemm_events_valid = true;
@@ -1548,10 +1556,15 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
       g2.pool_cap = want;
       PCDB_CUDA(cudaMemsetAsync(pool_count, 0, 8, st));
       PCDB_CUDA(cudaMemsetAsync(gs->q_cnt.p, 0, sizeof(int) * (Q + 1), st));
+      if (depth == 0) PCDB_CUDA(cudaEventRecord(ctx->ev_knn[2], st));
       if (sp2.a_res)
         PCDB_TRY((launch_gemm<true, 1, true>(ctx, map_a2, op2->map_b, g2, sp2.grid)));
       else
         PCDB_TRY((launch_gemm<false, 1, true>(ctx, map_a2, op2->map_b, g2, sp2.grid)));
+      if (depth == 0) {
+        PCDB_CUDA(cudaEventRecord(ctx->ev_knn[3], st));
+        ctx->knn_sweep_events_valid = true;
+      }
       PCDB_TRY(pcdb_read_small(ctx, &total, pool_count, 8));
       PCDB_TRY(pcdb_sync_reads(ctx));
       if ((int64_t)total <= gs->pool_cap) break;
@@ -1584,7 +1597,8 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
   PCDB_TRY(pcdb_read_small(ctx, &n_eval, w.scalars.as<char>() + 64, sizeof(n_eval)));
   PCDB_TRY(pcdb_sync_reads(ctx));
   if (!chi && !pca) ctx->stats.knn_candidates += (int64_t)n_eval;
-  if (!pca) ctx->stats.knn_fallback_queries += n_fb;  // (with the pre-filter: queries handed to the plain sweep)
+  if (!pca) ctx->stats.knn_fallback_queries += n_fb;
+  else ctx->stats.knn_prefilter_resweep_queries += n_fb;  // handed to the plain sweep, not to the exact scan
   if (n_fb > 0) {
     FallbackBufs& fb = gs->fb[depth ? 1 : 0];
     PCDB_CUDA(fb.q.ensure(sizeof(float) * (size_t)n_fb * D));

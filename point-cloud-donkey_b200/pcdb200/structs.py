@@ -148,7 +148,10 @@ class Stats(C.Structure):
             "knn_queries knn_candidates knn_fallback_queries kernel_launches"
         ).split()
     ] + [(n, C.c_double) for n in "features_ms knn_ms knn_gemm_ms votes_ms maxima_ms".split()] + [
-        ("comm_bytes", C.c_int64), ("comm_ms", C.c_double)]
+        ("comm_bytes", C.c_int64), ("comm_ms", C.c_double),
+        ("knn_bound_sweep_ms", C.c_double), ("knn_pool_sweep_ms", C.c_double),
+        ("knn_prefilter_dim", C.c_int64), ("knn_prefilter_sample_rows", C.c_int64),
+        ("knn_prefilter_resweep_queries", C.c_int64)]
 
 
 def ptr(a, ctype):

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), "libpcdb200.so does not export %s" % name
     assert sorted(api.SYMBOLS) == declared, "pcdb200/api.py binds a different symbol set than the header declares"
     lib.pcdb_abi_version.restype = C.c_int
-    assert lib.pcdb_abi_version() == 4
+    assert lib.pcdb_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header():
