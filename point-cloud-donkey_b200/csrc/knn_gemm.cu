@@ -65,6 +65,7 @@ constexpr int KB_RES_MAX = 6;             // resident K-blocks (D + 16 <= 384)
 constexpr int K_AUG = 16;                 // extra K columns carrying the |c|^2 term (one UMMA_K step)
 constexpr int CAND_CAP_MAX = 256;         // private staging entries per epilogue thread (64 / 128 / 256 by K)
 constexpr unsigned TMEM_COLS = 512;
+constexpr int STASH_SLOTS = 2;            // parked chunks per epilogue thread and tile (POOL): 8 warps x 2 x 4 KB = 4 operand boxes
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -235,6 +236,8 @@ struct GemmArgs {
   long long pool_cap;
   int* q_cnt;            // [Q] pool entries per query (for the CSR the re-rank works on)
   int q_cap;             // > 0: a query whose pool entries exceed this stops appending (the host re-searches it exactly)
+  int stash;             // POOL, <= 2 resident K blocks: chunks with a passing column are parked in shared memory and
+                         // picked apart AFTER the accumulator has been handed back (see the epilogue)
 };
 
 // moves a thread's staged candidates into the global pool: one returning atomic per flush
@@ -421,6 +424,43 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // 64 KB stage per tile pair on a kernel that already sits on the L2->SM limit), so |c|^2 is added here from a
       // shared-memory staged tile, one column per epilogue thread, software-prefetched.
       const int epi_tid = (warp - 4) * 32 + lane;
+      // POOL with a short K (the projected sweep: 8 MMAs per tile, 1024 clk): the accumulator has to go back to the MMA
+      // warp within one tile time, but picking a passing chunk apart (32 compares, mask, appends) costs ONE lane ~350 clk
+      // while its 31 siblings wait, and with ~80 pooled rows per query some warp of the pair meets such a chunk in nearly
+      // every tile — the hand-over then waits for the slowest of 16 warps.  So a lane that sees a passing chunk only
+      // PARKS its 32 values (8 x 16-byte stores into the unused resident-operand boxes 2..5, lane-interleaved: no bank
+      // conflicts whichever lanes hit) and takes them apart after its warp has arrived on tmem_empty.
+      const bool stash_on = POOL && A_RES && g.stash != 0 && KB <= 2;
+      float4* const stash = reinterpret_cast<float4*>(a_res + 2 * A_BOX_BYTES) + (warp - 4) * (STASH_SLOTS * 8 * 32) + lane;
+      int n_stash = 0, stash_nb[STASH_SLOTS];
+#pragma unroll
+      for (int i = 0; i < STASH_SLOTS; ++i) stash_nb[i] = 0;
+      // one passing chunk -> private list: the passing columns as a bit mask (32 independent compares), then one append
+      // per set bit (a column-by-column scan is ~300 dependent instructions of ONE warp while its 7 siblings and the MMA
+      // pipe wait for the accumulator: measured 0.5 ms per pooled row per query at Q = 88 k)
+      auto pool_take = [&](const unsigned (&v)[32], int n_base) {
+        unsigned pm = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pm |= (__uint_as_float(v[e]) <= thr ? 1u : 0u) << e;
+        if (!active) pm = 0;
+        if (n_base + 32 > g.N) pm &= n_base < g.N ? (0xffffffffu >> (32 - (int)(g.N - n_base))) : 0u;
+        while (pm) {
+          const int e = __ffs(pm) - 1;
+          pm &= pm - 1;
+          if (cnt < stage_cap) {
+            stage[cnt] = make_int2(n_base + e, 0);
+            ++cnt;
+          } else if (g.q_cap > 0) {  // a full private list inside ONE unit: the query is hopeless
+            hopeless = true;
+            thr = __int_as_float(0xff800000);
+            pm = 0;
+          } else {
+            pool_flush(g, row, stage, cnt);
+            stage[0] = make_int2(n_base + e, 0);
+            cnt = 1;
+          }
+        }
+      };
       float cn_next = 0.f;
       if (!A_RES) cn_next = __ldg(g.cnorm + (size_t)t0 * BN + epi_tid);
       for (int t = t0; t < t1; ++t) {
@@ -459,29 +499,16 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     if (mn <= thr) {                                                                               \
       const int n_base = t * BN + col0 + (C) * 32;                                                 \
       if (POOL) {                                                                                  \
-        /* the passing columns as a bit mask (32 independent compares), then one append per set bit: a */ \
-        /* column-by-column scan is ~300 dependent instructions of ONE warp while its 7 siblings and   */ \
-        /* the MMA pipe wait for the accumulator (measured 0.5 ms per pooled row per query at Q = 88 k) */ \
-        unsigned pm = 0;                                                                           \
-        _Pragma("unroll") for (int e = 0; e < 32; ++e)                                             \
-          pm |= (__uint_as_float(REG[e]) <= thr ? 1u : 0u) << e;                                   \
-        if (!active) pm = 0;                                                                       \
-        if (n_base + 32 > g.N) pm &= n_base < g.N ? (0xffffffffu >> (32 - (int)(g.N - n_base))) : 0u; \
-        while (pm) {                                                                               \
-          const int e = __ffs(pm) - 1;                                                             \
-          pm &= pm - 1;                                                                            \
-          if (cnt < stage_cap) {                                                                   \
-            stage[cnt] = make_int2(n_base + e, 0);                                                 \
-            ++cnt;                                                                                 \
-          } else if (g.q_cap > 0) { /* a full private list inside ONE unit: the query is hopeless */ \
-            hopeless = true;                                                                       \
-            thr = __int_as_float(0xff800000);                                                      \
-            pm = 0;                                                                                \
-          } else {                                                                                 \
-            pool_flush(g, row, stage, cnt);                                                        \
-            stage[0] = make_int2(n_base + e, 0);                                                   \
-            cnt = 1;                                                                               \
-          }                                                                                        \
+        if (stash_on && n_stash < STASH_SLOTS) {                                                   \
+          float4* sp = stash + n_stash * (8 * 32);                                                 \
+          _Pragma("unroll") for (int j4 = 0; j4 < 8; ++j4)                                         \
+            sp[j4 * 32] = make_float4(__uint_as_float(REG[j4 * 4 + 0]), __uint_as_float(REG[j4 * 4 + 1]), \
+                                      __uint_as_float(REG[j4 * 4 + 2]), __uint_as_float(REG[j4 * 4 + 3])); \
+          _Pragma("unroll") for (int i = 0; i < STASH_SLOTS; ++i)                                  \
+            if (i == n_stash) stash_nb[i] = n_base;                                                \
+          ++n_stash;                                                                               \
+        } else {                                                                                   \
+          pool_take(REG, n_base);                                                                  \
         }                                                                                          \
       } else {                                                                                     \
         _Pragma("unroll") for (int e = 0; e < 32; ++e) {                                           \
@@ -517,6 +544,24 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
+        }
+        if (POOL && n_stash > 0) {  // parked chunks of this tile, off the accumulator's critical path
+#pragma unroll
+          for (int i = 0; i < STASH_SLOTS; ++i)
+            if (i < n_stash) {
+              unsigned v[32];
+              const float4* sp = stash + i * (8 * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 x = sp[j4 * 32];
+                v[j4 * 4 + 0] = __float_as_uint(x.x);
+                v[j4 * 4 + 1] = __float_as_uint(x.y);
+                v[j4 * 4 + 2] = __float_as_uint(x.z);
+                v[j4 * 4 + 3] = __float_as_uint(x.w);
+              }
+              pool_take(v, stash_nb[i]);
+            }
+          n_stash = 0;
         }
       }
       if (POOL) {
@@ -971,7 +1016,7 @@ int prepare_operand(pcdb_ctx* ctx, const float* rows_d, int64_t n, int D, bool s
 // ---- PCA pre-filter set-up (one-off, at codebook upload) ---------------------------------------------------------
 // column sums of n rows taken with a stride (fp64 atomics on D accumulators)
 __global__ void k_col_sums(const float* __restrict__ x, long long n, long long stride, int D, double* sums) {
-  const int j = threadIdx.x;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;  // grid.y covers the columns in blocks of blockDim.x
   double acc = 0;
   for (long long r = blockIdx.x; r < n; r += gridDim.x)
     if (j < D) acc += (double)x[r * stride * D + j];
@@ -1172,6 +1217,95 @@ void host_jacobi(std::vector<double>& A, int n, std::vector<double>& V, int swee
   }
 }
 
+// Leading d-dimensional invariant subspace of a symmetric n x n matrix (fp64) for LONG rows (CSHOT: n = 1344, where
+// the cyclic Jacobi above would cost minutes): block power iteration on p = d + 16 vectors with modified Gram-Schmidt,
+// then Rayleigh-Ritz on the p x p projection.  Only the SPAN matters for how many rows the filter keeps, and only the
+// orthonormality of the result for its soundness (re-checked in fp64 on the fp32 values by the caller).
+// out: d basis vectors of length n, stored by rows.
+void host_subspace(const std::vector<double>& A, int n, int d, std::vector<double>& out) {
+  const int p = std::min(n, d + 16);
+  std::vector<double> X((size_t)n * p), Y((size_t)n * p);
+  unsigned long long rng = 0x9e3779b97f4a7c15ull;
+  for (double& v : X) {
+    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+    v = (double)(int)(rng >> 40) / 8388608.0 - 1.0;
+  }
+  auto orthonormalise = [&](std::vector<double>& M) {  // columns of M [n][p], two Gram-Schmidt passes
+    for (int pass = 0; pass < 2; ++pass)
+      for (int c = 0; c < p; ++c) {
+        for (int b = 0; b < c; ++b) {
+          double dot = 0;
+          for (int i = 0; i < n; ++i) dot += M[(size_t)i * p + c] * M[(size_t)i * p + b];
+          for (int i = 0; i < n; ++i) M[(size_t)i * p + c] -= dot * M[(size_t)i * p + b];
+        }
+        double nn = 0;
+        for (int i = 0; i < n; ++i) nn += M[(size_t)i * p + c] * M[(size_t)i * p + c];
+        nn = std::sqrt(nn);
+        if (!(nn > 1e-300)) {  // degenerate direction: replace by a unit vector (orthogonalised on the second pass)
+          for (int i = 0; i < n; ++i) M[(size_t)i * p + c] = (i == c % n) ? 1.0 : 0.0;
+        } else {
+          for (int i = 0; i < n; ++i) M[(size_t)i * p + c] /= nn;
+        }
+      }
+  };
+  auto multiply = [&](const std::vector<double>& Xin, std::vector<double>& Yout) {  // Y = A X
+    std::fill(Yout.begin(), Yout.end(), 0.0);
+    for (int i = 0; i < n; ++i) {
+      double* y = &Yout[(size_t)i * p];
+      for (int k = 0; k < n; ++k) {
+        const double a = A[(size_t)i * n + k];
+        const double* x = &Xin[(size_t)k * p];
+        for (int c = 0; c < p; ++c) y[c] += a * x[c];
+      }
+    }
+  };
+  orthonormalise(X);
+  for (int it = 0; it < 12; ++it) {
+    multiply(X, Y);
+    X.swap(Y);
+    orthonormalise(X);
+  }
+  // Rayleigh-Ritz: T = X^T A X (p x p), its eigenvectors rotate X onto the best approximations inside the span
+  multiply(X, Y);
+  std::vector<double> T((size_t)p * p, 0.0), W;
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < p; ++a) {
+      const double xa = X[(size_t)i * p + a];
+      for (int b = 0; b < p; ++b) T[(size_t)a * p + b] += xa * Y[(size_t)i * p + b];
+    }
+  for (int a = 0; a < p; ++a)
+    for (int b = a + 1; b < p; ++b) T[(size_t)a * p + b] = T[(size_t)b * p + a] = 0.5 * (T[(size_t)a * p + b] + T[(size_t)b * p + a]);
+  host_jacobi(T, p, W, 12);  // W by rows = eigenvectors of T, eigenvalues on the diagonal of T
+  std::vector<int> order(p);
+  for (int i = 0; i < p; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return T[(size_t)a * p + a] > T[(size_t)b * p + b]; });
+  out.assign((size_t)d * n, 0.0);
+  for (int c = 0; c < d; ++c) {
+    const double* w = &W[(size_t)order[c] * p];
+    for (int i = 0; i < n; ++i) {
+      double v = 0;
+      for (int a = 0; a < p; ++a) v += X[(size_t)i * p + a] * w[a];
+      out[(size_t)c * n + i] = v;
+    }
+  }
+  // one more Gram-Schmidt pass over the d result vectors (rows of out)
+  for (int pass = 0; pass < 2; ++pass)
+    for (int c = 0; c < d; ++c) {
+      double* vc = &out[(size_t)c * n];
+      for (int b = 0; b < c; ++b) {
+        const double* vb = &out[(size_t)b * n];
+        double dot = 0;
+        for (int i = 0; i < n; ++i) dot += vc[i] * vb[i];
+        for (int i = 0; i < n; ++i) vc[i] -= dot * vb[i];
+      }
+      double nn = 0;
+      for (int i = 0; i < n; ++i) nn += vc[i] * vc[i];
+      nn = std::sqrt(nn);
+      if (nn > 1e-300)
+        for (int i = 0; i < n; ++i) vc[i] /= nn;
+    }
+}
+
 template <int DC>
 int launch_project(pcdb_ctx* ctx, const float* x, int64_t n, int D, int d, const float* mean, const float* basis,
                    float* y) {
@@ -1205,8 +1339,11 @@ int pca_prepare(pcdb_ctx* ctx) {
   const int d = env_int("PCDB_GEMM_PCA_D", 112), f = env_int("PCDB_GEMM_SAMPLE", 16);
   const int64_t min_rows = env_int("PCDB_GEMM_PCA_MIN_ROWS", 131072);
   if (!env_int("PCDB_GEMM_PCA", 1) || cb.N < min_rows || cb.D % 16 != 0 || d % 16 != 0 || d < 48 || d > 192 ||
-      d + K_AUG >= cb.D || f < 2 || (cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX)
+      d + K_AUG >= cb.D || f < 2)
     return PCDB_OK;
+  // long rows (CSHOT-1344: streaming-query bound sweep over the sample, basis by block power iteration): opt-in until
+  // measured against the plain streaming sweep
+  if ((cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX && !env_int("PCDB_GEMM_PCA_WIDE", 0)) return PCDB_OK;
   const int D = cb.D;
   const float* words = cb.words.as<float>();
   // ---- mean and covariance of up to 65536 strided rows
@@ -1216,7 +1353,7 @@ int pca_prepare(pcdb_ctx* ctx) {
   PCDB_CUDA(dcov.ensure(sizeof(double) * (size_t)D * D));
   auto free_tmp = [&]() { dsum.release(); dcov.release(); };
   PCDB_CUDA(cudaMemsetAsync(dsum.p, 0, sizeof(double) * D, st));
-  k_col_sums<<<256, ((D + 31) / 32) * 32, 0, st>>>(words, n_cov, stride, D, dsum.as<double>());
+  k_col_sums<<<dim3(256, (D + 255) / 256), 256, 0, st>>>(words, n_cov, stride, D, dsum.as<double>());
   PCDB_LAUNCH_CHECK();
   std::vector<double> hmean(D);
   PCDB_CUDA(cudaMemcpyAsync(hmean.data(), dsum.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
@@ -1231,15 +1368,23 @@ int pca_prepare(pcdb_ctx* ctx) {
   free_tmp();
   for (double v : cov)
     if (!std::isfinite(v)) return PCDB_OK;  // non-finite codewords: no pre-filter
-  host_jacobi(cov, D, V, 8);
-  std::vector<int> order(D);
-  for (int i = 0; i < D; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return cov[(size_t)a * D + a] > cov[(size_t)b * D + b]; });
+  std::vector<double> lead;  // the d leading axes, by rows
+  if (D <= 512) {
+    host_jacobi(cov, D, V, 8);
+    std::vector<int> order(D);
+    for (int i = 0; i < D; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cov[(size_t)a * D + a] > cov[(size_t)b * D + b]; });
+    lead.resize((size_t)d * D);
+    for (int c = 0; c < d; ++c)
+      for (int k = 0; k < D; ++k) lead[(size_t)c * D + k] = V[(size_t)order[c] * D + k];
+  } else {
+    host_subspace(cov, D, d, lead);
+  }
   // basis [D][d] in fp32 + its orthonormality defect ||P^T P - I||_2 <= max row sum of |P^T P - I| (evaluated in fp64
   // on the fp32 values the device multiplies with)
   std::vector<float> hb((size_t)D * d), hm(D);
   for (int c = 0; c < d; ++c)
-    for (int k = 0; k < D; ++k) hb[(size_t)k * d + c] = (float)V[(size_t)order[c] * D + k];
+    for (int k = 0; k < D; ++k) hb[(size_t)k * d + c] = (float)lead[(size_t)c * D + k];
   double defect = 0;
   for (int a = 0; a < d; ++a) {
     double row = 0;
@@ -1407,7 +1552,8 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
   const int D = cb.D;
   PcaFilter& pf = gs->pca;
   static const int pca_min_q = env_int("PCDB_GEMM_PCA_MIN_Q", 8192);
-  const bool pca = !chi && depth == 0 && pf.ready && pf.sample.n > K && Q >= pca_min_q;
+  const bool pca = !chi && depth == 0 && pf.ready && pf.sample.n > K && Q >= pca_min_q &&
+                   !env_int("PCDB_GEMM_PCA_SKIP", 0);  // read per call: A/B runs against the plain sweep on one context
   GemmOperand& op = pca ? pf.sample : gs->op[chi ? 1 : 0];  // operand of the bound sweep
   // query side: fp16 copy + norms + margins
   const int aug = (D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;
@@ -1545,6 +1691,7 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
     g2.pool_count = pool_count;
     g2.q_cnt = gs->q_cnt.as<int>();
     g2.q_cap = pca ? q_cap_env : 0;
+    g2.stash = env_int("PCDB_GEMM_POOL_STASH", 1);  // 0: passing chunks are picked apart in place (read per call: A/B runs)
     unsigned long long total = 0;
     for (int attempt = 0;; ++attempt) {
       const int64_t want = std::max<int64_t>(gs->pool_cap, std::max<int64_t>((int64_t)1 << 22, Q * 64));
