@@ -429,7 +429,11 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // while its 31 siblings wait, and with ~80 pooled rows per query some warp of the pair meets such a chunk in nearly
       // every tile — the hand-over then waits for the slowest of 16 warps.  So a lane that sees a passing chunk only
       // PARKS its 32 values (8 x 16-byte stores into the unused resident-operand boxes 2..5, lane-interleaved: no bank
-      // conflicts whichever lanes hit) and takes them apart after its warp has arrived on tmem_empty.
+      // conflicts whichever lanes hit) and takes them apart after its warp has arrived on tmem_empty (pooled sweep at
+      // 115 rows per query: 67.7 -> 60.9 ms; with a threshold nothing passes the kernel takes 51 ms = 1300 clk per tile).
+      // Tried against that floor and rejected (profiles/r02_pool_variants_c3_*_rejected.json): sixteen epilogue warps
+      // with both tcgen05.ld of a warp in flight (floor unchanged: the epilogue's length is not what the hand-over waits
+      // for), and four N = 128 accumulators with three epilogue warp sets (2250 clk per tile).
       const bool stash_on = POOL && A_RES && g.stash != 0 && KB <= 2;
       float4* const stash = reinterpret_cast<float4*>(a_res + 2 * A_BOX_BYTES) + (warp - 4) * (STASH_SLOTS * 8 * 32) + lane;
       int n_stash = 0, stash_nb[STASH_SLOTS];
@@ -1341,9 +1345,9 @@ int pca_prepare(pcdb_ctx* ctx) {
   if (!env_int("PCDB_GEMM_PCA", 1) || cb.N < min_rows || cb.D % 16 != 0 || d % 16 != 0 || d < 48 || d > 192 ||
       d + K_AUG >= cb.D || f < 2)
     return PCDB_OK;
-  // long rows (CSHOT-1344: streaming-query bound sweep over the sample, basis by block power iteration): opt-in until
-  // measured against the plain streaming sweep
-  if ((cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX && !env_int("PCDB_GEMM_PCA_WIDE", 0)) return PCDB_OK;
+  // long rows (CSHOT-1344: streaming-query bound sweep over the sample, basis by block power iteration); measured at
+  // 1.07 M x 1344, 104 k queries: sweeps 33 ms against 172 ms for the plain streaming sweep (PCDB_GEMM_PCA_WIDE=0)
+  if ((cb.D + K_AUG + BK - 1) / BK > KB_RES_MAX && !env_int("PCDB_GEMM_PCA_WIDE", 1)) return PCDB_OK;
   const int D = cb.D;
   const float* words = cb.words.as<float>();
   // ---- mean and covariance of up to 65536 strided rows

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """A/B runs of the PCA pre-filter on a descriptor codebook of 1.07 M words, one context, identical results required.
   c3 (SHOT-352, d = 112): the pooled sweep with the passing chunks parked in shared memory (PCDB_GEMM_POOL_STASH=1,
-     default) and picked apart in place (=0), each also with a threshold nothing passes (PCDB_EXP_POOL_NOTHR=1: the
-     kernel's floor), and the plain sweep (PCDB_GEMM_PCA_SKIP=1).
-  c4 (CSHOT-1344, PCDB_GEMM_PCA_WIDE=1: basis by block power iteration, streaming bound sweep over the sample): the
-     pre-filter against the plain streaming sweep.
+     default) and picked apart in place (=0), with a threshold nothing passes (PCDB_EXP_POOL_NOTHR=1: the kernel's
+     floor), and the plain sweep (PCDB_GEMM_PCA_SKIP=1).  (Two rejected kernel variants were measured with earlier
+     versions of this script: profiles/r02_pool_variants_c3_*_rejected.json.)
+  c4 (CSHOT-1344: basis by block power iteration, streaming bound sweep over the sample): the pre-filter against the
+     plain streaming sweep.
 Prints one JSON document.  usage: python tools/pool_variants.py [c3|c4] [test clouds]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,8 +13,6 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "point-cloud-don
 import numpy as np
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 n_test = int(sys.argv[2]) if len(sys.argv) > 2 else (1024 if wl == "c3" else 512)
-if wl == "c4":
-    os.environ["PCDB_GEMM_PCA_WIDE"] = "1"
 from pcdb200 import api
 from pcdb200.structs import KNN_GEMM
 import test_gpu_scale as tgs
@@ -23,14 +22,14 @@ out = {"workload": wl, "queries": int(Q.shape[0]), "words": int(cb.N), "D": int(
        "variants": []}
 ref = None
 if wl == "c3":
-    variants = [dict(PCDB_GEMM_POOL_STASH=1), dict(PCDB_GEMM_POOL_STASH=0), dict(PCDB_GEMM_POOL_STASH=1, PCDB_EXP_POOL_NOTHR=1),
-                dict(PCDB_GEMM_POOL_STASH=0, PCDB_EXP_POOL_NOTHR=1), dict(PCDB_GEMM_PCA_SKIP=1), dict(PCDB_GEMM_POOL_STASH=1)]
+    variants = [dict(), dict(PCDB_GEMM_POOL_STASH=0), dict(PCDB_EXP_POOL_NOTHR=1), dict(PCDB_GEMM_PCA_SKIP=1), dict()]
 else:
     variants = [dict(), dict(PCDB_GEMM_PCA_SKIP=1), dict()]
 KEYS = ("PCDB_GEMM_POOL_STASH", "PCDB_EXP_POOL_NOTHR", "PCDB_GEMM_PCA_SKIP")
+DEFAULTS = {"PCDB_GEMM_POOL_STASH": 1}
 for v in variants:
     for k in KEYS:
-        os.environ[k] = str(v.get(k, 1 if k == "PCDB_GEMM_POOL_STASH" else 0))
+        os.environ[k] = str(v.get(k, DEFAULTS.get(k, 0)))
     rec = {"env": v, "runs": []}
     for it in range(3):
         ctx.reset_stats()
