@@ -434,7 +434,7 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // Tried against that floor and rejected (profiles/r02_pool_variants_c3_*_rejected.json): sixteen epilogue warps
       // with both tcgen05.ld of a warp in flight (floor unchanged: the epilogue's length is not what the hand-over waits
       // for), and four N = 128 accumulators with three epilogue warp sets (2250 clk per tile).
-      const bool stash_on = POOL && A_RES && g.stash != 0 && KB <= 2;
+      const bool stash_on = POOL && A_RES && (g.stash & 1) != 0 && KB <= 2;
       float4* const stash = reinterpret_cast<float4*>(a_res + 2 * A_BOX_BYTES) + (warp - 4) * (STASH_SLOTS * 8 * 32) + lane;
       int n_stash = 0, stash_nb[STASH_SLOTS];
 #pragma unroll
@@ -442,10 +442,8 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       // one passing chunk -> private list: the passing columns as a bit mask (32 independent compares), then one append
       // per set bit (a column-by-column scan is ~300 dependent instructions of ONE warp while its 7 siblings and the MMA
       // pipe wait for the accumulator: measured 0.5 ms per pooled row per query at Q = 88 k)
-      auto pool_take = [&](const unsigned (&v)[32], int n_base) {
-        unsigned pm = 0;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) pm |= (__uint_as_float(v[e]) <= thr ? 1u : 0u) << e;
+      // passing columns of one chunk (bit e = column n_base + e) -> private list, one append per set bit
+      auto pool_append = [&](unsigned pm, int n_base) {
         if (!active) pm = 0;
         if (n_base + 32 > g.N) pm &= n_base < g.N ? (0xffffffffu >> (32 - (int)(g.N - n_base))) : 0u;
         while (pm) {
@@ -464,6 +462,15 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             cnt = 1;
           }
         }
+      };
+      // in place (no parking slot left, or long rows): the passing columns as a bit mask (32 independent compares — a
+      // column-by-column scan is ~300 dependent instructions of ONE warp while its 7 siblings and the MMA pipe wait for
+      // the accumulator: measured 0.5 ms per pooled row per query at Q = 88 k)
+      auto pool_take = [&](const unsigned (&v)[32], int n_base) {
+        unsigned pm = 0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pm |= (__uint_as_float(v[e]) <= thr ? 1u : 0u) << e;
+        pool_append(pm, n_base);
       };
       float cn_next = 0.f;
       if (!A_RES) cn_next = __ldg(g.cnorm + (size_t)t0 * BN + epi_tid);
@@ -532,24 +539,51 @@ k_knn_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       }                                                                                            \
     }                                                                                              \
   }
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; c += 2) {
-          tc_ld_wait();                                  // chunk c is in ra
-          tc_ld_32x32b_x32(taddr + (c + 1) * 32, rb);    // chunk c+1 in flight while c is filtered
-          PCDB_FILTER_CHUNK(ra, c)
+        auto hand_back = [&]() {  // the accumulator returns to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        };
+        if (POOL && A_RES && (g.stash & 2)) {
+          // short rows: the accumulator is handed back as soon as its last chunk sits in registers — the hand-over, not
+          // the length of the epilogue, paces this sweep (see the parking note above) — and that chunk is filtered after
           tc_ld_wait();
-          if (c + 2 < BN / 64) tc_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
-          PCDB_FILTER_CHUNK(rb, c + 1)
+          tc_ld_32x32b_x32(taddr + 32, rb);
+          PCDB_FILTER_CHUNK(ra, 0)
+          tc_ld_wait();
+          tc_ld_32x32b_x32(taddr + 64, ra);
+          PCDB_FILTER_CHUNK(rb, 1)
+          tc_ld_wait();
+          tc_ld_32x32b_x32(taddr + 96, rb);
+          PCDB_FILTER_CHUNK(ra, 2)
+          tc_ld_wait();
+          hand_back();
+          PCDB_FILTER_CHUNK(rb, 3)
+        } else if (POOL && (g.stash & 4)) {  // experiment: no read-back at all (what the hand-over alone costs)
+          tc_ld_wait();
+          hand_back();
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / 64; c += 2) {
+            tc_ld_wait();                                  // chunk c is in ra
+            tc_ld_32x32b_x32(taddr + (c + 1) * 32, rb);    // chunk c+1 in flight while c is filtered
+            PCDB_FILTER_CHUNK(ra, c)
+            tc_ld_wait();
+            if (c + 2 < BN / 64) tc_ld_32x32b_x32(taddr + (c + 2) * 32, ra);
+            PCDB_FILTER_CHUNK(rb, c + 1)
+          }
+          hand_back();
         }
 #undef PCDB_FILTER_CHUNK
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&bars->tmem_empty[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-        if (POOL && n_stash > 0) {  // parked chunks of this tile, off the accumulator's critical path
+        if (POOL && n_stash > 0) {
+          // parked chunks of this tile, off the accumulator's critical path.  (Taking them apart with the whole warp —
+          // lane e compares column e, one ballot is the mask — measured SLOWER than the owner lane doing it alone, 68.3
+          // against 59.9 ms per sweep: the owner's work runs in the shadow of its siblings' wait for the next
+          // accumulator, a whole-warp drain serialises in front of that wait.)
 #pragma unroll
           for (int i = 0; i < STASH_SLOTS; ++i)
             if (i < n_stash) {
@@ -1695,7 +1729,9 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
     g2.pool_count = pool_count;
     g2.q_cnt = gs->q_cnt.as<int>();
     g2.q_cap = pca ? q_cap_env : 0;
-    g2.stash = env_int("PCDB_GEMM_POOL_STASH", 1);  // 0: passing chunks are picked apart in place (read per call: A/B runs)
+    // bit 0: passing chunks are parked in shared memory, bit 1: early hand-over of the accumulator (short rows only),
+    // bit 2: experiment without read-back (wrong results; the hand-over's own cost).  Read per call: A/B runs.
+    g2.stash = env_int("PCDB_GEMM_POOL_STASH", 3);
     unsigned long long total = 0;
     for (int attempt = 0;; ++attempt) {
       const int64_t want = std::max<int64_t>(gs->pool_cap, std::max<int64_t>((int64_t)1 << 22, Q * 64));

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """A/B runs of the PCA pre-filter on a descriptor codebook of 1.07 M words, one context, identical results required.
-  c3 (SHOT-352, d = 112): the pooled sweep with the passing chunks parked in shared memory (PCDB_GEMM_POOL_STASH=1,
-     default) and picked apart in place (=0), with a threshold nothing passes (PCDB_EXP_POOL_NOTHR=1: the kernel's
-     floor), and the plain sweep (PCDB_GEMM_PCA_SKIP=1).  (Two rejected kernel variants were measured with earlier
+  c3 (SHOT-352, d = 112): the pooled sweep with PCDB_GEMM_POOL_STASH = 3 (default: passing chunks parked in shared
+     memory + early hand-over of the accumulator), 1 (parking only), 0 (neither), each also with a threshold nothing
+     passes (PCDB_EXP_POOL_NOTHR=1: the kernel's floor; with STASH=4 the epilogue does not even read the accumulator:
+     what the hand-over alone costs), and the plain sweep (PCDB_GEMM_PCA_SKIP=1).  (Two rejected kernel variants were measured with earlier
      versions of this script: profiles/r02_pool_variants_c3_*_rejected.json.)
   c4 (CSHOT-1344: basis by block power iteration, streaming bound sweep over the sample): the pre-filter against the
      plain streaming sweep.
@@ -22,11 +23,13 @@ out = {"workload": wl, "queries": int(Q.shape[0]), "words": int(cb.N), "D": int(
        "variants": []}
 ref = None
 if wl == "c3":
-    variants = [dict(), dict(PCDB_GEMM_POOL_STASH=0), dict(PCDB_EXP_POOL_NOTHR=1), dict(PCDB_GEMM_PCA_SKIP=1), dict()]
+    variants = [dict(), dict(PCDB_GEMM_POOL_STASH=1), dict(PCDB_GEMM_POOL_STASH=0), dict(PCDB_EXP_POOL_NOTHR=1),
+                dict(PCDB_GEMM_POOL_STASH=1, PCDB_EXP_POOL_NOTHR=1), dict(PCDB_GEMM_POOL_STASH=4, PCDB_EXP_POOL_NOTHR=1),
+                dict(PCDB_GEMM_PCA_SKIP=1), dict()]
 else:
     variants = [dict(), dict(PCDB_GEMM_PCA_SKIP=1), dict()]
 KEYS = ("PCDB_GEMM_POOL_STASH", "PCDB_EXP_POOL_NOTHR", "PCDB_GEMM_PCA_SKIP")
-DEFAULTS = {"PCDB_GEMM_POOL_STASH": 1}
+DEFAULTS = {"PCDB_GEMM_POOL_STASH": 3}
 for v in variants:
     for k in KEYS:
         os.environ[k] = str(v.get(k, DEFAULTS.get(k, 0)))
@@ -40,7 +43,7 @@ for v in variants:
                             "gemm_ms": round(st["knn_gemm_ms"], 3), "bound_sweep_ms": round(st["knn_bound_sweep_ms"], 3),
                             "pool_sweep_ms": round(st["knn_pool_sweep_ms"], 3), "pooled_per_query": round(st["knn_candidates"] / Q.shape[0], 2),
                             "resweep_queries": int(st["knn_prefilter_resweep_queries"]), "prefilter_dim": int(st["knn_prefilter_dim"])})
-    if not v.get("PCDB_EXP_POOL_NOTHR"):
+    if not v.get("PCDB_EXP_POOL_NOTHR") and v.get("PCDB_GEMM_POOL_STASH", 3) != 4:
         if ref is None:
             ref = r
         rec["identical_to_first_variant"] = bool(np.array_equal(ref[0], r[0]) and np.array_equal(ref[1].view(np.uint32), r[1].view(np.uint32)) and np.array_equal(ref[2], r[2]))
