@@ -908,6 +908,10 @@ struct PcaFilter {
   double orth_defect = 0;  // bound on ||P^T P - I||_2
   float eta_c = 0;         // bound on |fl(y_c) - y_c| over the codebook (fp32 projection rounding)
   float mean_norm = 0;
+  // Back-off: a batch whose queries mostly run past their pool cap (scene clutter far from every codeword: C5 sent 73 %
+  // of its queries to the plain sweep after paying for both pre-filter sweeps) switches the filter off for the next
+  // `backoff` eligible batches, doubling up to 256 while retries keep failing; results are exact either way.
+  int backoff = 0, backoff_left = 0;
   // per batch
   DevBuf yq, yq_h, rnorm_q, qn2p, qnormp, qerrp, epsp, marginp;
   void release() {
@@ -916,6 +920,7 @@ struct PcaFilter {
     DevBuf* all[] = {&s2g, &basis, &mean, &yq, &yq_h, &rnorm_q, &qn2p, &qnormp, &qerrp, &epsp, &marginp};
     for (DevBuf* b : all) b->release();
     ready = false;
+    backoff = backoff_left = 0;
   }
 };
 
@@ -1590,8 +1595,12 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
   const int D = cb.D;
   PcaFilter& pf = gs->pca;
   static const int pca_min_q = env_int("PCDB_GEMM_PCA_MIN_Q", 8192);
-  const bool pca = !chi && depth == 0 && pf.ready && pf.sample.n > K && Q >= pca_min_q &&
-                   !env_int("PCDB_GEMM_PCA_SKIP", 0);  // read per call: A/B runs against the plain sweep on one context
+  bool pca = !chi && depth == 0 && pf.ready && pf.sample.n > K && Q >= pca_min_q &&
+             !env_int("PCDB_GEMM_PCA_SKIP", 0);  // read per call: A/B runs against the plain sweep on one context
+  if (pca && pf.backoff_left > 0) {  // recent batches overflowed their pools: plain sweep for now
+    --pf.backoff_left;
+    pca = false;
+  }
   GemmOperand& op = pca ? pf.sample : gs->op[chi ? 1 : 0];  // operand of the bound sweep
   // query side: fp16 copy + norms + margins
   const int aug = (D + K_AUG + BK - 1) / BK <= KB_RES_MAX ? 1 : 0;
@@ -1786,6 +1795,15 @@ int knn_gemm_impl(pcdb_ctx* ctx, const float* queries_d, int64_t Q, int k, int d
   if (!chi && !pca) ctx->stats.knn_candidates += (int64_t)n_eval;
   if (!pca) ctx->stats.knn_fallback_queries += n_fb;
   else ctx->stats.knn_prefilter_resweep_queries += n_fb;  // handed to the plain sweep, not to the exact scan
+  if (pca) {
+    static const int backoff_env = env_int("PCDB_GEMM_PCA_BACKOFF", 1);
+    if (backoff_env && (int64_t)n_fb * 4 > Q) {
+      pf.backoff = std::min(256, std::max(16, 2 * pf.backoff));
+      pf.backoff_left = pf.backoff;
+    } else {
+      pf.backoff = 0;
+    }
+  }
   if (n_fb > 0) {
     FallbackBufs& fb = gs->fb[depth ? 1 : 0];
     PCDB_CUDA(fb.q.ensure(sizeof(float) * (size_t)n_fb * D));

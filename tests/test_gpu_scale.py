@@ -103,9 +103,22 @@ def test_c3_headline_scale_gemm_equals_scan(api, orc):
 
 
 def test_c4_headline_scale_gemm_equals_scan(api, orc):
-    ctx, prm, cb, Q = _descriptor_codebook(api, "c4", 1_070_000, 12)
-    assert cb.N >= 1_000_000 and Q.shape[0] >= 2_000 and Q.shape[1] == 1344
-    Q = Q[:4096]
+    ctx, prm, cb, Q = _descriptor_codebook(api, "c4", 1_070_000, 56)
+    assert cb.N >= 1_000_000 and Q.shape[0] >= 8_192 and Q.shape[1] == 1344
+    # >= 8192 queries: the PCA pre-filter for long rows (basis by block power iteration, streaming bound sweep over the
+    # sample, pooled sweep over the 112-dimensional projections) against the exact scan
+    Qa = Q[:10_240]
+    ctx.reset_stats()
+    aa = ctx.knn(Qa, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
+    sta = ctx.stats()
+    ba = ctx.knn(Qa, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
+    assert _same(aa, ba), "%d of %d rows differ (pre-filter)" % ((aa[0] != ba[0]).sum(), aa[0].size)
+    if os.environ.get("PCDB_GEMM_PCA", "1") != "0" and os.environ.get("PCDB_GEMM_PCA_WIDE", "1") != "0":
+        assert sta["knn_prefilter_dim"] > 0 and sta["knn_candidates"] / Qa.shape[0] > 5
+    a2 = ctx.knn(Qa[:8_500], k=2, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)   # the pre-filter with K = 2
+    b2 = ctx.knn(Qa[:8_500], k=2, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
+    assert _same(a2, b2)
+    Q = Q[:4096]                                                             # few queries: the plain streaming sweep
     a = ctx.knn(Q, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_GEMM)
     b = ctx.knn(Q, k=1, dist_type=DIST_EUCLIDEAN, mode=KNN_SCAN)
     assert _same(a, b), "%d of %d rows differ" % ((a[0] != b[0]).sum(), a[0].size)
@@ -117,6 +130,8 @@ def test_c4_headline_scale_gemm_equals_scan(api, orc):
     m = orc.Model(prm, cb)
     o = m.knn(Q[:8], k=1, dist_type=DIST_EUCLIDEAN)
     assert np.array_equal(a[0][:8], o[0]) and np.array_equal(a[1][:8].view(np.uint32), o[1].view(np.uint32))
-    print("C4 scale: %d queries x %d words x 1344; chi^2 pooled candidates/query %.1f (fallback %d)"
-          % (Q.shape[0], cb.N, stc["knn_candidates"] / 2048, stc["knn_fallback_queries"]))
+    print("C4 scale: %d queries x %d words x 1344 (pre-filter: %d queries, %.1f pooled rows per query, %d swept again); "
+          "chi^2 pooled candidates/query %.1f (fallback %d)"
+          % (Q.shape[0], cb.N, Qa.shape[0], sta["knn_candidates"] / Qa.shape[0], sta["knn_prefilter_resweep_queries"],
+             stc["knn_candidates"] / 2048, stc["knn_fallback_queries"]))
     ctx.close()
