@@ -285,6 +285,11 @@ def sharded_legs(args, rank, world, local_rank, stream, dist, torch, api):
         ctx = api.Context(device=local_rank)
         ctx.set_stream(stream.cuda_stream)
         wl, prm, cb = build_world("c4", args.words, ctx, rank_log=(rank == 0))
+        # rows dealt cyclically over the shards (sharded.interleave_codebook: training appends the codewords class by
+        # class; a contiguous shard would hold a few classes and overflow the pre-filter's pools for all the others);
+        # the replicated arm below runs on the very same table
+        cb, _ = sharded.interleave_codebook(cb, world)
+        ctx.set_codebook(cb)
         batch = args.shard_batch
         x, n, c, o, _ = test_batch(wl, batch, rank, 0)
         dx, dn, dc = torch.from_numpy(x).cuda(), torch.from_numpy(n).cuda(), torch.from_numpy(c.astype(np.int32)).cuda()
@@ -319,7 +324,7 @@ def sharded_legs(args, rank, world, local_rank, stream, dist, torch, api):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         q_local = st_sh["n_features"] / steps
         out["sharded_codebook"] = {
-            "workload": "C4 Washington-shaped CSHOT-1344, N=%d codewords row-sharded over %d GPUs (%d rows = %.2f GB "
+            "workload": "C4 Washington-shaped CSHOT-1344, N=%d codewords, rows dealt cyclically over %d GPUs (%d rows = %.2f GB "
                         "fp32 + %.2f GB fp16 per GPU instead of %.2f + %.2f), vote tables replicated, %d clouds per GPU "
                         "per step" % (cb.N, world, hi - lo, (hi - lo) * cb.D * 4 / 1e9, (hi - lo) * cb.D * 2 / 1e9,
                                       cb.N * cb.D * 4 / 1e9, cb.N * cb.D * 2 / 1e9, batch),

@@ -176,3 +176,46 @@ def test_shard_bounds():
     from pcdb200 import sharded
     assert sharded.shard_bounds(10, 4) == [0, 3, 6, 8, 10]
     assert sharded.shard_bounds(3, 8)[-1] == 3 and sharded.shard_bounds(0, 2) == [0, 0, 0]
+
+
+def test_interleaved_codebook_is_the_same_model():
+    """sharded.interleave_codebook deals the rows cyclically over the shards (training appends codewords class by class,
+    so contiguous shards of the untouched table hold a few classes each): the permuted table must be the same model —
+    same distances, rows mapped through the permutation, same votes, same labels — and every contiguous shard of it
+    must see every class."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
+    from oracle import oracle_py as orc
+    from pcdb200 import sharded, synth
+    prm = synth.workload_params("c2", knn_k=2)
+    tr_cls = [0, 0, 1, 1, 2, 2]
+    xyz, nrm, rgb, off = synth.make_clouds(tr_cls, [300 + i for i in range(6)], 900)
+    fx, fl, fd, foff = orc.compute_features(prm, xyz, nrm, rgb, off)
+    bb = np.stack([orc.aabb(xyz[off[i]:off[i + 1]]) for i in range(6)])
+    cb = orc.train(prm, fx, fl, fd, foff, tr_cls, list(range(6)), bb, 3)
+    world = 3
+    cbi, perm = sharded.interleave_codebook(cb, world)
+    assert cbi.N == cb.N and sorted(perm.tolist()) == list(range(cb.N))
+    assert np.array_equal(cbi.words, cb.words[perm]) and np.array_equal(cbi.kp_train, cb.kp_train[perm])
+    for i in (0, 1, cb.N // 2, cb.N - 1):  # the vote block of a row travels with it
+        a0, a1 = int(cbi.vote_off[i]), int(cbi.vote_off[i + 1])
+        b0, b1 = int(cb.vote_off[perm[i]]), int(cb.vote_off[perm[i] + 1])
+        assert a1 - a0 == b1 - b0 and np.array_equal(cbi.vote_xyz[a0:a1], cb.vote_xyz[b0:b1]) \
+            and np.array_equal(cbi.vote_class[a0:a1], cb.vote_class[b0:b1])
+    # contiguous shards of the dealt table see every class; those of the original table do not
+    b = sharded.shard_bounds(cb.N, world)
+    row_class = np.array([cb.vote_class[cb.vote_off[r]] for r in range(cb.N)])
+    for r in range(world):
+        assert len(set(row_class[perm][b[r]:b[r + 1]].tolist())) == 3
+    assert any(len(set(row_class[b[r]:b[r + 1]].tolist())) < 3 for r in range(world))
+    xt, nt, rt, ot = synth.make_clouds([0, 1, 2], [700, 701, 702], 900)
+    m0, m1 = orc.Model(prm, cb), orc.Model(prm, cbi)
+    tx, tl, td, toff = orc.compute_features(prm, xt, nt, rt, ot)
+    i0, d0, c0 = m0.knn(td, k=2)
+    i1, d1, c1 = m1.knn(td, k=2)
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32)) and np.array_equal(c0, c1)
+    untied = d0[:, 0] != d0[:, 1]
+    assert untied.mean() > 0.9 and np.array_equal(perm[i1[untied]], i0[untied])
+    l0, _, _ = m0.classify_batch(xt, nt, rt, ot, want_maxima=False)
+    l1, _, _ = m1.classify_batch(xt, nt, rt, ot, want_maxima=False)
+    assert np.array_equal(l0, l1) and l0.tolist() == [0, 1, 2]
