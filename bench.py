@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def build_world(name, n_words_override, ctx, rank_log=True, dist=""):
+def build_world(name, n_words_override, ctx, rank_log=True, dist="", upload=True):
     """Synthetic training set -> GPU features -> GPU-activated codebook (untimed set-up).  `dist` overrides the
     workload's DistanceType BEFORE training: the per-class sigma^2 of the vote filter is learned from training-time
     distances, so a codebook trained under one functor casts no votes under the other."""
@@ -128,7 +128,8 @@ def build_world(name, n_words_override, ctx, rank_log=True, dist=""):
     fx, fl, fd = np.concatenate(fx), np.concatenate(fl), np.concatenate(fd)
     t1 = time.time()
     cb = train.train_codebook(ctx, prm, fx, fl, fd, foff, tr_cls, list(range(len(tr_cls))), np.stack(bbs), n_cls)
-    ctx.set_codebook(cb)
+    if upload:
+        ctx.set_codebook(cb)
     if rank_log:
         log("codebook: %d training clouds, %d features -> N=%d words (D=%d); features %.1fs, activation+bookkeeping %.1fs"
             % (len(tr_cls), fd.shape[0], cb.N, cb.D, t1 - t0, time.time() - t1))
@@ -284,7 +285,7 @@ def sharded_legs(args, rank, world, local_rank, stream, dist, torch, api):
     try:
         ctx = api.Context(device=local_rank)
         ctx.set_stream(stream.cuda_stream)
-        wl, prm, cb = build_world("c4", args.words, ctx, rank_log=(rank == 0))
+        wl, prm, cb = build_world("c4", args.words, ctx, rank_log=(rank == 0), upload=False)
         # rows dealt cyclically over the shards (sharded.interleave_codebook: training appends the codewords class by
         # class; a contiguous shard would hold a few classes and overflow the pre-filter's pools for all the others);
         # the replicated arm below runs on the very same table
