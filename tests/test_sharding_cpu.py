@@ -219,3 +219,35 @@ def test_interleaved_codebook_is_the_same_model():
     l0, _, _ = m0.classify_batch(xt, nt, rt, ot, want_maxima=False)
     l1, _, _ = m1.classify_batch(xt, nt, rt, ot, want_maxima=False)
     assert np.array_equal(l0, l1) and l0.tolist() == [0, 1, 2]
+
+
+def test_interleave_codebook_csr_with_empty_rows_and_optional_arrays():
+    """Rows without votes, a world that does not divide N, absent optional arrays: every row keeps its own vote block."""
+    sys.path.insert(0, os.path.join(ROOT, "point-cloud-donkey_b200"))
+    from pcdb200 import sharded
+    from pcdb200.structs import Codebook
+    rng = np.random.default_rng(5)
+    for n_rows, world, with_opt in ((53, 4, True), (7, 8, False), (64, 2, True), (1, 3, False)):
+        cnt = rng.integers(0, 4, n_rows)
+        off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        V = int(off[-1])
+        tag = np.repeat(np.arange(n_rows), cnt)                     # every vote remembers its row
+        cb = Codebook(rng.random((n_rows, 16), np.float32), off, np.stack([tag, tag, tag], 1), tag + 0.5, tag % 3,
+                      tag, np.tile(np.arange(7, dtype=np.float32), (V, 1)) + tag[:, None],
+                      (tag + 0.25) if with_opt else None, rng.random((n_rows, 3), np.float32),
+                      np.arange(n_rows) if with_opt else None, np.ones(3), (np.arange(n_rows) + 2.0) if with_opt else None)
+        out, perm = sharded.interleave_codebook(cb, world)
+        assert sorted(perm.tolist()) == list(range(n_rows)) and out.N == n_rows
+        assert np.array_equal(perm % world, np.sort(perm % world))  # grouped by residue = contiguous shards of a deal
+        assert int(out.vote_off[-1]) == V and np.array_equal(np.diff(out.vote_off), cnt[perm])
+        for i in range(n_rows):
+            a0, a1 = int(out.vote_off[i]), int(out.vote_off[i + 1])
+            assert (out.vote_instance[a0:a1] == perm[i]).all() and (out.vote_xyz[a0:a1, 0] == perm[i]).all()
+            assert np.allclose(out.vote_weight[a0:a1], perm[i] + 0.5) and (out.vote_bbox[a0:a1, 0] == perm[i]).all()
+            if with_opt:
+                assert np.allclose(out.vote_class_weight[a0:a1], perm[i] + 0.25)
+        assert np.array_equal(out.words, cb.words[perm])
+        if with_opt:
+            assert np.array_equal(out.codeword_ids, perm) and np.allclose(out.codeword_weight, perm + 2.0)
+        else:
+            assert out.vote_class_weight is None or len(out.vote_class_weight) == 0
