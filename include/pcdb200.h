@@ -293,7 +293,10 @@ int pcdb_comm_info(pcdb_ctx* ctx, int32_t* rank_out, int32_t* n_ranks_out, int32
  * (`words` points at row row_lo) and the COMPLETE vote tables (all arrays as in pcdb_set_codebook, indexed by global
  * row).  Afterwards pcdb_knn and pcdb_classify_batch(_d) take THIS RANK's queries / clouds and return their results as
  * an unsharded codebook would, bit for bit: query all-gather, local tcgen05 search, one all-to-all of
- * (f32 distance, i32 row) x K per query, device-side merge (ties -> lower row), votes cast by the query's owner. */
+ * (f32 distance, i32 row) x K per query, device-side merge (ties -> lower row), votes cast by the query's owner.
+ * Speed, not results, depends on WHICH rows a shard holds: training appends codewords class by class
+ * (implicit_shape_model.cpp:447-475), so deal the rows of the table over the shards before sharding it (INTEGRATION.md D;
+ * pcdb200.sharded.interleave_codebook) — a shard without near words for most queries cannot use the pre-filter. */
 int pcdb_set_codebook_sharded(pcdb_ctx* ctx, const float* words, int64_t row_lo, int64_t row_hi, int64_t N_total,
                               int32_t D, const int64_t* vote_off, const float* vote_xyz, const float* vote_weight,
                               const uint32_t* vote_class, const uint32_t* vote_instance, const float* vote_bbox,
